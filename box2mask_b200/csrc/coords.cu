@@ -1,0 +1,301 @@
+// Coordinate hash, strided coordinate maps and kernel-map builders.
+//
+// Replaces the coordinate manager of MinkowskiEngine 0.5.4 as reached from
+// /root/reference/models/model.py:43 (ME.SparseTensor), models/detection_net.py:42-133 (stride-2 and
+// transposed convolutions) and models/resnet.py:61-65 (3x3x3 convolutions).
+// All of this is integer work bounded by HBM/L2 latency: one thread per (row, offset) probe,
+// coalesced int4 coordinate reads, coalesced int32 table writes.
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+namespace b2m {
+
+__device__ __forceinline__ int floor_to_multiple(int v, int s) {
+  int q = (v >= 0) ? (v / s) : -((-v + s - 1) / s);
+  return q * s;
+}
+
+__global__ void hash_insert_kernel(const int4* __restrict__ coords, int64_t n, unsigned long long* keys,
+                                   int32_t* vals, uint64_t mask, int32_t* status) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = __ldg(coords + i);
+  if (!coord_in_range(c.x, c.y, c.z, c.w)) { atomicAdd(status + 1, 1); return; }
+  const unsigned long long key = pack_key(c.x, c.y, c.z, c.w);
+  uint64_t slot = hash64(key) & mask;
+  while (true) {
+    const unsigned long long prev = atomicCAS(keys + slot, (unsigned long long)B2M_KEY_EMPTY, key);
+    if (prev == B2M_KEY_EMPTY || prev == key) {
+      atomicMin(vals + slot, (int32_t)i);
+      if (prev == key) atomicAdd(status, 1);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ int32_t hash_lookup(const unsigned long long* __restrict__ keys,
+                                               const int32_t* __restrict__ vals, uint64_t mask,
+                                               unsigned long long key) {
+  uint64_t slot = hash64(key) & mask;
+  while (true) {
+    const unsigned long long kk = __ldg(keys + slot);
+    if (kk == key) return __ldg(vals + slot);
+    if (kk == B2M_KEY_EMPTY) return -1;
+    slot = (slot + 1) & mask;
+  }
+}
+
+__global__ void hash_query_kernel(const int4* __restrict__ q, int64_t m, const unsigned long long* __restrict__ keys,
+                                  const int32_t* __restrict__ vals, uint64_t mask, int32_t* __restrict__ rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int4 c = __ldg(q + i);
+  int32_t r = -1;
+  if (coord_in_range(c.x, c.y, c.z, c.w)) r = hash_lookup(keys, vals, mask, pack_key(c.x, c.y, c.z, c.w));
+  rows[i] = r;
+}
+
+// nbr[k][row] for an odd kernel, offsets (ix - K/2, iy - K/2, iz - K/2) * tensor_stride, x fastest.
+__global__ void kmap_submanifold_kernel(const int4* __restrict__ coords, int64_t n, int ts, int ksize,
+                                        const unsigned long long* __restrict__ keys,
+                                        const int32_t* __restrict__ vals, uint64_t mask,
+                                        int32_t* __restrict__ nbr) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int kvol = ksize * ksize * ksize;
+  if (gid >= n * kvol) return;
+  const int64_t row = gid % n;
+  const int k = (int)(gid / n);
+  const int h = ksize / 2;
+  const int dx = (k % ksize - h) * ts;
+  const int dy = ((k / ksize) % ksize - h) * ts;
+  const int dz = (k / (ksize * ksize) - h) * ts;
+  int32_t r;
+  if (dx == 0 && dy == 0 && dz == 0) {
+    r = (int32_t)row;  // the centre offset always maps a row to itself (coordinates are unique)
+  } else {
+    const int4 c = __ldg(coords + row);
+    const int x = c.y + dx, y = c.z + dy, z = c.w + dz;
+    r = -1;
+    if (coord_in_range(c.x, x, y, z)) r = hash_lookup(keys, vals, mask, pack_key(c.x, x, y, z));
+  }
+  nbr[gid] = r;
+}
+
+__global__ void downsample_keys_kernel(const int4* __restrict__ coords, int64_t n, int stride,
+                                       unsigned long long* __restrict__ keys, int32_t* __restrict__ idx,
+                                       int32_t* status) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = __ldg(coords + i);
+  const int x = floor_to_multiple(c.y, stride), y = floor_to_multiple(c.z, stride), z = floor_to_multiple(c.w, stride);
+  if (!coord_in_range(c.x, x, y, z)) atomicAdd(status, 1);
+  keys[i] = pack_key(c.x, x, y, z);
+  idx[i] = (int32_t)i;
+}
+
+__global__ void head_flags_kernel(const unsigned long long* __restrict__ sorted_keys, int64_t n, int32_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flags[i] = (i == 0 || sorted_keys[i] != sorted_keys[i - 1]) ? 1 : 0;
+}
+
+__global__ void downsample_emit_kernel(const unsigned long long* __restrict__ sorted_keys,
+                                       const int32_t* __restrict__ sorted_idx, const int32_t* __restrict__ rank_incl,
+                                       int64_t n, int4* __restrict__ out_coords, int32_t* __restrict__ parent_row,
+                                       int32_t* __restrict__ n_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t row = rank_incl[i] - 1;
+  parent_row[sorted_idx[i]] = row;
+  if (i == 0 || sorted_keys[i] != sorted_keys[i - 1]) {
+    int b, x, y, z;
+    unpack_key(sorted_keys[i], b, x, y, z);
+    out_coords[row] = make_int4(b, x, y, z);
+  }
+  if (i == n - 1) *n_out = row + 1;
+}
+
+__global__ void kmap_stride2_kernel(const int4* __restrict__ fine, int64_t n_fine, const int32_t* __restrict__ parent,
+                                    int64_t n_coarse, int fs, int32_t* __restrict__ nbr_down,
+                                    int32_t* __restrict__ nbr_up) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_fine) return;
+  const int4 c = __ldg(fine + f);
+  const int cs = 2 * fs;
+  const int ox = (c.y - floor_to_multiple(c.y, cs)) / fs;
+  const int oy = (c.z - floor_to_multiple(c.z, cs)) / fs;
+  const int oz = (c.w - floor_to_multiple(c.w, cs)) / fs;
+  const int k = ox + 2 * oy + 4 * oz;
+  const int32_t p = parent[f];
+  if (nbr_down) nbr_down[(int64_t)k * n_coarse + p] = (int32_t)f;
+  if (nbr_up) {
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) nbr_up[(int64_t)kk * n_fine + f] = (kk == k) ? p : -1;
+  }
+}
+
+__global__ void kmap_count_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int32_t* __restrict__ counts) {
+  const int k = blockIdx.y;
+  int local = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (int64_t)gridDim.x * blockDim.x)
+    local += nbr[(int64_t)k * n_out + i] >= 0;
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(counts + k, local);
+}
+
+struct DownsampleWs {
+  size_t off_keys_in, off_keys_out, off_idx_in, off_idx_out, off_flags, off_rank, off_status, off_cub, cub_bytes, total;
+};
+static DownsampleWs downsample_ws(int64_t n) {
+  DownsampleWs w;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  size_t off = 0;
+  w.off_keys_in = off;  off += al(8 * (size_t)n);
+  w.off_keys_out = off; off += al(8 * (size_t)n);
+  w.off_idx_in = off;   off += al(4 * (size_t)n);
+  w.off_idx_out = off;  off += al(4 * (size_t)n);
+  w.off_flags = off;    off += al(4 * (size_t)n);
+  w.off_rank = off;     off += al(4 * (size_t)n);
+  w.off_status = off;   off += 256;
+  size_t sort_bytes = 0, scan_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+  cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+  w.cub_bytes = al(sort_bytes > scan_bytes ? sort_bytes : scan_bytes);
+  w.off_cub = off;      off += w.cub_bytes;
+  w.total = off;
+  return w;
+}
+
+}  // namespace b2m
+
+using namespace b2m;
+
+extern "C" int64_t b2m_hash_capacity(int64_t n) {
+  int64_t cap = 1024;
+  while (cap < 2 * n) cap <<= 1;
+  return cap;
+}
+
+extern "C" int b2m_hash_build(const int32_t* coords, int64_t n, uint64_t* table_keys, int32_t* table_vals,
+                              int64_t capacity, int32_t* status, b2m_stream_t stream) {
+  if (!coords || !table_keys || !table_vals || !status || n < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (capacity < 2 * n || (capacity & (capacity - 1)) != 0) return B2M_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(table_keys, 0xFF, (size_t)capacity * 8, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  if (cudaMemsetAsync(table_vals, 0x7F, (size_t)capacity * 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  if (cudaMemsetAsync(status, 0, 8, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  if (n == 0) return B2M_OK;
+  hash_insert_kernel<<<cdiv(n, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n,
+                                                  reinterpret_cast<unsigned long long*>(table_keys), table_vals,
+                                                  (uint64_t)(capacity - 1), status);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" int b2m_hash_query(const int32_t* query_coords, int64_t m, const uint64_t* table_keys,
+                              const int32_t* table_vals, int64_t capacity, int32_t* rows, b2m_stream_t stream) {
+  if (!query_coords || !table_keys || !table_vals || !rows || m < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (m == 0) return B2M_OK;
+  hash_query_kernel<<<cdiv(m, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const int4*>(query_coords), m, reinterpret_cast<const unsigned long long*>(table_keys),
+      table_vals, (uint64_t)(capacity - 1), rows);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" size_t b2m_downsample_workspace_bytes(int64_t n) { return downsample_ws(n < 1 ? 1 : n).total; }
+
+extern "C" int b2m_downsample_coords(const int32_t* coords, int64_t n, int32_t new_stride, int32_t* out_coords,
+                                     int32_t* parent_row, int32_t* n_out, void* workspace, size_t workspace_bytes,
+                                     b2m_stream_t stream) {
+  if (!coords || !out_coords || !parent_row || !n_out || !workspace || n < 0 || new_stride <= 0)
+    return B2M_ERR_INVALID_ARGUMENT;
+  if (n >= (int64_t)1 << 31) return B2M_ERR_UNSUPPORTED_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    if (cudaMemsetAsync(n_out, 0, 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+    return B2M_OK;
+  }
+  const DownsampleWs w = downsample_ws(n);
+  if (workspace_bytes < w.total) return B2M_ERR_WORKSPACE_TOO_SMALL;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  auto* keys_in = reinterpret_cast<unsigned long long*>(ws + w.off_keys_in);
+  auto* keys_out = reinterpret_cast<unsigned long long*>(ws + w.off_keys_out);
+  auto* idx_in = reinterpret_cast<int32_t*>(ws + w.off_idx_in);
+  auto* idx_out = reinterpret_cast<int32_t*>(ws + w.off_idx_out);
+  auto* flags = reinterpret_cast<int32_t*>(ws + w.off_flags);
+  auto* rank = reinterpret_cast<int32_t*>(ws + w.off_rank);
+  auto* status = reinterpret_cast<int32_t*>(ws + w.off_status);
+  if (cudaMemsetAsync(status, 0, 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  const int blocks = cdiv(n, 256);
+  downsample_keys_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, new_stride, keys_in, idx_in, status);
+  B2M_CHECK_LAUNCH();
+  size_t cub_bytes = w.cub_bytes;
+  if (cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, keys_in, keys_out, idx_in, idx_out, (int)n, 0, 64, st) != cudaSuccess)
+    return B2M_ERR_CUDA_LAUNCH;
+  head_flags_kernel<<<blocks, 256, 0, st>>>(keys_out, n, flags);
+  B2M_CHECK_LAUNCH();
+  cub_bytes = w.cub_bytes;
+  if (cub::DeviceScan::InclusiveSum(ws + w.off_cub, cub_bytes, flags, rank, (int)n, st) != cudaSuccess)
+    return B2M_ERR_CUDA_LAUNCH;
+  downsample_emit_kernel<<<blocks, 256, 0, st>>>(keys_out, idx_out, rank, n, reinterpret_cast<int4*>(out_coords), parent_row, n_out);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" int b2m_kernel_map_submanifold(const int32_t* coords, int64_t n, int32_t tensor_stride, int32_t kernel_size,
+                                          const uint64_t* table_keys, const int32_t* table_vals, int64_t capacity,
+                                          int32_t* nbr, b2m_stream_t stream) {
+  if (!coords || !table_keys || !table_vals || !nbr || n < 0 || tensor_stride <= 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (kernel_size != 1 && kernel_size != 3 && kernel_size != 5) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (n == 0) return B2M_OK;
+  const int64_t total = n * kernel_size * kernel_size * kernel_size;
+  kmap_submanifold_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const int4*>(coords), n, tensor_stride, kernel_size,
+      reinterpret_cast<const unsigned long long*>(table_keys), table_vals, (uint64_t)(capacity - 1), nbr);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" int b2m_kernel_map_stride2(const int32_t* fine_coords, int64_t n_fine, const int32_t* parent_row,
+                                      int64_t n_coarse, int32_t fine_stride, int32_t* nbr_down, int32_t* nbr_up,
+                                      b2m_stream_t stream) {
+  if (!fine_coords || !parent_row || n_fine < 0 || n_coarse < 0 || fine_stride <= 0) return B2M_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nbr_down && n_coarse > 0)
+    if (cudaMemsetAsync(nbr_down, 0xFF, (size_t)8 * n_coarse * 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  if (n_fine == 0) return B2M_OK;
+  kmap_stride2_kernel<<<cdiv(n_fine, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(fine_coords), n_fine, parent_row,
+                                                        n_coarse, fine_stride, nbr_down, nbr_up);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" int b2m_kernel_map_count(const int32_t* nbr, int32_t kvol, int64_t n_out, int32_t* counts, b2m_stream_t stream) {
+  if (!nbr || !counts || kvol <= 0 || n_out < 0) return B2M_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(counts, 0, (size_t)kvol * 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  if (n_out == 0) return B2M_OK;
+  int bx = cdiv(n_out, 256 * 8);
+  if (bx > 1024) bx = 1024;
+  kmap_count_kernel<<<dim3(bx, kvol), 256, 0, st>>>(nbr, n_out, counts);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" int b2m_version(void) { return 1; }
+
+extern "C" const char* b2m_error_string(int code) {
+  switch (code) {
+    case B2M_OK: return "ok";
+    case B2M_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case B2M_ERR_CUDA_LAUNCH: return "CUDA launch or runtime error";
+    case B2M_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case B2M_ERR_UNSUPPORTED_SHAPE: return "unsupported shape";
+    case B2M_ERR_COORD_RANGE: return "coordinate outside the packable range";
+    default: return "unknown error";
+  }
+}

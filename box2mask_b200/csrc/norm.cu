@@ -1,0 +1,284 @@
+// BatchNorm over sparse-tensor rows (+ residual, + ReLU), column statistics, dtype conversion.
+//
+// Replaces MinkowskiBatchNorm (-> torch.nn.BatchNorm1d, /root/reference/models/resnet.py:63,66,159 and
+// models/detection_net.py:40..187), MinkowskiReLU and `out += residual` (models/resnet.py:67,80-81).
+// HBM-bound passes: 16-byte (8 x bf16) vector loads/stores, one read + one write per element, column
+// statistics reduced in fp32 per thread, fp32 in shared memory per block, fp64 atomics across blocks.
+#include "common.cuh"
+
+namespace b2m {
+
+constexpr int kNormThreads = 256;
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 float_to_bf16x8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+__global__ void cast_pad_kernel(const float* __restrict__ x, int64_t n, int c, int c_pad, uint16_t* __restrict__ out) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n * c_pad) return;
+  const int64_t r = gid / c_pad;
+  const int j = (int)(gid % c_pad);
+  const float v = (j < c) ? x[r * c + j] : 0.f;
+  reinterpret_cast<__nv_bfloat16*>(out)[gid] = __float2bfloat16_rn(v);
+}
+
+// Generic two-quantity column reduction over rows [n, c] of 8-wide vectors.
+// MODE 0: (sum x, sum x^2).  MODE 1: (sum g, sum g*xhat) with g = dout * (out > 0 if relu).
+template <int MODE>
+__global__ void __launch_bounds__(kNormThreads)
+colreduce_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ out, const uint16_t* __restrict__ dout,
+                 int64_t n, int c, const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                 double* __restrict__ red) {
+  extern __shared__ float sh[];  // [rows_per_pass][c][2]
+  const int G = c / 8;
+  const int rpp = kNormThreads / G;  // rows per pass
+  const int g = threadIdx.x % G;
+  const int rl = threadIdx.x / G;
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; }
+  float mu[8], is[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i]; }
+  }
+  if (rl < rpp) {
+    for (int64_t r = (int64_t)blockIdx.x * rpp + rl; r < n; r += (int64_t)gridDim.x * rpp) {
+      float xv[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + r * c) + g), xv);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] += xv[i]; b[i] = fmaf(xv[i], xv[i], b[i]); }
+      } else {
+        float gv[8];
+        bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(dout + r * c) + g), gv);
+        if (relu) {
+          float ov[8];
+          bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(out + r * c) + g), ov);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) if (!(ov[i] > 0.f)) gv[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] += gv[i]; b[i] = fmaf(gv[i], (xv[i] - mu[i]) * is[i], b[i]); }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sh[(rl * c + g * 8 + i) * 2] = a[i];
+      sh[(rl * c + g * 8 + i) * 2 + 1] = b[i];
+    }
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < c; col += kNormThreads) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < rpp; ++r) { s1 += sh[(r * c + col) * 2]; s2 += sh[(r * c + col) * 2 + 1]; }
+    atomicAdd(red + col, (double)s1);
+    atomicAdd(red + c + col, (double)s2);
+  }
+}
+
+// One block per launch computes the per-channel affine (scale, shift), the saved statistics and the
+// running-statistics update; written to a small float workspace that the apply kernel reads.
+__global__ void bn_prepare_kernel(const double* __restrict__ sums, int64_t n, int c, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float* running_mean, float* running_var,
+                                  float momentum, float eps, int training, float* __restrict__ save_mean,
+                                  float* __restrict__ save_invstd) {
+  for (int j = threadIdx.x; j < c; j += blockDim.x) {
+    float mean, invstd;
+    if (training) {
+      const double m = sums[j] / (double)n;
+      double var = sums[c + j] / (double)n - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      invstd = (float)(1.0 / sqrt(var + (double)eps));
+      if (running_mean) running_mean[j] = (1.f - momentum) * running_mean[j] + momentum * mean;
+      if (running_var) {
+        const double unbiased = (n > 1) ? var * (double)n / (double)(n - 1) : var;
+        running_var[j] = (1.f - momentum) * running_var[j] + momentum * (float)unbiased;
+      }
+    } else {
+      mean = running_mean[j];
+      invstd = (float)(1.0 / sqrt((double)running_var[j] + (double)eps));
+    }
+    save_mean[j] = mean;
+    save_invstd[j] = invstd;
+  }
+  (void)gamma; (void)beta;
+}
+
+__global__ void __launch_bounds__(kNormThreads)
+bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int c, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
+                const uint16_t* __restrict__ residual, int relu, uint16_t* __restrict__ out) {
+  const int G = c / 8;
+  const int64_t total = n * G;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(v % G);
+    float xv[8], o[8];
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x) + v), xv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = g * 8 + i;
+      const float sc = __ldg(gamma + j) * __ldg(invstd + j);
+      o[i] = fmaf(xv[i] - __ldg(mean + j), sc, __ldg(beta + j));
+    }
+    if (residual) {
+      float rv[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(residual) + v), rv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += rv[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+    }
+    reinterpret_cast<uint4*>(out)[v] = float_to_bf16x8(o);
+  }
+}
+
+__global__ void __launch_bounds__(kNormThreads)
+bn_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ out, const uint16_t* __restrict__ dout,
+                    int64_t n, int c, const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ gamma, const double* __restrict__ red, int relu, int training,
+                    uint16_t* __restrict__ dx, uint16_t* __restrict__ dres, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta) {
+  const int G = c / 8;
+  const int64_t total = n * G;
+  if (blockIdx.x == 0) {
+    for (int j = threadIdx.x; j < c; j += blockDim.x) {
+      if (dbeta) dbeta[j] = (float)red[j];
+      if (dgamma) dgamma[j] = (float)red[c + j];
+    }
+  }
+  const float inv_n = 1.f / (float)n;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(v % G);
+    float xv[8], gv[8], o[8];
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x) + v), xv);
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(dout) + v), gv);
+    if (relu) {
+      float ov[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(out) + v), ov);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (!(ov[i] > 0.f)) gv[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = g * 8 + i;
+      const float is = __ldg(invstd + j);
+      const float sc = __ldg(gamma + j) * is;
+      if (training) {
+        const float xh = (xv[i] - __ldg(mean + j)) * is;
+        const float sg = (float)red[j] * inv_n;
+        const float sgx = (float)red[c + j] * inv_n;
+        o[i] = sc * (gv[i] - sg - xh * sgx);
+      } else {
+        o[i] = sc * gv[i];
+      }
+    }
+    reinterpret_cast<uint4*>(dx)[v] = float_to_bf16x8(o);
+    if (dres) reinterpret_cast<uint4*>(dres)[v] = float_to_bf16x8(gv);
+  }
+}
+
+static int reduce_grid(int64_t n, int c) {
+  const int rpp = kNormThreads / (c / 8);
+  int64_t blocks = (n + rpp * 16 - 1) / (rpp * 16);  // >= 16 rows per thread lane
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+static int apply_grid(int64_t total_vec) {
+  int64_t blocks = (total_vec + kNormThreads - 1) / kNormThreads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace b2m
+
+using namespace b2m;
+
+extern "C" int b2m_cast_pad_bf16(const float* x, int64_t n, int32_t c, int32_t c_pad, uint16_t* out, b2m_stream_t stream) {
+  if (!x || !out || n < 0 || c <= 0 || c_pad < c) return B2M_ERR_INVALID_ARGUMENT;
+  if (n == 0) return B2M_OK;
+  cast_pad_kernel<<<cdiv(n * c_pad, 256), 256, 0, (cudaStream_t)stream>>>(x, n, c, c_pad, out);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+static bool norm_shape_ok(int c) { return c > 0 && c % 8 == 0 && c <= 2048 && (c / 8) <= kNormThreads; }
+
+extern "C" int b2m_colstats(const uint16_t* x, int64_t n, int32_t c, double* sums, b2m_stream_t stream) {
+  if (!x || !sums || n < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (!norm_shape_ok(c)) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (n == 0) return B2M_OK;
+  const int rpp = kNormThreads / (c / 8);
+  const size_t sh = (size_t)rpp * c * 2 * sizeof(float);
+  colreduce_kernel<0><<<reduce_grid(n, c), kNormThreads, sh, (cudaStream_t)stream>>>(x, nullptr, nullptr, n, c, nullptr,
+                                                                                    nullptr, 0, sums);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" int b2m_bn_forward(const uint16_t* x, int64_t n, int32_t c, const double* sums, const float* gamma,
+                              const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                              int32_t training, const uint16_t* residual, int32_t relu, uint16_t* out, float* save_mean,
+                              float* save_invstd, b2m_stream_t stream) {
+  if (!x || !gamma || !beta || !out || !save_mean || !save_invstd || n < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (training && !sums) return B2M_ERR_INVALID_ARGUMENT;
+  if (!training && (!running_mean || !running_var)) return B2M_ERR_INVALID_ARGUMENT;
+  if (!norm_shape_ok(c)) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (n == 0) return B2M_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_prepare_kernel<<<1, 256, 0, st>>>(sums, n, c, gamma, beta, running_mean, running_var, momentum, eps, training,
+                                      save_mean, save_invstd);
+  B2M_CHECK_LAUNCH();
+  bn_apply_kernel<<<apply_grid(n * (c / 8)), kNormThreads, 0, st>>>(x, n, c, gamma, beta, save_mean, save_invstd,
+                                                                   residual, relu, out);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" int b2m_bn_backward_reduce(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n, int32_t c,
+                                      const float* save_mean, const float* save_invstd, int32_t relu, double* red,
+                                      b2m_stream_t stream) {
+  if (!x || !dout || !save_mean || !save_invstd || !red || n < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (relu && !out) return B2M_ERR_INVALID_ARGUMENT;
+  if (!norm_shape_ok(c)) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (n == 0) return B2M_OK;
+  const int rpp = kNormThreads / (c / 8);
+  const size_t sh = (size_t)rpp * c * 2 * sizeof(float);
+  colreduce_kernel<1><<<reduce_grid(n, c), kNormThreads, sh, (cudaStream_t)stream>>>(x, out, dout, n, c, save_mean,
+                                                                                    save_invstd, relu, red);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" int b2m_bn_backward_apply(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n, int32_t c,
+                                     const float* save_mean, const float* save_invstd, const float* gamma,
+                                     const double* red, int32_t relu, int32_t training, uint16_t* dx,
+                                     uint16_t* dresidual, float* dgamma, float* dbeta, b2m_stream_t stream) {
+  if (!x || !dout || !save_mean || !save_invstd || !gamma || !red || !dx || n < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (relu && !out) return B2M_ERR_INVALID_ARGUMENT;
+  if (!norm_shape_ok(c)) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (n == 0) return B2M_OK;
+  bn_bwd_apply_kernel<<<apply_grid(n * (c / 8)), kNormThreads, 0, (cudaStream_t)stream>>>(
+      x, out, dout, n, c, save_mean, save_invstd, gamma, red, relu, training, dx, dresidual, dgamma, dbeta);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}

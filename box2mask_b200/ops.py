@@ -1,0 +1,286 @@
+"""Thin functional wrappers over the C-ABI (include/b2m.h). torch is used only for device memory and
+streams; every computation below happens in libb2m.so. All tensors must live on a CUDA device."""
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def _lib_or_raise():
+    return _lib.load()
+
+
+def _cuda(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise _lib.B2MError("%s must be a CUDA tensor (no CPU fallback in the product path)" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.B2MError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise _lib.B2MError("%s must be contiguous" % name)
+    return t
+
+
+def as_u16(t):
+    """bf16 tensor viewed as the uint16 bit patterns the C-ABI carries (no copy)."""
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# coordinates
+# ---------------------------------------------------------------------------------------------
+class HashTable:
+    __slots__ = ("keys", "vals", "capacity", "status")
+
+    def __init__(self, keys, vals, capacity, status):
+        self.keys, self.vals, self.capacity, self.status = keys, vals, capacity, status
+
+
+def hash_build(coords):
+    lib = _lib_or_raise()
+    _cuda(coords, torch.int32, "coords")
+    n = coords.shape[0]
+    cap = lib.b2m_hash_capacity(n)
+    keys = torch.empty(cap, dtype=torch.int64, device=coords.device)
+    vals = torch.empty(cap, dtype=torch.int32, device=coords.device)
+    status = torch.empty(2, dtype=torch.int32, device=coords.device)
+    check(lib.b2m_hash_build(ptr(coords), n, ptr(keys), ptr(vals), cap, ptr(status), stream_ptr()), "hash_build")
+    return HashTable(keys, vals, cap, status)
+
+
+def hash_query(table, query):
+    lib = _lib_or_raise()
+    _cuda(query, torch.int32, "query")
+    rows = torch.empty(query.shape[0], dtype=torch.int32, device=query.device)
+    check(lib.b2m_hash_query(ptr(query), query.shape[0], ptr(table.keys), ptr(table.vals), table.capacity, ptr(rows),
+                             stream_ptr()), "hash_query")
+    return rows
+
+
+def downsample_coords(coords, new_stride):
+    """-> (out_coords int32[M,4] sorted unique, parent_row int32[N]). One host sync to read M."""
+    lib = _lib_or_raise()
+    _cuda(coords, torch.int32, "coords")
+    n = coords.shape[0]
+    out = torch.empty((n, 4), dtype=torch.int32, device=coords.device)
+    parent = torch.empty(n, dtype=torch.int32, device=coords.device)
+    n_out = torch.zeros(1, dtype=torch.int32, device=coords.device)
+    ws_bytes = lib.b2m_downsample_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=coords.device)
+    check(lib.b2m_downsample_coords(ptr(coords), n, int(new_stride), ptr(out), ptr(parent), ptr(n_out), ptr(ws),
+                                    ws_bytes, stream_ptr()), "downsample_coords")
+    m = int(n_out.item())
+    return out[:m].contiguous(), parent
+
+
+def kernel_map_submanifold(coords, tensor_stride, kernel_size, table):
+    lib = _lib_or_raise()
+    n = coords.shape[0]
+    nbr = torch.empty((kernel_size ** 3, n), dtype=torch.int32, device=coords.device)
+    check(lib.b2m_kernel_map_submanifold(ptr(coords), n, int(tensor_stride), int(kernel_size), ptr(table.keys),
+                                         ptr(table.vals), table.capacity, ptr(nbr), stream_ptr()),
+          "kernel_map_submanifold")
+    return nbr
+
+
+def kernel_map_stride2(fine_coords, parent_row, n_coarse, fine_stride):
+    lib = _lib_or_raise()
+    n_fine = fine_coords.shape[0]
+    nbr_down = torch.empty((8, n_coarse), dtype=torch.int32, device=fine_coords.device)
+    nbr_up = torch.empty((8, n_fine), dtype=torch.int32, device=fine_coords.device)
+    check(lib.b2m_kernel_map_stride2(ptr(fine_coords), n_fine, ptr(parent_row), n_coarse, int(fine_stride),
+                                     ptr(nbr_down), ptr(nbr_up), stream_ptr()), "kernel_map_stride2")
+    return nbr_down, nbr_up
+
+
+def kernel_map_count(nbr):
+    lib = _lib_or_raise()
+    counts = torch.empty(nbr.shape[0], dtype=torch.int32, device=nbr.device)
+    check(lib.b2m_kernel_map_count(ptr(nbr), nbr.shape[0], nbr.shape[1], ptr(counts), stream_ptr()), "kernel_map_count")
+    return counts
+
+
+# ---------------------------------------------------------------------------------------------
+# convolution
+# ---------------------------------------------------------------------------------------------
+def cast_pad_bf16(x, c_pad):
+    lib = _lib_or_raise()
+    _cuda(x, torch.float32, "x")
+    out = torch.empty((x.shape[0], c_pad), dtype=torch.bfloat16, device=x.device)
+    check(lib.b2m_cast_pad_bf16(ptr(x), x.shape[0], x.shape[1], c_pad, ptr(out), stream_ptr()), "cast_pad_bf16")
+    return out
+
+
+def pack_weights(kernel, mode):
+    """kernel f32 [K, C_in, C_out] (or [C_in, C_out]) -> packed bf16 UMMA B image (uint8 buffer)."""
+    lib = _lib_or_raise()
+    _cuda(kernel, torch.float32, "kernel")
+    if kernel.dim() == 2:
+        kvol, (c_in, c_out) = 1, kernel.shape
+    else:
+        kvol, c_in, c_out = kernel.shape
+    nbytes = lib.b2m_packed_weight_bytes(kvol, c_in, c_out, mode)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=kernel.device)
+    check(lib.b2m_pack_weights(ptr(kernel), kvol, c_in, c_out, mode, ptr(packed), stream_ptr()), "pack_weights")
+    return packed
+
+
+def conv_forward(x, nbr, packed_w, kvol, n_out, c_n, colsum=None):
+    """y bf16[n_out, c_n] = sum_k x[nbr[k]] @ B[k]; colsum f64[2*c_n] (zeroed by the caller) optional."""
+    lib = _lib_or_raise()
+    _cuda(x, torch.bfloat16, "x")
+    y = torch.empty((n_out, c_n), dtype=torch.bfloat16, device=x.device)
+    check(lib.b2m_conv_forward(ptr(x), x.shape[0], x.shape[1], ptr(nbr), kvol, n_out, ptr(packed_w), c_n, ptr(y),
+                               ptr(colsum), stream_ptr()), "conv_forward")
+    return y
+
+
+def conv_wgrad(x, dy, nbr, kvol, n_out):
+    lib = _lib_or_raise()
+    _cuda(x, torch.bfloat16, "x")
+    _cuda(dy, torch.bfloat16, "dy")
+    c_in, c_out = x.shape[1], dy.shape[1]
+    dw = torch.zeros((kvol, c_in, c_out), dtype=torch.float32, device=x.device)
+    check(lib.b2m_conv_wgrad(ptr(x), x.shape[0], c_in, ptr(dy), c_out, ptr(nbr), kvol, n_out, ptr(dw), stream_ptr()),
+          "conv_wgrad")
+    return dw
+
+
+# ---------------------------------------------------------------------------------------------
+# batch norm
+# ---------------------------------------------------------------------------------------------
+def colstats(x):
+    lib = _lib_or_raise()
+    _cuda(x, torch.bfloat16, "x")
+    sums = torch.zeros(2 * x.shape[1], dtype=torch.float64, device=x.device)
+    check(lib.b2m_colstats(ptr(x), x.shape[0], x.shape[1], ptr(sums), stream_ptr()), "colstats")
+    return sums
+
+
+def bn_forward(x, sums, gamma, beta, running_mean, running_var, momentum, eps, training, residual=None, relu=False):
+    lib = _lib_or_raise()
+    _cuda(x, torch.bfloat16, "x")
+    n, c = x.shape
+    out = torch.empty_like(x)
+    save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
+    save_invstd = torch.empty(c, dtype=torch.float32, device=x.device)
+    check(lib.b2m_bn_forward(ptr(x), n, c, ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                             float(momentum), float(eps), int(bool(training)), ptr(residual), int(bool(relu)), ptr(out),
+                             ptr(save_mean), ptr(save_invstd), stream_ptr()), "bn_forward")
+    return out, save_mean, save_invstd
+
+
+def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, want_dresidual):
+    lib = _lib_or_raise()
+    n, c = x.shape
+    red = torch.zeros(2 * c, dtype=torch.float64, device=x.device)
+    check(lib.b2m_bn_backward_reduce(ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd),
+                                     int(bool(relu)), ptr(red), stream_ptr()), "bn_backward_reduce")
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dresidual else None
+    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    check(lib.b2m_bn_backward_apply(ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd), ptr(gamma),
+                                    ptr(red), int(bool(relu)), int(bool(training)), ptr(dx), ptr(dres), ptr(dgamma),
+                                    ptr(dbeta), stream_ptr()), "bn_backward_apply")
+    return dx, dres, dgamma, dbeta
+
+
+# ---------------------------------------------------------------------------------------------
+# pooling
+# ---------------------------------------------------------------------------------------------
+def segment_mean_forward(f, ids, s):
+    lib = _lib_or_raise()
+    _cuda(f, torch.bfloat16, "f")
+    _cuda(ids, torch.int64, "ids")
+    out = torch.empty((s, f.shape[1]), dtype=torch.float32, device=f.device)
+    counts = torch.empty(s, dtype=torch.float32, device=f.device)
+    check(lib.b2m_segment_mean_forward(ptr(f), ptr(ids), f.shape[0], f.shape[1], s, ptr(out), ptr(counts),
+                                       stream_ptr()), "segment_mean_forward")
+    return out, counts
+
+
+def segment_mean_backward(dout, ids, counts, n):
+    lib = _lib_or_raise()
+    _cuda(dout, torch.float32, "dout")
+    df = torch.empty((n, dout.shape[1]), dtype=torch.bfloat16, device=dout.device)
+    check(lib.b2m_segment_mean_backward(ptr(dout), ptr(ids), ptr(counts), n, dout.shape[1], ptr(df), stream_ptr()),
+          "segment_mean_backward")
+    return df
+
+
+def segment_max_forward(f, ids, s):
+    lib = _lib_or_raise()
+    _cuda(f, torch.bfloat16, "f")
+    out = torch.empty((s, f.shape[1]), dtype=torch.float32, device=f.device)
+    argmax = torch.empty((s, f.shape[1]), dtype=torch.int32, device=f.device)
+    check(lib.b2m_segment_max_forward(ptr(f), ptr(ids), f.shape[0], f.shape[1], s, ptr(out), ptr(argmax),
+                                      stream_ptr()), "segment_max_forward")
+    return out, argmax
+
+
+# ---------------------------------------------------------------------------------------------
+# decode
+# ---------------------------------------------------------------------------------------------
+def aabb_nms(boxes, cluster_th, max_clusters=None, want_heatmaps=True):
+    """-> (representatives i64[K], cluster_of i32[M], heatmaps f32[K,M] or None). One host sync (K)."""
+    lib = _lib_or_raise()
+    _cuda(boxes, torch.float32, "boxes")
+    m = boxes.shape[0]
+    dev = boxes.device
+    n_clusters = torch.zeros(1, dtype=torch.int32, device=dev)
+    reps = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+    cluster_of = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+    if max_clusters is None:
+        max_clusters = m
+    heat = torch.empty((max_clusters, m), dtype=torch.float32, device=dev) if want_heatmaps else None
+    ws_bytes = lib.b2m_nms_workspace_bytes(m)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.b2m_aabb_nms(ptr(boxes), m, float(cluster_th), ptr(n_clusters), ptr(reps), ptr(cluster_of), ptr(heat),
+                           max_clusters if want_heatmaps else 0, ptr(ws), ws_bytes, stream_ptr()), "aabb_nms")
+    k = int(n_clusters.item())
+    return reps[:k].long(), cluster_of[:m], (heat[:min(k, max_clusters)] if want_heatmaps else None)
+
+
+def heatmap_project(heat, fg_rank, seg2vox, mask_bin_th):
+    lib = _lib_or_raise()
+    _cuda(heat, torch.float32, "heat")
+    k, m_fg = heat.shape
+    n_vox = seg2vox.shape[0]
+    words = (n_vox + 31) // 32
+    masks = torch.empty((k, words), dtype=torch.int32, device=heat.device)
+    check(lib.b2m_heatmap_project(ptr(heat), k, m_fg, ptr(fg_rank), ptr(seg2vox), n_vox, float(mask_bin_th), ptr(masks),
+                                  stream_ptr()), "heatmap_project")
+    return masks
+
+
+def mask_nms(masks, th):
+    """bit-packed masks int32[k, words] in score order -> keep bool[k]."""
+    lib = _lib_or_raise()
+    k, words = masks.shape
+    keep = torch.empty(max(k, 1), dtype=torch.uint8, device=masks.device)
+    n_keep = torch.zeros(1, dtype=torch.int32, device=masks.device)
+    ws_bytes = lib.b2m_mask_nms_workspace_bytes(k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=masks.device)
+    check(lib.b2m_mask_nms(ptr(masks), k, words, float(th), ptr(keep), ptr(n_keep), ptr(ws), ws_bytes, stream_ptr()),
+          "mask_nms")
+    return keep[:k].bool()
+
+
+def unpack_masks(masks, n_vox):
+    lib = _lib_or_raise()
+    k, words = masks.shape
+    out = torch.empty((k, n_vox), dtype=torch.uint8, device=masks.device)
+    check(lib.b2m_unpack_masks(ptr(masks), k, words, n_vox, ptr(out), stream_ptr()), "unpack_masks")
+    return out.bool()
+
+
+def pack_masks_torch(masks_bool):
+    """bool[k, n] -> int32[k, ceil(n/32)] bit-packed (host-side helper for tests; little-endian bits)."""
+    k, n = masks_bool.shape
+    words = (n + 31) // 32
+    pad = words * 32 - n
+    m = torch.nn.functional.pad(masks_bool.to(torch.int64), (0, pad)).view(k, words, 32)
+    weights = (2 ** torch.arange(32, dtype=torch.int64, device=masks_bool.device))
+    w = (m * weights).sum(-1)
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)
+    return w.to(torch.int32).contiguous()

@@ -1,0 +1,200 @@
+/*
+ * b2m.h — C-ABI of the B200-native (sm_100a) hot path of Box2Mask.
+ *
+ * This is the boundary the Python host (box2mask_b200/, importable as `MinkowskiEngine`) binds with
+ * ctypes. It replaces what the reference reaches through `import MinkowskiEngine as ME`
+ * (MinkowskiEngine==0.5.4, pinned at /root/reference/docs/installation.md:6,42; not vendored) and the
+ * CPU torch loops of /root/reference/models/iou_nms.py. Each entry point cites the reference call site
+ * (file:line, relative to /root/reference) whose work it performs.
+ *
+ * Conventions
+ *  - plain pointers + sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`.
+ *  - no allocation inside: outputs and workspaces are caller-allocated; `*_workspace_bytes` queries.
+ *  - stream-ordered on `stream` (a cudaStream_t passed as void*); no host synchronisation inside
+ *    unless stated; re-entrant; no global mutable state.
+ *  - return 0 (B2M_OK) or a negative error code; never throws. `b2m_error_string` names a code.
+ *  - "bf16" = __nv_bfloat16 bit patterns carried as uint16_t.
+ *  - Kernel maps are dense neighbour tables `nbr[K][n_out]` (int32, -1 = no neighbour): entry
+ *    (k, o) is the input row whose coordinate equals coord(o) + delta_k. Offsets enumerate with the
+ *    first spatial axis fastest, k = ix + K*iy + K*K*iz; odd kernels are centred, even kernels start
+ *    at 0 (MinkowskiEngine region-iterator convention).
+ */
+#ifndef B2M_H_
+#define B2M_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2M_OK 0
+#define B2M_ERR_INVALID_ARGUMENT (-1)
+#define B2M_ERR_CUDA_LAUNCH (-2)
+#define B2M_ERR_WORKSPACE_TOO_SMALL (-3)
+#define B2M_ERR_UNSUPPORTED_SHAPE (-4)
+#define B2M_ERR_COORD_RANGE (-5)
+
+typedef void* b2m_stream_t; /* cudaStream_t */
+
+int b2m_version(void);
+const char* b2m_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * Coordinate hash (open addressing, 64-bit packed keys)           reference: ME.SparseTensor(...)
+ * models/model.py:43, models/detection_net.py:499,503 (coordinate-manager insert)
+ * ---------------------------------------------------------------------------------------------- */
+/* number of slots for n coordinates: power of two >= 2n, >= 1024 */
+int64_t b2m_hash_capacity(int64_t n);
+/* Insert rows 0..n-1 of coords int32[n,4] = (b,x,y,z). table_keys uint64[capacity], table_vals
+ * int32[capacity] are (re)initialised inside. status int32[2] (device): [0] = number of rows whose
+ * coordinate was already present (duplicates keep the LOWEST row index, i.e. first occurrence),
+ * [1] = number of rows outside the packable range [-32768, 32767]. */
+int b2m_hash_build(const int32_t* coords, int64_t n, uint64_t* table_keys, int32_t* table_vals,
+                   int64_t capacity, int32_t* status, b2m_stream_t stream);
+/* rows[m] = row index of each query coordinate, -1 if absent */
+int b2m_hash_query(const int32_t* query_coords, int64_t m, const uint64_t* table_keys,
+                   const int32_t* table_vals, int64_t capacity, int32_t* rows, b2m_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Strided coordinate map          reference: MinkowskiConvolution(kernel_size=2, stride=2)
+ * models/detection_net.py:42,48,54,61,68,74,81 (implied coordinate-map stride)
+ * out = unique rows of floor(c / new_stride) * new_stride (batch kept), sorted lexicographically by
+ * (b,x,y,z) — the same rows and order as np.unique(axis=0). parent_row[i] = output row of input i.
+ * n_out (device int32[1]) receives the number of output rows; out_coords has room for n rows.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b2m_downsample_workspace_bytes(int64_t n);
+int b2m_downsample_coords(const int32_t* coords, int64_t n, int32_t new_stride, int32_t* out_coords,
+                          int32_t* parent_row, int32_t* n_out, void* workspace, size_t workspace_bytes,
+                          b2m_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Kernel maps
+ * ---------------------------------------------------------------------------------------------- */
+/* stride-1 (submanifold) map for an odd kernel (3 or 5): nbr int32[K^3, n].
+ * reference: MinkowskiConvolution(kernel_size=3) models/resnet.py:61-65; kernel_size=5
+ * models/detection_net.py:37 */
+int b2m_kernel_map_submanifold(const int32_t* coords, int64_t n, int32_t tensor_stride,
+                               int32_t kernel_size, const uint64_t* table_keys,
+                               const int32_t* table_vals, int64_t capacity, int32_t* nbr,
+                               b2m_stream_t stream);
+/* kernel 2 / stride 2 maps from the parent relation of b2m_downsample_coords.
+ * nbr_down int32[8, n_coarse]: child row of coarse row o at offset k (strided conv, coarse output).
+ * nbr_up   int32[8, n_fine]  : parent row if offset(f)==k else -1 (transposed conv, fine output).
+ * reference: models/detection_net.py:42-82 (down) and :88-133 (MinkowskiConvolutionTranspose) */
+int b2m_kernel_map_stride2(const int32_t* fine_coords, int64_t n_fine, const int32_t* parent_row,
+                           int64_t n_coarse, int32_t fine_stride, int32_t* nbr_down, int32_t* nbr_up,
+                           b2m_stream_t stream);
+/* ME-style pair lists from a dense table: counts int32[K] (pairs per offset). With in_rows/out_rows
+ * non-null and offsets int32[K] (exclusive prefix of counts) also fills the lists, each offset's pairs
+ * ordered by output row. Used by tests/inspection; the convolutions consume the dense table. */
+int b2m_kernel_map_count(const int32_t* nbr, int32_t kvol, int64_t n_out, int32_t* counts,
+                         b2m_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sparse convolution (gather -> tcgen05 implicit GEMM, fp32 accumulation in TMEM)
+ * reference: MinkowskiConvolution.forward / MinkowskiConvolutionTranspose.forward and their autograd
+ * backward — models/detection_net.py:235-337, models/resnet.py:70-83, models/training.py:68
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 rows -> bf16 rows with the channel count zero-padded to c_pad (multiple of 16) */
+int b2m_cast_pad_bf16(const float* x, int64_t n, int32_t c, int32_t c_pad, uint16_t* out,
+                      b2m_stream_t stream);
+/* Weight packing: fp32 kernel[kvol, c_in, c_out] -> bf16 UMMA B-operand image (K-major, 128B swizzle).
+ * mode 0: forward operand   B[k]  = W[k]            (reduction dim = c_in,  N = c_out)
+ * mode 1: dgrad, same-coords B[k]  = W[kvol-1-k]^T  (reduction dim = c_out, N = c_in)
+ * mode 2: dgrad, strided     B[k]  = W[k]^T         (reduction dim = c_out, N = c_in)
+ * c_red (the reduction dim) is padded to a multiple of 64 with zeros. */
+size_t b2m_packed_weight_bytes(int32_t kvol, int32_t c_in, int32_t c_out, int32_t mode);
+int b2m_pack_weights(const float* kernel, int32_t kvol, int32_t c_in, int32_t c_out, int32_t mode,
+                     uint16_t* packed, b2m_stream_t stream);
+/* y[o, :] = sum_k x[nbr[k][o], :] * B[k]   (rows with nbr < 0 contribute zero; nbr == NULL means the
+ * identity map with kvol == 1). x bf16[n_in, c_red], y bf16[n_out, c_n]. c_red % 16 == 0,
+ * c_n % 16 == 0, c_n <= 512. colsum (optional, double[2*c_n], caller-zeroed) accumulates per-column
+ * sum and sum of squares of the fp32 results (BatchNorm batch statistics). */
+int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, const int32_t* nbr, int32_t kvol,
+                     int64_t n_out, const uint16_t* packed_w, int32_t c_n, uint16_t* y, double* colsum,
+                     b2m_stream_t stream);
+/* dw[k, ci, co] += sum_o x[nbr[k][o], ci] * dy[o, co]   (fp32, caller-zeroed, atomically accumulated)
+ * x bf16[n_in, c_in], dy bf16[n_out, c_out]; c_in % 16 == 0, c_out % 16 == 0, c_out <= 256. */
+int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t* dy, int32_t c_out,
+                   const int32_t* nbr, int32_t kvol, int64_t n_out, float* dw, b2m_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm (+ residual, + ReLU) over rows          reference: MinkowskiBatchNorm -> BatchNorm1d
+ * models/resnet.py:63,66,159; models/detection_net.py:40..187; ReLU / `out += residual`
+ * models/resnet.py:67,80-81
+ * ---------------------------------------------------------------------------------------------- */
+/* sums double[2c] += (sum_x, sum_x^2) per column of x bf16[n,c] */
+int b2m_colstats(const uint16_t* x, int64_t n, int32_t c, double* sums, b2m_stream_t stream);
+/* training: mean/var from sums (biased var for normalisation), running stats updated with momentum
+ * (unbiased var), save_mean/save_invstd float[c] written. eval (training==0): uses running stats.
+ * out = act( (x-mean)*invstd*gamma + beta (+ residual) ), act = ReLU if relu else identity. */
+int b2m_bn_forward(const uint16_t* x, int64_t n, int32_t c, const double* sums, const float* gamma,
+                   const float* beta, float* running_mean, float* running_var, float momentum,
+                   float eps, int32_t training, const uint16_t* residual, int32_t relu, uint16_t* out,
+                   float* save_mean, float* save_invstd, b2m_stream_t stream);
+/* pass 1: red double[2c] += (sum_g, sum_g*xhat), g = dout masked by (out > 0) when relu.
+ * pass 2: dx = gamma*invstd*(g - sum_g/n - xhat*sum_gxhat/n); dresidual = g (optional);
+ *         dgamma = sum_gxhat, dbeta = sum_g. In eval mode dx = gamma*invstd*g. */
+int b2m_bn_backward_reduce(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n,
+                           int32_t c, const float* save_mean, const float* save_invstd, int32_t relu,
+                           double* red, b2m_stream_t stream);
+int b2m_bn_backward_apply(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n,
+                          int32_t c, const float* save_mean, const float* save_invstd,
+                          const float* gamma, const double* red, int32_t relu, int32_t training,
+                          uint16_t* dx, uint16_t* dresidual, float* dgamma, float* dbeta,
+                          b2m_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Superpoint pooling                reference: models/detection_net.py:345-352 (re-keyed
+ * SparseTensor + MinkowskiGlobalAvgPooling / MinkowskiGlobalMaxPooling), ids utils/util.py:123-130
+ * ---------------------------------------------------------------------------------------------- */
+/* out float[s, c] = mean over rows v with ids[v] == s of f bf16[n, c]; counts float[s] written.
+ * out and counts are zeroed inside. */
+int b2m_segment_mean_forward(const uint16_t* f, const int64_t* ids, int64_t n, int32_t c, int64_t s,
+                             float* out, float* counts, b2m_stream_t stream);
+/* df bf16[n, c] = dout[ids[v], :] / counts[ids[v]] */
+int b2m_segment_mean_backward(const float* dout, const int64_t* ids, const float* counts, int64_t n,
+                              int32_t c, uint16_t* df, b2m_stream_t stream);
+/* out float[s, c] = max over the segment, argmax int32[s, c] = row that attained it */
+int b2m_segment_max_forward(const uint16_t* f, const int64_t* ids, int64_t n, int32_t c, int64_t s,
+                            float* out, int32_t* argmax, b2m_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Box-vote decoding                 reference: models/iou_nms.py and models/detection_net.py:369-488
+ * ---------------------------------------------------------------------------------------------- */
+/* NMS_clustering (models/iou_nms.py:68-105). boxes float[m,7] = (score, min xyz, max xyz).
+ * Greedy in order of descending score (ties: lower index first). Outputs:
+ *  n_clusters int32[1]; representatives int32[m] (first n_clusters valid, box index of each cluster);
+ *  cluster_of int32[m] (cluster index each box was assigned to);
+ *  heatmaps float[max_clusters, m] (row c = IoU of representative c with ALL boxes, self = 1) — rows
+ *  beyond max_clusters are not written (n_clusters still counts them).
+ * IoU arithmetic is the reference's fp32 operation order with IEEE rounding and no FMA contraction:
+ *  I = (dx*dy)*dz with d = max(min(max_a,max_b) - max(min_a,min_b), 0);
+ *  U = ((A_r + A_j) - I) + 1e-6f;  iou = I / U. */
+size_t b2m_nms_workspace_bytes(int64_t m);
+int b2m_aabb_nms(const float* boxes, int64_t m, float cluster_th, int32_t* n_clusters,
+                 int32_t* representatives, int32_t* cluster_of, float* heatmaps, int64_t max_clusters,
+                 void* workspace, size_t workspace_bytes, b2m_stream_t stream);
+/* Heat-map rows -> bit-packed voxel masks (models/detection_net.py:436-446):
+ *  mask[c, v] = heat[c, fg_rank[seg2vox[v]]] > mask_bin_th, 0 where fg_rank < 0 (background).
+ *  heat float[k, m_fg], fg_rank int32[s] (rank of superpoint among foreground ones or -1),
+ *  seg2vox int64[n_vox]; masks uint32[k, words], words = ceil(n_vox/32); bit v%32 of word v/32. */
+int b2m_heatmap_project(const float* heat, int64_t k, int64_t m_fg, const int32_t* fg_rank,
+                        const int64_t* seg2vox, int64_t n_vox, float mask_bin_th, uint32_t* masks,
+                        b2m_stream_t stream);
+/* mask_NMS (models/iou_nms.py:130-144) on bit-packed masks given in score order.
+ *  keep uint8[k] = 1 for kept masks; n_keep int32[1]. IoU = float(|a&b|) / float(|a|b|) > th suppresses.
+ *  workspace: int32[k*k] intersections + int32[k] areas. */
+size_t b2m_mask_nms_workspace_bytes(int64_t k);
+int b2m_mask_nms(const uint32_t* masks, int64_t k, int64_t words, float th, uint8_t* keep,
+                 int32_t* n_keep, void* workspace, size_t workspace_bytes, b2m_stream_t stream);
+/* unpack bit masks to bool bytes uint8[k, n_vox] */
+int b2m_unpack_masks(const uint32_t* masks, int64_t k, int64_t words, int64_t n_vox, uint8_t* out,
+                     b2m_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2M_H_ */
