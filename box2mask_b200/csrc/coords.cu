@@ -181,7 +181,7 @@ extern "C" int64_t b2m_hash_capacity(int64_t n) {
 
 extern "C" int b2m_hash_build(const int32_t* coords, int64_t n, uint64_t* table_keys, int32_t* table_vals,
                               int64_t capacity, int32_t* status, b2m_stream_t stream) {
-  if (!coords || !table_keys || !table_vals || !status || n < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if ((!coords && n > 0) || !table_keys || !table_vals || !status || n < 0) return B2M_ERR_INVALID_ARGUMENT;
   if (capacity < 2 * n || (capacity & (capacity - 1)) != 0) return B2M_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(table_keys, 0xFF, (size_t)capacity * 8, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
@@ -197,8 +197,8 @@ extern "C" int b2m_hash_build(const int32_t* coords, int64_t n, uint64_t* table_
 
 extern "C" int b2m_hash_query(const int32_t* query_coords, int64_t m, const uint64_t* table_keys,
                               const int32_t* table_vals, int64_t capacity, int32_t* rows, b2m_stream_t stream) {
-  if (!query_coords || !table_keys || !table_vals || !rows || m < 0) return B2M_ERR_INVALID_ARGUMENT;
   if (m == 0) return B2M_OK;
+  if (!query_coords || !table_keys || !table_vals || !rows || m < 0) return B2M_ERR_INVALID_ARGUMENT;
   hash_query_kernel<<<cdiv(m, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const int4*>(query_coords), m, reinterpret_cast<const unsigned long long*>(table_keys),
       table_vals, (uint64_t)(capacity - 1), rows);
@@ -211,14 +211,14 @@ extern "C" size_t b2m_downsample_workspace_bytes(int64_t n) { return downsample_
 extern "C" int b2m_downsample_coords(const int32_t* coords, int64_t n, int32_t new_stride, int32_t* out_coords,
                                      int32_t* parent_row, int32_t* n_out, void* workspace, size_t workspace_bytes,
                                      b2m_stream_t stream) {
-  if (!coords || !out_coords || !parent_row || !n_out || !workspace || n < 0 || new_stride <= 0)
-    return B2M_ERR_INVALID_ARGUMENT;
-  if (n >= (int64_t)1 << 31) return B2M_ERR_UNSUPPORTED_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  if (n == 0) {
+  if (n == 0 && n_out && new_stride > 0) {
     if (cudaMemsetAsync(n_out, 0, 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
     return B2M_OK;
   }
+  if (!coords || !out_coords || !parent_row || !n_out || !workspace || n < 0 || new_stride <= 0)
+    return B2M_ERR_INVALID_ARGUMENT;
+  if (n >= (int64_t)1 << 31) return B2M_ERR_UNSUPPORTED_SHAPE;
   const DownsampleWs w = downsample_ws(n);
   if (workspace_bytes < w.total) return B2M_ERR_WORKSPACE_TOO_SMALL;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
@@ -249,9 +249,9 @@ extern "C" int b2m_downsample_coords(const int32_t* coords, int64_t n, int32_t n
 extern "C" int b2m_kernel_map_submanifold(const int32_t* coords, int64_t n, int32_t tensor_stride, int32_t kernel_size,
                                           const uint64_t* table_keys, const int32_t* table_vals, int64_t capacity,
                                           int32_t* nbr, b2m_stream_t stream) {
-  if (!coords || !table_keys || !table_vals || !nbr || n < 0 || tensor_stride <= 0) return B2M_ERR_INVALID_ARGUMENT;
   if (kernel_size != 1 && kernel_size != 3 && kernel_size != 5) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n == 0) return B2M_OK;
+  if (!coords || !table_keys || !table_vals || !nbr || n < 0 || tensor_stride <= 0) return B2M_ERR_INVALID_ARGUMENT;
   const int64_t total = n * kernel_size * kernel_size * kernel_size;
   kmap_submanifold_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const int4*>(coords), n, tensor_stride, kernel_size,

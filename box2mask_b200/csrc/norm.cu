@@ -152,7 +152,7 @@ bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int c, const float* _
 
 __global__ void __launch_bounds__(kNormThreads)
 bn_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ out, const uint16_t* __restrict__ dout,
-                    int64_t n, int c, const float* __restrict__ mean, const float* __restrict__ invstd,
+                    int64_t n, int64_t n_stat, int c, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ gamma, const double* __restrict__ red, int relu, int training,
                     uint16_t* __restrict__ dx, uint16_t* __restrict__ dres, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
@@ -164,7 +164,7 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__
       if (dgamma) dgamma[j] = (float)red[c + j];
     }
   }
-  const float inv_n = 1.f / (float)n;
+  const float inv_n = 1.f / (float)n_stat;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(v % G);
     float xv[8], gv[8], o[8];
@@ -235,7 +235,7 @@ extern "C" int b2m_colstats(const uint16_t* x, int64_t n, int32_t c, double* sum
   return B2M_OK;
 }
 
-extern "C" int b2m_bn_forward(const uint16_t* x, int64_t n, int32_t c, const double* sums, const float* gamma,
+extern "C" int b2m_bn_forward(const uint16_t* x, int64_t n, int64_t n_stat, int32_t c, const double* sums, const float* gamma,
                               const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                               int32_t training, const uint16_t* residual, int32_t relu, uint16_t* out, float* save_mean,
                               float* save_invstd, b2m_stream_t stream) {
@@ -245,7 +245,7 @@ extern "C" int b2m_bn_forward(const uint16_t* x, int64_t n, int32_t c, const dou
   if (!norm_shape_ok(c)) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n == 0) return B2M_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  bn_prepare_kernel<<<1, 256, 0, st>>>(sums, n, c, gamma, beta, running_mean, running_var, momentum, eps, training,
+  bn_prepare_kernel<<<1, 256, 0, st>>>(sums, n_stat, c, gamma, beta, running_mean, running_var, momentum, eps, training,
                                       save_mean, save_invstd);
   B2M_CHECK_LAUNCH();
   bn_apply_kernel<<<apply_grid(n * (c / 8)), kNormThreads, 0, st>>>(x, n, c, gamma, beta, save_mean, save_invstd,
@@ -269,7 +269,8 @@ extern "C" int b2m_bn_backward_reduce(const uint16_t* x, const uint16_t* out, co
   return B2M_OK;
 }
 
-extern "C" int b2m_bn_backward_apply(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n, int32_t c,
+extern "C" int b2m_bn_backward_apply(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n,
+                                     int64_t n_stat, int32_t c,
                                      const float* save_mean, const float* save_invstd, const float* gamma,
                                      const double* red, int32_t relu, int32_t training, uint16_t* dx,
                                      uint16_t* dresidual, float* dgamma, float* dbeta, b2m_stream_t stream) {
@@ -278,7 +279,7 @@ extern "C" int b2m_bn_backward_apply(const uint16_t* x, const uint16_t* out, con
   if (!norm_shape_ok(c)) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n == 0) return B2M_OK;
   bn_bwd_apply_kernel<<<apply_grid(n * (c / 8)), kNormThreads, 0, (cudaStream_t)stream>>>(
-      x, out, dout, n, c, save_mean, save_invstd, gamma, red, relu, training, dx, dresidual, dgamma, dbeta);
+      x, out, dout, n, n_stat, c, save_mean, save_invstd, gamma, red, relu, training, dx, dresidual, dgamma, dbeta);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }

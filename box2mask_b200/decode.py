@@ -1,0 +1,93 @@
+"""Box-vote decoding on the GPU: drop-ins for the reference's CPU torch loops.
+
+NMS_clustering / mask_NMS keep the reference's signatures and return values
+(/root/reference/models/iou_nms.py:68-105,130-144); detection2mask follows
+/root/reference/models/detection_net.py:369-488 but keeps heat-maps and masks on the device,
+bit-packed, until the final projection.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def NMS_clustering(boxes, cluster_th=0.5, get_heatmaps=True):
+    """boxes f32[M,7] = (score, min, max). Returns (representatives i64[K], clusters: list of i64 tensors in
+    descending-score order, heatmaps f32[K,M]) like the reference; tensors stay on boxes' CUDA device."""
+    assert boxes.shape[1] == 7 and boxes.dim() == 2
+    assert 0 < cluster_th < 1
+    boxes = boxes.contiguous().float()
+    reps, cluster_of, heat = ops.aabb_nms(boxes, cluster_th, want_heatmaps=get_heatmaps)
+    order = torch.argsort(-boxes[:, 0], stable=True)
+    sorted_cluster = cluster_of[order]
+    clusters = [order[sorted_cluster == c] for c in range(len(reps))]
+    if get_heatmaps:
+        return reps, clusters, heat
+    return reps, clusters
+
+
+def mask_NMS(sorted_masks, cluster_th=0.5, allow_empty=False):
+    """sorted_masks bool[K,N] (or bit-packed int32[K,words]); returns (kept indices i64[K'], None)."""
+    packed = sorted_masks if sorted_masks.dtype == torch.int32 else ops.pack_masks_torch(sorted_masks)
+    keep = ops.mask_nms(packed, cluster_th)
+    return torch.nonzero(keep).flatten(), None
+
+
+def to_bbs_min_max(locations, offsets, bounds, scores=None):
+    """/root/reference/utils/util.py:46-64."""
+    centers = offsets + locations
+    bbs = torch.cat([centers - bounds, centers + bounds], dim=1)
+    return torch.cat((scores, bbs), dim=1) if scores is not None else bbs
+
+
+def detection2mask(net, batch, pred, cfg, mode="eval", score_filtering=True, cluster_th=0.3, score_th=0.3,
+                   mask_bin_th=0.3, mask_nms_th=0.3):
+    """pred: dict head -> f32 tensor (any device). Returns {scene name: {conf, label_id, mask, ...}}."""
+    dev = torch.device(net.device)
+    P = {k: v.to(dev).float() for k, v in pred.items()}
+    loc = batch["input_location"].to(dev)
+    pred_bbs = to_bbs_min_max(loc, P[cfg.mlp_offsets], P[cfg.mlp_bounds], torch.sigmoid(P[cfg.mlp_bb_scores]))
+    sem_idx = torch.argmax(P[cfg.mlp_semantics], 1)
+    class_ids = torch.as_tensor(net.semantic_valid_class_ids, device=dev).long()
+    pred_sem = class_ids[sem_idx]
+    batch_ids = batch["batch_ids"].to(dev)
+    results = {}
+    for scene_idx, scene in enumerate(batch["scene"]):
+        scene_mask = batch_ids == scene_idx
+        scene_sem = pred_sem[scene_mask]
+        scene_fg = net.is_foreground(scene_sem)
+        scene_fg = torch.as_tensor(scene_fg, device=dev).bool()
+        scene_bbs = pred_bbs[scene_mask][scene_fg].contiguous()
+        seg2vox = batch["seg2vox"][scene_idx].to(dev).long().contiguous()
+        n_vox = seg2vox.shape[0]
+        if scene_bbs.shape[0] == 0:
+            results[scene["name"]] = {"conf": torch.zeros(0), "label_id": np.zeros(0, dtype="int32"),
+                                      "mask": torch.zeros((0, n_vox), dtype=torch.bool)}
+            continue
+        reps, cluster_of, heat = ops.aabb_nms(scene_bbs, cluster_th)
+        scores = scene_bbs[reps][:, 0]
+        if score_filtering:
+            sel = scores > score_th
+            heat, scores, reps = heat[sel].contiguous(), scores[sel], reps[sel]
+        fg_rank = torch.full((scene_fg.shape[0],), -1, dtype=torch.int32, device=dev)
+        fg_rank[scene_fg] = torch.arange(int(scene_fg.sum()), dtype=torch.int32, device=dev)
+        packed = ops.heatmap_project(heat, fg_rank, seg2vox, mask_bin_th)
+        keep = ops.mask_nms(packed, mask_nms_th)
+        packed, scores, reps = packed[keep].contiguous(), scores[keep], reps[keep]
+        masks = ops.unpack_masks(packed, n_vox)
+        sem_vox = scene_sem[seg2vox]
+        # per-instance majority label (np.bincount + argmax, detection_net.py:461-466)
+        n_lab = int(class_ids.max().item()) + 1
+        onehot = torch.zeros((n_vox, n_lab), device=dev)
+        onehot[torch.arange(n_vox, device=dev), sem_vox] = 1
+        labels = torch.argmax(masks.float() @ onehot, 1).to(torch.int32).cpu().numpy()
+        res = {"conf": scores.cpu(), "label_id": labels}
+        if mode == "eval" and "vox2point" in batch:
+            res["mask"] = masks[:, batch["vox2point"][scene_idx].to(dev)].cpu()
+        else:
+            res["mask"] = masks.cpu()
+            res["cluster_representatives"] = reps.cpu()
+            res["bbs"] = scene_bbs[reps].cpu()
+            res["pred_fg"] = scene_fg.cpu()
+        results[scene["name"]] = res
+    return results

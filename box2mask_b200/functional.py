@@ -1,0 +1,122 @@
+"""Autograd functions over the C-ABI ops (box2mask_b200/ops.py).
+
+Activations are stored in bf16 (fp32 accumulation inside the kernels); parameters and their gradients
+are fp32. Each Function's backward calls the matching CUDA kernels — there is no torch fallback.
+"""
+import torch
+
+from . import ops
+
+
+class SparseConvFn(torch.autograd.Function):
+    """y = sum_k x[nbr_fwd[k]] @ W[k]  (reference: MinkowskiConvolution / MinkowskiConvolutionTranspose forward,
+    /root/reference/models/detection_net.py:235-337; backward = autograd of the same, models/training.py:68).
+
+    nbr_fwd : dense neighbour table of the forward map [K, n_out] (None = identity, K == 1)
+    nbr_bwd : table of the transposed relation [K, n_in] used for dgrad
+    dgrad_mode : weight packing for dgrad (1 = mirrored offsets, same coordinates; 2 = strided / transposed)
+    Returns (y bf16 [n_out, c_out], colsum f64 [2*c_out] = per-column (sum, sum of squares) of y).
+    """
+
+    @staticmethod
+    def forward(ctx, x, kernel, nbr_fwd, nbr_bwd, dgrad_mode, n_out, c_in_real):
+        kvol = 1 if kernel.dim() == 2 else kernel.shape[0]
+        c_out = kernel.shape[-1]
+        w = kernel.detach()
+        if w.shape[-2] != x.shape[1]:  # first conv: input channels zero-padded to a multiple of 16
+            pad = x.shape[1] - w.shape[-2]
+            w = torch.nn.functional.pad(w, (0, 0, 0, pad))
+        w = w.contiguous()
+        packed = ops.pack_weights(w, 0)
+        colsum = torch.zeros(2 * c_out, dtype=torch.float64, device=x.device)
+        y = ops.conv_forward(x, nbr_fwd, packed, kvol, n_out, c_out, colsum)
+        ctx.save_for_backward(x, kernel)
+        ctx.nbr_fwd, ctx.nbr_bwd, ctx.dgrad_mode, ctx.n_out, ctx.kvol = nbr_fwd, nbr_bwd, dgrad_mode, n_out, kvol
+        ctx.c_in_real = c_in_real
+        ctx.mark_non_differentiable(colsum)
+        return y, colsum
+
+    @staticmethod
+    def backward(ctx, dy, _dcolsum):
+        x, kernel = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            w = kernel.detach().contiguous()
+            packed_t = ops.pack_weights(w, ctx.dgrad_mode)
+            dx = ops.conv_forward(dy, ctx.nbr_bwd, packed_t, ctx.kvol, x.shape[0], x.shape[1])
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_wgrad(x, dy, ctx.nbr_fwd, ctx.kvol, ctx.n_out)
+            if dw.shape[1] != ctx.c_in_real:
+                dw = dw[:, :ctx.c_in_real, :]
+            dw = dw.reshape(kernel.shape).contiguous()
+        return dx, dw, None, None, None, None, None
+
+
+class BatchNormFn(torch.autograd.Function):
+    """out = act(BN(x) (+ residual)) over rows; reference: MinkowskiBatchNorm -> BatchNorm1d
+    (/root/reference/models/resnet.py:63,66,159), ReLU and `out += residual` (models/resnet.py:67,80-81)."""
+
+    @staticmethod
+    def forward(ctx, x, sums, gamma, beta, running_mean, running_var, momentum, eps, training, residual, relu,
+                sync_group):
+        n = x.shape[0]
+        n_stat = n
+        if training:
+            if sums is None:
+                sums = ops.colstats(x)
+            if sync_group is not None:
+                packed = torch.cat([sums, torch.tensor([float(n)], dtype=torch.float64, device=x.device)])
+                torch.distributed.all_reduce(packed, group=sync_group)
+                sums, n_stat = packed[:-1].contiguous(), int(round(float(packed[-1].item())))
+            if n_stat <= 1:
+                raise ValueError("Expected more than 1 value per channel when training")
+        out, save_mean, save_invstd = ops.bn_forward(x, sums, gamma.detach(), beta.detach(), running_mean, running_var,
+                                                     momentum, eps, training, residual, relu, n_stat)
+        ctx.save_for_backward(x, out, save_mean, save_invstd, gamma)
+        ctx.relu, ctx.training, ctx.has_res, ctx.n_stat, ctx.sync_group = relu, training, residual is not None, n_stat, sync_group
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, out, save_mean, save_invstd, gamma = ctx.saved_tensors
+        hook = None
+        if ctx.sync_group is not None and ctx.training:
+            hook = lambda red: torch.distributed.all_reduce(red, group=ctx.sync_group)  # noqa: E731
+        dx, dres, dgamma, dbeta = ops.bn_backward(x, out, dout.contiguous(), save_mean, save_invstd, gamma.detach(),
+                                                  ctx.relu, ctx.training, ctx.has_res, ctx.n_stat, hook)
+        return dx, None, dgamma, dbeta, None, None, None, None, None, dres, None, None
+
+
+class SegmentMeanFn(torch.autograd.Function):
+    """Superpoint mean pooling (/root/reference/models/detection_net.py:345-352)."""
+
+    @staticmethod
+    def forward(ctx, f, ids, s):
+        out, counts = ops.segment_mean_forward(f, ids, s)
+        ctx.save_for_backward(ids, counts)
+        ctx.n = f.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ids, counts = ctx.saved_tensors
+        return ops.segment_mean_backward(dout.contiguous().float(), ids, counts, ctx.n), None, None
+
+
+class SegmentMaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, ids, s):
+        out, argmax = ops.segment_max_forward(f, ids, s)
+        ctx.save_for_backward(argmax)
+        ctx.shape = f.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (argmax,) = ctx.saved_tensors
+        df = torch.zeros(ctx.shape, dtype=torch.float32, device=dout.device)
+        valid = argmax < ctx.shape[0]
+        cols = torch.arange(ctx.shape[1], device=dout.device)[None].expand_as(argmax)
+        df.index_put_((argmax[valid].long(), cols[valid]), dout[valid].float(), accumulate=True)
+        return df.to(torch.bfloat16), None, None

@@ -1,0 +1,137 @@
+"""SparseTensor and the coordinate manager (host side).
+
+Mirrors ME.SparseTensor as the reference uses it: `ME.SparseTensor(features, coordinates, device=...)`
+(/root/reference/models/model.py:43, models/detection_net.py:348,499,503), attributes `.F` / `.C`
+(`.C` is mutable in place: `out.C[:,0] = pooling_ids`, models/detection_net.py:347), `out += residual`
+(models/resnet.py:80). The coordinate manager owns, per tensor stride, the int32 [N,4] coordinates,
+their GPU hash table and the cached kernel maps; every tensor derived from one input shares it.
+"""
+import torch
+
+from .. import ops
+
+
+class CoordinateManager:
+    """Per-input cache of coordinate levels and kernel maps. Keys are tensor strides (ints)."""
+
+    def __init__(self, coords):
+        self.levels = {1: coords}       # stride -> int32 [N,4] on device
+        self.tables = {}                # stride -> ops.HashTable
+        self.sub_maps = {}              # (stride, ksize) -> nbr [K^3, N]
+        self.stride2 = {}               # fine stride -> (parent_row, nbr_down, nbr_up)
+
+    def coords(self, stride):
+        return self.levels[stride]
+
+    def table(self, stride):
+        if stride not in self.tables:
+            t = ops.hash_build(self.levels[stride])
+            self.tables[stride] = t
+        return self.tables[stride]
+
+    def submanifold_map(self, stride, ksize):
+        key = (stride, ksize)
+        if key not in self.sub_maps:
+            self.sub_maps[key] = ops.kernel_map_submanifold(self.levels[stride], stride, ksize, self.table(stride))
+        return self.sub_maps[key]
+
+    def stride2_maps(self, fine_stride):
+        """Creates the coarse level (2*fine_stride) if needed; returns (nbr_down [8,Nc], nbr_up [8,Nf])."""
+        if fine_stride not in self.stride2:
+            fine = self.levels[fine_stride]
+            coarse, parent = ops.downsample_coords(fine, 2 * fine_stride)
+            self.levels[2 * fine_stride] = coarse
+            nbr_down, nbr_up = ops.kernel_map_stride2(fine, parent, coarse.shape[0], fine_stride)
+            self.stride2[fine_stride] = (nbr_down, nbr_up)
+        return self.stride2[fine_stride]
+
+
+class SparseTensor:
+    def __init__(self, features, coordinates=None, device=None, coordinate_manager=None, tensor_stride=1,
+                 quantization_mode=None, **_unused):
+        if coordinate_manager is None:
+            if coordinates is None:
+                raise ValueError("SparseTensor needs coordinates or a coordinate_manager")
+            if device is None:
+                device = features.device
+            device = torch.device(device)
+            if device.type != "cuda":
+                raise ops._lib.B2MError("box2mask_b200 SparseTensor lives on a CUDA device (no CPU path)")
+            coords = coordinates.to(device=device, dtype=torch.int32).contiguous()
+            if coords.dim() != 2 or coords.shape[1] != 4:
+                raise ValueError("coordinates must be [N, 4] = (batch, x, y, z)")
+            features = features.to(device)
+            if features.shape[0] != coords.shape[0]:
+                raise ValueError("features and coordinates disagree on the number of rows")
+            coordinate_manager = CoordinateManager(coords)
+            tensor_stride = 1
+        self._F = features
+        self._manager = coordinate_manager
+        self._stride = int(tensor_stride)
+        self._C = None
+        self._colsum = None   # per-column (sum, sumsq) of F produced by the conv epilogue, consumed by BatchNorm
+
+    # -- reference-visible attributes -------------------------------------------------------------
+    @property
+    def F(self):
+        return self._F
+
+    @property
+    def C(self):
+        if self._C is None:
+            self._C = self._manager.coords(self._stride).clone()   # ME hands out a copy; callers mutate it
+        return self._C
+
+    @property
+    def coordinate_manager(self):
+        return self._manager
+
+    @property
+    def tensor_stride(self):
+        return [self._stride] * 3
+
+    @property
+    def device(self):
+        return self._F.device
+
+    @property
+    def shape(self):
+        return self._F.shape
+
+    def __len__(self):
+        return self._F.shape[0]
+
+    def _like(self, features, stride=None):
+        return SparseTensor(features, coordinate_manager=self._manager,
+                            tensor_stride=self._stride if stride is None else stride)
+
+    def __iadd__(self, other):
+        self._check_same_key(other)
+        self._F = self._F + other._F
+        self._colsum = None
+        return self
+
+    def __add__(self, other):
+        self._check_same_key(other)
+        return self._like(self._F + other._F)
+
+    def _check_same_key(self, other):
+        if not isinstance(other, SparseTensor) or other._manager is not self._manager or other._stride != self._stride:
+            raise ValueError("SparseTensor arithmetic needs operands on the same coordinate map")
+
+    def __repr__(self):
+        return "SparseTensor(rows=%d, channels=%d, tensor_stride=%d, dtype=%s)" % (
+            self._F.shape[0], self._F.shape[1], self._stride, self._F.dtype)
+
+
+TensorField = SparseTensor  # only referenced in a type annotation (models/resnet.py:244)
+
+
+def cat(*tensors):
+    """ME.cat: channel concatenation of tensors on the same coordinate map (models/detection_net.py:286-336)."""
+    if len(tensors) == 1 and isinstance(tensors[0], (list, tuple)):
+        tensors = tuple(tensors[0])
+    first = tensors[0]
+    for t in tensors[1:]:
+        first._check_same_key(t)
+    return first._like(torch.cat([t._F for t in tensors], dim=1))

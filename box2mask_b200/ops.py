@@ -156,30 +156,34 @@ def colstats(x):
     return sums
 
 
-def bn_forward(x, sums, gamma, beta, running_mean, running_var, momentum, eps, training, residual=None, relu=False):
+def bn_forward(x, sums, gamma, beta, running_mean, running_var, momentum, eps, training, residual=None, relu=False,
+               n_stat=None):
     lib = _lib_or_raise()
     _cuda(x, torch.bfloat16, "x")
     n, c = x.shape
     out = torch.empty_like(x)
     save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
     save_invstd = torch.empty(c, dtype=torch.float32, device=x.device)
-    check(lib.b2m_bn_forward(ptr(x), n, c, ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+    check(lib.b2m_bn_forward(ptr(x), n, n if n_stat is None else int(n_stat), c, ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
                              float(momentum), float(eps), int(bool(training)), ptr(residual), int(bool(relu)), ptr(out),
                              ptr(save_mean), ptr(save_invstd), stream_ptr()), "bn_forward")
     return out, save_mean, save_invstd
 
 
-def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, want_dresidual):
+def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, want_dresidual, n_stat=None,
+                reduce_hook=None):
     lib = _lib_or_raise()
     n, c = x.shape
     red = torch.zeros(2 * c, dtype=torch.float64, device=x.device)
     check(lib.b2m_bn_backward_reduce(ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd),
                                      int(bool(relu)), ptr(red), stream_ptr()), "bn_backward_reduce")
+    if reduce_hook is not None:
+        reduce_hook(red)  # SyncBN: all-reduce (sum_g, sum_g*xhat) over ranks
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dresidual else None
     dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
     dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
-    check(lib.b2m_bn_backward_apply(ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd), ptr(gamma),
+    check(lib.b2m_bn_backward_apply(ptr(x), ptr(out), ptr(dout), n, n if n_stat is None else int(n_stat), c, ptr(save_mean), ptr(save_invstd), ptr(gamma),
                                     ptr(red), int(bool(relu)), int(bool(training)), ptr(dx), ptr(dres), ptr(dgamma),
                                     ptr(dbeta), stream_ptr()), "bn_backward_apply")
     return dx, dres, dgamma, dbeta

@@ -74,10 +74,21 @@ def make_scene(seed, scale=0.84, voxel_size=0.02, density=2.0e4, n_classes=20):
         "input_location": loc,
         "gt_bb_offsets": rng.uniform(-1, 1, (s, 3)).astype(np.float32),
         "gt_bb_bounds": rng.uniform(0.05, 1, (s, 3)).astype(np.float32),
-        "gt_semantics": rng.integers(0, n_classes, s).astype(np.int64),
+        "gt_semantics": rng.integers(0, n_classes + 1, s).astype(np.int64),   # 0 = unlabeled (ignored)
         "fg_instances": fg,
         "gt_boxes": boxes,
     }
+
+
+def label_maps(n_classes=20):
+    """ScanNet-like label tables (dataprocessing/scannet.py:114-118): valid class ids 1..n, id 0 unlabeled -> -100,
+    ids 1 and 2 (wall, floor) are background."""
+    valid = torch.arange(1, n_classes + 1)
+    id2idx = torch.cat([torch.tensor([-100]), torch.arange(n_classes)])
+
+    def is_foreground(sem_ids):
+        return sem_ids > 2
+    return valid, id2idx, is_foreground
 
 
 def batched_coordinates(coords_list, dtype=torch.int32):

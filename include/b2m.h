@@ -127,10 +127,11 @@ int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t
  * ---------------------------------------------------------------------------------------------- */
 /* sums double[2c] += (sum_x, sum_x^2) per column of x bf16[n,c] */
 int b2m_colstats(const uint16_t* x, int64_t n, int32_t c, double* sums, b2m_stream_t stream);
-/* training: mean/var from sums (biased var for normalisation), running stats updated with momentum
+/* n_stat = number of rows the sums were taken over (== n on one GPU; the all-rank total under SyncBN).
+ * training: mean/var from sums (biased var for normalisation), running stats updated with momentum
  * (unbiased var), save_mean/save_invstd float[c] written. eval (training==0): uses running stats.
  * out = act( (x-mean)*invstd*gamma + beta (+ residual) ), act = ReLU if relu else identity. */
-int b2m_bn_forward(const uint16_t* x, int64_t n, int32_t c, const double* sums, const float* gamma,
+int b2m_bn_forward(const uint16_t* x, int64_t n, int64_t n_stat, int32_t c, const double* sums, const float* gamma,
                    const float* beta, float* running_mean, float* running_var, float momentum,
                    float eps, int32_t training, const uint16_t* residual, int32_t relu, uint16_t* out,
                    float* save_mean, float* save_invstd, b2m_stream_t stream);
@@ -141,7 +142,7 @@ int b2m_bn_backward_reduce(const uint16_t* x, const uint16_t* out, const uint16_
                            int32_t c, const float* save_mean, const float* save_invstd, int32_t relu,
                            double* red, b2m_stream_t stream);
 int b2m_bn_backward_apply(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n,
-                          int32_t c, const float* save_mean, const float* save_invstd,
+                          int64_t n_stat, int32_t c, const float* save_mean, const float* save_invstd,
                           const float* gamma, const double* red, int32_t relu, int32_t training,
                           uint16_t* dx, uint16_t* dresidual, float* dgamma, float* dbeta,
                           b2m_stream_t stream);

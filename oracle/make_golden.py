@@ -65,8 +65,66 @@ def golden_nms():
     np.savez_compressed(os.path.join(OUT, "nms_cases.npz"), **out)
 
 
+
+
+def golden_net():
+    """Run the reference's own SelectionNet / Model code (over oracle/me_shim.py) on a small seeded batch."""
+    from box2mask_b200.selection_net import default_config
+    from box2mask_b200.synthetic import label_maps, make_batch
+    from oracle import me_shim
+    from oracle.selection_net import seeded_state_dict
+    me_shim.install()
+    sys.path.insert(0, REF)
+    # the reference hard-codes .to('cuda') in its loss (models/model.py:197,213); run it on the CPU here
+    orig_to = torch.Tensor.to
+
+    def to_cpu(self, *a, **k):
+        a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
+        return orig_to(self, *a, **k)
+    torch.Tensor.to = to_cpu
+    import models.model as ref_model
+
+    cfg = default_config(mlp_bb_scores_start_epoch=0)
+    valid, id2idx, is_fg = label_maps(20)
+    model = ref_model.Model(cfg, valid, id2idx, None, is_fg, device="cpu")
+    net = model.detection_model
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    net.load_state_dict(seeded_state_dict(shapes, seed=0))
+    batch = make_batch(2, seed=7, scale=0.14, density=1.2e4)
+    print("golden net batch: voxels", batch["vox_coords"].shape[0], "superpoints", batch["input_location"].shape[0])
+    out = {"vox_coords": batch["vox_coords"].numpy(), "vox_features": batch["vox_features"].numpy(),
+           "pooling_ids": batch["pooling_ids"].numpy(), "input_location": batch["input_location"].numpy(),
+           "gt_bb_offsets": batch["gt_bb_offsets"].numpy(), "gt_bb_bounds": batch["gt_bb_bounds"].numpy(),
+           "gt_semantics": batch["gt_semantics"].numpy(), "fg_instances": batch["fg_instances"].numpy(),
+           "keys": np.array(list(shapes.keys())), "shapes": np.array([str(s) for s in shapes.values()])}
+    # eval-mode forward (running statistics)
+    model.eval()
+    pred = model.get_prediction(batch, with_grad=False, to_cpu=True, min_size=False)
+    for k, v in pred.items():
+        out["eval_" + k] = v.numpy()
+    # train-mode forward + losses + a few gradients
+    model.train()
+    losses, pred = model.compute_loss_detection(batch, epoch=0)
+    losses["optimization_loss"].backward()
+    for k, v in pred.items():
+        out["train_" + k] = v.detach().numpy()
+    for k in ("optimization_loss", "offset_loss", "bounds_loss", "bb_score_loss", "bb_target_scores"):
+        out["loss_" + k] = np.float64(float(losses[k]))
+    out["loss_semantics_loss"] = np.float64(float(losses["semantics_loss"]))
+    params = dict(net.named_parameters())
+    for k in ("conv0p1s1.kernel", "block1.0.conv1.kernel", "block8.1.conv2.kernel", "added_block3.1.conv2.kernel",
+              "convtr7p2s2.kernel", "conv2p2s2.kernel", "block2.0.downsample.0.kernel", "bn0.bn.weight",
+              "block8.1.norm2.bn.bias", "mlp_offsets.6.kernel", "mlp_semantics.0.bias"):
+        g = params[k].grad
+        out["grad_" + k] = g.numpy() if g.numel() <= 40000 else g.flatten()[:40000].numpy()
+        out["gradnorm_" + k] = np.float64(float(g.norm()))
+    torch.Tensor.to = orig_to
+    np.savez_compressed(os.path.join(OUT, "selection_net_small.npz"), **out)
+    print({k: float(v) for k, v in out.items() if k.startswith("loss_")})
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference not mounted at %s" % REF)
     os.makedirs(OUT, exist_ok=True)
     golden_nms()
+    golden_net()

@@ -1,0 +1,36 @@
+"""CPU: the C-ABI library builds/loads and exports every symbol include/b2m.h declares (no compute calls)."""
+import os
+import re
+
+from box2mask_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "b2m.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2m_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header():
+    build.build()
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert sorted(_lib.SIGNATURES) == syms            # the ctypes table mirrors the header one to one
+    assert lib.b2m_version() == 1
+    assert lib.b2m_error_string(-4) == b"unsupported shape"
+    assert lib.b2m_hash_capacity(1000) == 2048 and lib.b2m_hash_capacity(0) == 1024
+    assert lib.b2m_packed_weight_bytes(27, 96, 128, 0) == 27 * 2 * 128 * 64 * 2
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "box2mask_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

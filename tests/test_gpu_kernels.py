@@ -1,0 +1,336 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every C-ABI kernel against the CPU oracle on the
+same seeded inputs. Integer/index work must be bit-exact; floating point within the stated tolerance."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from box2mask_b200 import ops  # noqa: E402
+from box2mask_b200.synthetic import make_boxes, make_scene  # noqa: E402
+from oracle import nms as onms  # noqa: E402
+from oracle import sparse_ops as so  # noqa: E402
+
+DEV = "cuda"
+
+
+def _coords(xyz, b=0):
+    xyz = np.asarray(xyz, dtype=np.int32)
+    return np.concatenate([np.full((len(xyz), 1), b, np.int32), xyz], 1)
+
+
+@pytest.fixture(scope="module")
+def scene_coords():
+    s0 = make_scene(3, scale=0.45)
+    s1 = make_scene(4, scale=0.35)
+    return np.concatenate([_coords(s0["vox_coords"], 0), _coords(s1["vox_coords"], 1)], 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# coordinates, hash, kernel maps: bit-exact
+# ------------------------------------------------------------------------------------------------
+def test_hash_build_query(scene_coords):
+    c = torch.from_numpy(scene_coords).to(DEV)
+    table = ops.hash_build(c)
+    assert table.status.cpu().tolist() == [0, 0]
+    rows = ops.hash_query(table, c)
+    assert torch.equal(rows.cpu(), torch.arange(len(c), dtype=torch.int32))
+    q = c.clone()
+    q[:, 1] += 1000
+    assert int((ops.hash_query(table, q) >= 0).sum()) == 0
+    # duplicates keep the first occurrence; out-of-range coordinates are counted, not inserted
+    d = torch.cat([c[:100], c[:50], torch.tensor([[0, 40000, 0, 0]], dtype=torch.int32, device=DEV)], 0)
+    t2 = ops.hash_build(d)
+    assert t2.status.cpu().tolist() == [50, 1]
+    assert torch.equal(ops.hash_query(t2, c[:100]).cpu(), torch.arange(100, dtype=torch.int32))
+
+
+def test_empty_inputs():
+    c = torch.zeros((0, 4), dtype=torch.int32, device=DEV)
+    t = ops.hash_build(c)
+    out, parent = ops.downsample_coords(c, 2)
+    assert out.shape == (0, 4) and parent.shape == (0,)
+    nbr = ops.kernel_map_submanifold(c, 1, 3, t)
+    assert nbr.shape == (27, 0)
+
+
+@pytest.mark.parametrize("ksize,ts", [(3, 1), (5, 1)])
+def test_kernel_map_submanifold_bit_exact(scene_coords, ksize, ts):
+    c = torch.from_numpy(scene_coords).to(DEV)
+    nbr = ops.kernel_map_submanifold(c, ts, ksize, ops.hash_build(c))
+    ref = so.kernel_map_submanifold(scene_coords, ts, ksize)
+    assert np.array_equal(nbr.cpu().numpy(), ref)
+    counts = ops.kernel_map_count(nbr).cpu().numpy()
+    assert np.array_equal(counts, (ref >= 0).sum(1))
+
+
+def test_strided_levels_bit_exact(scene_coords):
+    """All 7 stride-2 levels: coordinates (sorted unique), parent rows, k2s2 maps and the k3 map at each level."""
+    cur_np, cur = scene_coords, torch.from_numpy(scene_coords).to(DEV)
+    ts = 1
+    for level in range(7):
+        out, parent = ops.downsample_coords(cur, 2 * ts)
+        ref_out, ref_parent = so.downsample_coords(cur_np, 2 * ts)
+        assert np.array_equal(out.cpu().numpy(), ref_out), level
+        assert np.array_equal(parent.cpu().numpy(), ref_parent), level
+        nd, nu = ops.kernel_map_stride2(cur, parent, len(ref_out), ts)
+        rd, ru = so.kernel_map_stride2(cur_np, ref_parent, len(ref_out), ts)
+        assert np.array_equal(nd.cpu().numpy(), rd) and np.array_equal(nu.cpu().numpy(), ru), level
+        ts *= 2
+        cur_np, cur = ref_out, out
+        nbr = ops.kernel_map_submanifold(cur, ts, 3, ops.hash_build(cur))
+        assert np.array_equal(nbr.cpu().numpy(), so.kernel_map_submanifold(cur_np, ts, 3)), level
+
+
+def test_kernel_map_negative_and_unsorted():
+    rng = np.random.default_rng(5)
+    xyz = np.unique(rng.integers(-20, 20, (3000, 3)), axis=0)
+    c_np = _coords(xyz)[rng.permutation(len(xyz))]
+    c = torch.from_numpy(c_np).to(DEV)
+    nbr = ops.kernel_map_submanifold(c, 1, 3, ops.hash_build(c))
+    assert np.array_equal(nbr.cpu().numpy(), so.kernel_map_submanifold(c_np, 1, 3))
+    out, parent = ops.downsample_coords(c, 2)
+    ro, rp = so.downsample_coords(c_np, 2)
+    assert np.array_equal(out.cpu().numpy(), ro) and np.array_equal(parent.cpu().numpy(), rp)
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution: bf16 operands, fp32 accumulation.  Tolerance: |err| <= 8e-3*|ref| + 2e-2 against an fp64
+# evaluation on the same bf16-rounded operands (bf16 output rounding is 2^-9 relative).
+# ------------------------------------------------------------------------------------------------
+def _conv_case(kvol, c_in, c_out, n, seed, real_map=None):
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    if real_map is not None:
+        nbr_np = real_map
+        n = nbr_np.shape[1]
+    elif kvol == 1:
+        nbr_np = None
+    else:
+        nbr_np = rng.integers(0, n, (kvol, n)).astype(np.int32)
+        nbr_np[rng.random((kvol, n)) < 0.55] = -1
+    x = so.bf16_round(torch.randn(n, c_in))
+    w = so.bf16_round(torch.randn(kvol, c_in, c_out) / np.sqrt(c_in * max(kvol * 0.45, 1)))
+    return nbr_np, x, w, n
+
+
+@pytest.mark.parametrize("kvol,c_in,c_out,n", [
+    (27, 32, 32, 4000), (27, 64, 64, 3000), (27, 128, 96, 6000), (27, 96, 96, 515), (8, 256, 256, 2000),
+    (27, 512, 256, 700), (27, 256, 512, 700), (27, 384, 256, 500), (125, 16, 32, 3000), (1, 32, 64, 300),
+    (1, 256, 256, 129), (27, 192, 128, 1), (8, 96, 96, 127),
+])
+def test_conv_forward(kvol, c_in, c_out, n):
+    nbr_np, x, w, n = _conv_case(kvol, c_in, c_out, n, seed=kvol + c_in)
+    ref = so.sparse_conv(x.double(), nbr_np, w.double(), n_out=n)
+    nbr = torch.from_numpy(nbr_np).to(DEV) if nbr_np is not None else None
+    colsum = torch.zeros(2 * c_out, dtype=torch.float64, device=DEV)
+    y = ops.conv_forward(x.to(DEV).to(torch.bfloat16), nbr, ops.pack_weights(w.to(DEV), 0), kvol, n, c_out, colsum)
+    err = (y.float().cpu().double() - ref).abs()
+    assert bool((err <= 8e-3 * ref.abs() + 2e-2).all()), float(err.max())
+    assert torch.allclose(colsum[:c_out].cpu(), ref.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(colsum[c_out:].cpu(), (ref * ref).sum(0), rtol=1e-4, atol=1e-2)
+
+
+def test_conv_forward_real_maps_and_dgrad(scene_coords):
+    """Real kernel maps (k3 at L0, k2s2 down/up); dgrad through the mirrored / transposed weight packing."""
+    c = torch.from_numpy(scene_coords).to(DEV)
+    nbr3 = so.kernel_map_submanifold(scene_coords, 1, 3)
+    coarse, parent = so.downsample_coords(scene_coords, 2)
+    nbr_down, nbr_up = so.kernel_map_stride2(scene_coords, parent, len(coarse), 1)
+    n = len(scene_coords)
+    torch.manual_seed(0)
+    x = so.bf16_round(torch.randn(n, 64)).double().requires_grad_(True)
+    w = so.bf16_round(torch.randn(27, 64, 96) / 30).double().requires_grad_(True)
+    y = so.sparse_conv(x, nbr3, w)
+    dy = so.bf16_round(torch.randn(n, 96)).double()
+    y.backward(dy)
+    dev_nbr = torch.from_numpy(nbr3).to(DEV)
+    got = ops.conv_forward(x.detach().float().to(DEV).to(torch.bfloat16), dev_nbr, ops.pack_weights(w.detach().float().to(DEV), 0), 27, n, 96)
+    assert bool(((got.float().cpu().double() - y.detach()).abs() <= 8e-3 * y.detach().abs() + 2e-2).all())
+    dx = ops.conv_forward(dy.float().to(DEV).to(torch.bfloat16), dev_nbr, ops.pack_weights(w.detach().float().to(DEV), 1), 27, n, 64)
+    assert bool(((dx.float().cpu().double() - x.grad).abs() <= 8e-3 * x.grad.abs() + 2e-2).all())
+    dw = ops.conv_wgrad(x.detach().float().to(DEV).to(torch.bfloat16), dy.float().to(DEV).to(torch.bfloat16), dev_nbr, 27, n)
+    assert torch.allclose(dw.cpu().double(), w.grad, rtol=2e-3, atol=2e-3 * float(w.grad.abs().max()))
+    # strided conv and its dgrad (mode 2 on nbr_up), transposed conv (mode 0 on nbr_up)
+    xs = so.bf16_round(torch.randn(n, 32)).double().requires_grad_(True)
+    ws = so.bf16_round(torch.randn(8, 32, 64) / 10).double().requires_grad_(True)
+    ys = so.sparse_conv(xs, nbr_down, ws)
+    dys = so.bf16_round(torch.randn(len(coarse), 64)).double()
+    ys.backward(dys)
+    d_down, d_up = torch.from_numpy(nbr_down).to(DEV), torch.from_numpy(nbr_up).to(DEV)
+    got = ops.conv_forward(xs.detach().float().to(DEV).to(torch.bfloat16), d_down, ops.pack_weights(ws.detach().float().to(DEV), 0), 8, len(coarse), 64)
+    assert bool(((got.float().cpu().double() - ys.detach()).abs() <= 8e-3 * ys.detach().abs() + 2e-2).all())
+    dxs = ops.conv_forward(dys.float().to(DEV).to(torch.bfloat16), d_up, ops.pack_weights(ws.detach().float().to(DEV), 2), 8, n, 32)
+    assert bool(((dxs.float().cpu().double() - xs.grad).abs() <= 8e-3 * xs.grad.abs() + 2e-2).all())
+    dws = ops.conv_wgrad(xs.detach().float().to(DEV).to(torch.bfloat16), dys.float().to(DEV).to(torch.bfloat16), d_down, 8, len(coarse))
+    assert torch.allclose(dws.cpu().double(), ws.grad, rtol=2e-3, atol=2e-3 * float(ws.grad.abs().max()))
+
+
+@pytest.mark.parametrize("kvol,c_in,c_out,n", [
+    (27, 64, 64, 3000), (27, 128, 96, 6000), (27, 96, 96, 515), (27, 32, 32, 4000), (8, 256, 256, 2000),
+    (27, 512, 256, 700), (125, 16, 32, 3000), (1, 64, 64, 1000), (8, 96, 128, 70000), (27, 192, 128, 63),
+])
+def test_conv_wgrad(kvol, c_in, c_out, n):
+    nbr_np, x, _, n = _conv_case(kvol, c_in, c_out, n, seed=kvol + c_out)
+    dy = so.bf16_round(torch.randn(n, c_out))
+    ref = torch.zeros(kvol, c_in, c_out, dtype=torch.float64)
+    if nbr_np is None:
+        ref[0] = x.double().t() @ dy.double()
+    else:
+        for k, (i, o) in enumerate(so.map_to_pairs(nbr_np)):
+            if len(i):
+                ref[k] = x.double()[i].t() @ dy.double()[o]
+    nbr = torch.from_numpy(nbr_np).to(DEV) if nbr_np is not None else None
+    dw = ops.conv_wgrad(x.to(DEV).to(torch.bfloat16), dy.to(DEV).to(torch.bfloat16), nbr, kvol, n)
+    # fp32 accumulation over up to 7e4 products + fp32 atomics across CTAs: rel 2e-3 of the largest entry
+    assert torch.allclose(dw.cpu().double(), ref, rtol=2e-3, atol=2e-3 * float(ref.abs().max()) + 1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm (+ residual + ReLU) against torch.nn.functional.batch_norm in fp32 on the same bf16 inputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,c,relu,res", [(5000, 96, True, True), (3001, 32, False, False), (700, 256, True, False),
+                                          (2, 512, False, True), (20000, 128, True, True)])
+def test_bn_forward_backward(n, c, relu, res):
+    torch.manual_seed(n + c)
+    x = so.bf16_round(torch.randn(n, c) * 2 + 0.5)
+    r = so.bf16_round(torch.randn(n, c)) if res else None
+    gamma, beta = torch.rand(c) + 0.5, torch.randn(c)
+    rm, rv = torch.zeros(c), torch.ones(c)
+    xr = x.clone().requires_grad_(True)
+    rr = r.clone().requires_grad_(True) if res else None
+    g_ = gamma.clone().requires_grad_(True)
+    b_ = beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    ref = torch.nn.functional.batch_norm(xr, rm_ref, rv_ref, g_, b_, True, 0.1, 1e-5)
+    if res:
+        ref = ref + rr
+    if relu:
+        ref = torch.relu(ref)
+    xd = x.to(DEV).to(torch.bfloat16)
+    rd = r.to(DEV).to(torch.bfloat16) if res else None
+    rm_d, rv_d = rm.to(DEV), rv.to(DEV)
+    sums = ops.colstats(xd)
+    assert torch.allclose(sums[:c].cpu(), x.double().sum(0), rtol=1e-5, atol=1e-2)
+    out, sm, si = ops.bn_forward(xd, sums, gamma.to(DEV), beta.to(DEV), rm_d, rv_d, 0.1, 1e-5, True, rd, relu)
+    # bf16 output rounding: 2^-8 relative + small absolute
+    assert torch.allclose(out.float().cpu(), ref.detach(), rtol=8e-3, atol=1e-2)
+    assert torch.allclose(rm_d.cpu(), rm_ref, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rv_d.cpu(), rv_ref, rtol=1e-4, atol=1e-5)
+    dout = so.bf16_round(torch.randn(n, c))
+    # the reference masks with ITS OWN relu output; use the device output so that near-zero ties agree
+    ref_out_mask = (out.float().cpu() > 0) if relu else None
+    ref2 = torch.nn.functional.batch_norm(xr, None, None, g_, b_, True, 0.1, 1e-5)
+    if res:
+        ref2 = ref2 + rr
+    g = dout * ref_out_mask if relu else dout
+    ref2.backward(g)
+    dx, dres, dgamma, dbeta = ops.bn_backward(xd, out, dout.to(DEV).to(torch.bfloat16), sm, si, gamma.to(DEV), relu, True, res)
+    assert torch.allclose(dx.float().cpu(), xr.grad, rtol=1e-2, atol=1e-2 * float(xr.grad.abs().max()) + 1e-3)
+    assert torch.allclose(dgamma.cpu(), g_.grad, rtol=1e-3, atol=1e-3 * float(g_.grad.abs().max()) + 1e-2)
+    assert torch.allclose(dbeta.cpu(), b_.grad, rtol=1e-3, atol=1e-3 * float(b_.grad.abs().max()) + 1e-2)
+    if res:
+        assert torch.allclose(dres.float().cpu(), rr.grad, rtol=8e-3, atol=1e-3)
+
+
+def test_bn_eval_mode():
+    torch.manual_seed(0)
+    n, c = 1000, 64
+    x = so.bf16_round(torch.randn(n, c))
+    gamma, beta, rm, rv = torch.rand(c) + 0.5, torch.randn(c), torch.randn(c) * 0.1, torch.rand(c) + 0.5
+    ref = torch.nn.functional.batch_norm(x, rm, rv, gamma, beta, False, 0.1, 1e-5)
+    out, _, _ = ops.bn_forward(x.to(DEV).to(torch.bfloat16), None, gamma.to(DEV), beta.to(DEV), rm.to(DEV), rv.to(DEV),
+                               0.1, 1e-5, False, None, False)
+    assert torch.allclose(out.float().cpu(), ref, rtol=8e-3, atol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling
+# ------------------------------------------------------------------------------------------------
+def test_segment_mean_max():
+    torch.manual_seed(0)
+    n, c, s = 20000, 96, 180
+    ids = torch.randint(0, s - 2, (n,))
+    ids[0] = s - 2                      # a segment of size 1 ...
+    ids[1:4000] = s - 1                 # ... and a large one
+    f = so.bf16_round(torch.randn(n, c))
+    fd, idd = f.to(DEV).to(torch.bfloat16), ids.to(DEV)
+    out, counts = ops.segment_mean_forward(fd, idd, s)
+    ref = so.segment_mean(f.double(), ids, s)
+    assert torch.allclose(out.cpu().double(), ref, rtol=1e-4, atol=1e-5)
+    assert torch.equal(counts.cpu().long(), torch.bincount(ids, minlength=s))
+    dout = torch.randn(s, c)
+    df = ops.segment_mean_backward(dout.to(DEV), idd, counts, n)
+    refd = dout[ids] / torch.bincount(ids, minlength=s)[ids][:, None]
+    assert torch.allclose(df.float().cpu(), refd, rtol=8e-3, atol=1e-4)
+    mx, arg = ops.segment_max_forward(fd, idd, s)
+    assert torch.equal(mx.cpu(), so.segment_max(f, ids, s))
+    assert torch.equal(f[arg.cpu().long(), torch.arange(c)[None].expand(s, c)], mx.cpu())
+
+
+# ------------------------------------------------------------------------------------------------
+# NMS / decode: bit-exact against the reference-generated golden vectors and the oracle
+# ------------------------------------------------------------------------------------------------
+def _check_nms(boxes, th, reps_ref, heat_ref, cluster_of_ref):
+    reps, cluster_of, heat = ops.aabb_nms(boxes.to(DEV), th)
+    assert np.array_equal(reps.cpu().numpy(), reps_ref)
+    assert np.array_equal(cluster_of.cpu().numpy(), cluster_of_ref)
+    assert np.array_equal(heat.cpu().numpy(), heat_ref)          # bit-exact fp32
+
+
+@pytest.mark.parametrize("name", ["nms_small", "nms_medium", "nms_lowth"])
+def test_nms_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    _check_nms(torch.from_numpy(g["boxes"]), float(g["th"]), g["reps"], g["heat"], g["cluster_of"])
+
+
+def test_nms_hand_cases(golden_dir):
+    g = np.load(os.path.join(golden_dir, "nms_cases.npz"))
+    for case in ["identical", "nested_eighth", "disjoint", "zero_volume", "chain"]:
+        _check_nms(torch.from_numpy(g[case + "_boxes"]), 0.5, g[case + "_reps"], g[case + "_heat"], g[case + "_cluster_of"])
+
+
+def test_nms_random_2k_vs_oracle():
+    boxes = make_boxes(2000, 150, seed=7)
+    reps, clusters, heat = onms.nms_clustering(boxes, 0.5)
+    cof = np.full(len(boxes), -1, np.int32)
+    for c, mem in enumerate(clusters):
+        cof[mem.numpy()] = c
+    _check_nms(boxes, 0.5, reps.numpy(), heat.numpy(), cof)
+    # score ties resolve to the lower index (stable order)
+    tb = boxes[:200].clone()
+    tb[:, 0] = torch.round(tb[:, 0] * 4) / 4
+    reps, clusters, heat = onms.nms_clustering(tb, 0.5)
+    cof = np.full(len(tb), -1, np.int32)
+    for c, mem in enumerate(clusters):
+        cof[mem.numpy()] = c
+    _check_nms(tb, 0.5, reps.numpy(), heat.numpy(), cof)
+
+
+def test_heatmap_project_and_mask_nms(golden_dir):
+    g = np.load(os.path.join(golden_dir, "nms_medium.npz"))
+    heat = torch.from_numpy(g["heat"])                 # [K, M_fg]
+    k, m_fg = heat.shape
+    rng = np.random.default_rng(0)
+    s = m_fg + 57
+    fg_mask = np.zeros(s, bool)
+    fg_mask[rng.permutation(s)[:m_fg]] = True
+    n_vox = 10007
+    seg2vox = torch.from_numpy(rng.integers(0, s, n_vox))
+    full = torch.zeros(k, s)
+    full[:, torch.from_numpy(fg_mask)] = heat
+    ref_masks = full[:, seg2vox] > 0.3
+    fg_rank = torch.full((s,), -1, dtype=torch.int32)
+    fg_rank[torch.from_numpy(fg_mask)] = torch.arange(m_fg, dtype=torch.int32)
+    packed = ops.heatmap_project(heat.to(DEV), fg_rank.to(DEV), seg2vox.to(DEV), 0.3)
+    assert torch.equal(ops.unpack_masks(packed, n_vox).cpu(), ref_masks)
+    assert torch.equal(ops.pack_masks_torch(ref_masks.to(DEV)), packed)
+    nonempty = ref_masks.sum(1) > 0
+    keep_ref = onms.mask_nms(ref_masks[nonempty], 0.6)
+    keep = ops.mask_nms(ops.pack_masks_torch(ref_masks[nonempty].to(DEV)), 0.6)
+    assert np.array_equal(torch.nonzero(keep).flatten().cpu().numpy(), keep_ref.numpy())
+    # the fixture's own mask-NMS result (masks = heat > 0.3 in fg space)
+    keep2 = ops.mask_nms(ops.pack_masks_torch((heat > 0.3).to(DEV)), 0.6)
+    assert np.array_equal(torch.nonzero(keep2).flatten().cpu().numpy(), g["mask_keep"])
