@@ -10,6 +10,41 @@ def _lib_or_raise():
     return _lib.load()
 
 
+class Profile:
+    """Launch accounting (always on) and optional CUDA-event timing of every C-ABI call (bench.py)."""
+    launches = 0          # kernels launched through the C-ABI since the last reset
+    enabled = False       # when True, each call is bracketed by CUDA events on the current stream
+    records = []          # (kind, algorithmic flops, algorithmic bytes, start event, end event)
+    _pairs = {}           # id(nbr) -> number of valid (in,out) pairs
+
+    @classmethod
+    def reset(cls):
+        cls.launches, cls.records, cls._pairs = 0, [], {}
+
+    @classmethod
+    def pairs(cls, nbr, n_out):
+        if nbr is None:
+            return n_out
+        key = (nbr.data_ptr(), tuple(nbr.shape))
+        if key not in cls._pairs:
+            cls._pairs[key] = int((nbr >= 0).sum().item())
+        return cls._pairs[key]
+
+
+def _run(kind, n_kernels, call, flops=None, nbytes=None):
+    Profile.launches += n_kernels
+    if not Profile.enabled:
+        return call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f = flops() if callable(flops) else flops
+    b = nbytes() if callable(nbytes) else nbytes
+    e0.record()
+    r = call()
+    e1.record()
+    Profile.records.append((kind, f or 0, b or 0, e0, e1))
+    return r
+
+
 def _cuda(t, dtype=None, name="tensor"):
     if not t.is_cuda:
         raise _lib.B2MError("%s must be a CUDA tensor (no CPU fallback in the product path)" % name)
@@ -43,7 +78,8 @@ def hash_build(coords):
     keys = torch.empty(cap, dtype=torch.int64, device=coords.device)
     vals = torch.empty(cap, dtype=torch.int32, device=coords.device)
     status = torch.empty(2, dtype=torch.int32, device=coords.device)
-    check(lib.b2m_hash_build(ptr(coords), n, ptr(keys), ptr(vals), cap, ptr(status), stream_ptr()), "hash_build")
+    _run("hash_build", 1, lambda: check(lib.b2m_hash_build(ptr(coords), n, ptr(keys), ptr(vals), cap, ptr(status),
+                                                           stream_ptr()), "hash_build"), nbytes=16 * n + 12 * cap)
     return HashTable(keys, vals, cap, status)
 
 
@@ -66,8 +102,9 @@ def downsample_coords(coords, new_stride):
     n_out = torch.zeros(1, dtype=torch.int32, device=coords.device)
     ws_bytes = lib.b2m_downsample_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=coords.device)
-    check(lib.b2m_downsample_coords(ptr(coords), n, int(new_stride), ptr(out), ptr(parent), ptr(n_out), ptr(ws),
-                                    ws_bytes, stream_ptr()), "downsample_coords")
+    _run("downsample_coords", 8, lambda: check(lib.b2m_downsample_coords(
+        ptr(coords), n, int(new_stride), ptr(out), ptr(parent), ptr(n_out), ptr(ws), ws_bytes, stream_ptr()),
+        "downsample_coords"), nbytes=16 * n + 4 * n)
     m = int(n_out.item())
     return out[:m].contiguous(), parent
 
@@ -76,9 +113,9 @@ def kernel_map_submanifold(coords, tensor_stride, kernel_size, table):
     lib = _lib_or_raise()
     n = coords.shape[0]
     nbr = torch.empty((kernel_size ** 3, n), dtype=torch.int32, device=coords.device)
-    check(lib.b2m_kernel_map_submanifold(ptr(coords), n, int(tensor_stride), int(kernel_size), ptr(table.keys),
-                                         ptr(table.vals), table.capacity, ptr(nbr), stream_ptr()),
-          "kernel_map_submanifold")
+    _run("kernel_map_submanifold", 1, lambda: check(lib.b2m_kernel_map_submanifold(
+        ptr(coords), n, int(tensor_stride), int(kernel_size), ptr(table.keys), ptr(table.vals), table.capacity, ptr(nbr),
+        stream_ptr()), "kernel_map_submanifold"), nbytes=16 * n + 4 * n * kernel_size ** 3)
     return nbr
 
 
@@ -87,8 +124,9 @@ def kernel_map_stride2(fine_coords, parent_row, n_coarse, fine_stride):
     n_fine = fine_coords.shape[0]
     nbr_down = torch.empty((8, n_coarse), dtype=torch.int32, device=fine_coords.device)
     nbr_up = torch.empty((8, n_fine), dtype=torch.int32, device=fine_coords.device)
-    check(lib.b2m_kernel_map_stride2(ptr(fine_coords), n_fine, ptr(parent_row), n_coarse, int(fine_stride),
-                                     ptr(nbr_down), ptr(nbr_up), stream_ptr()), "kernel_map_stride2")
+    _run("kernel_map_stride2", 1, lambda: check(lib.b2m_kernel_map_stride2(
+        ptr(fine_coords), n_fine, ptr(parent_row), n_coarse, int(fine_stride), ptr(nbr_down), ptr(nbr_up), stream_ptr()),
+        "kernel_map_stride2"), nbytes=20 * n_fine + 32 * n_fine + 32 * n_coarse)
     return nbr_down, nbr_up
 
 
@@ -106,7 +144,9 @@ def cast_pad_bf16(x, c_pad):
     lib = _lib_or_raise()
     _cuda(x, torch.float32, "x")
     out = torch.empty((x.shape[0], c_pad), dtype=torch.bfloat16, device=x.device)
-    check(lib.b2m_cast_pad_bf16(ptr(x), x.shape[0], x.shape[1], c_pad, ptr(out), stream_ptr()), "cast_pad_bf16")
+    _run("cast_pad_bf16", 1, lambda: check(lib.b2m_cast_pad_bf16(ptr(x), x.shape[0], x.shape[1], c_pad, ptr(out),
+                                                               stream_ptr()), "cast_pad_bf16"),
+         nbytes=4 * x.numel() + 2 * x.shape[0] * c_pad)
     return out
 
 
@@ -120,7 +160,9 @@ def pack_weights(kernel, mode):
         kvol, c_in, c_out = kernel.shape
     nbytes = lib.b2m_packed_weight_bytes(kvol, c_in, c_out, mode)
     packed = torch.empty(nbytes, dtype=torch.uint8, device=kernel.device)
-    check(lib.b2m_pack_weights(ptr(kernel), kvol, c_in, c_out, mode, ptr(packed), stream_ptr()), "pack_weights")
+    _run("pack_weights", 1, lambda: check(lib.b2m_pack_weights(ptr(kernel), kvol, c_in, c_out, mode, ptr(packed),
+                                                             stream_ptr()), "pack_weights"),
+         nbytes=kvol * c_in * c_out * 4 + nbytes)
     return packed
 
 
@@ -129,8 +171,10 @@ def conv_forward(x, nbr, packed_w, kvol, n_out, c_n, colsum=None):
     lib = _lib_or_raise()
     _cuda(x, torch.bfloat16, "x")
     y = torch.empty((n_out, c_n), dtype=torch.bfloat16, device=x.device)
-    check(lib.b2m_conv_forward(ptr(x), x.shape[0], x.shape[1], ptr(nbr), kvol, n_out, ptr(packed_w), c_n, ptr(y),
-                               ptr(colsum), stream_ptr()), "conv_forward")
+    _run("conv_forward", 1, lambda: check(lib.b2m_conv_forward(
+        ptr(x), x.shape[0], x.shape[1], ptr(nbr), kvol, n_out, ptr(packed_w), c_n, ptr(y), ptr(colsum), stream_ptr()),
+        "conv_forward"), flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] * c_n,
+        nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] + 2.0 * n_out * c_n)
     return y
 
 
@@ -140,8 +184,10 @@ def conv_wgrad(x, dy, nbr, kvol, n_out):
     _cuda(dy, torch.bfloat16, "dy")
     c_in, c_out = x.shape[1], dy.shape[1]
     dw = torch.zeros((kvol, c_in, c_out), dtype=torch.float32, device=x.device)
-    check(lib.b2m_conv_wgrad(ptr(x), x.shape[0], c_in, ptr(dy), c_out, ptr(nbr), kvol, n_out, ptr(dw), stream_ptr()),
-          "conv_wgrad")
+    _run("conv_wgrad", 1, lambda: check(lib.b2m_conv_wgrad(
+        ptr(x), x.shape[0], c_in, ptr(dy), c_out, ptr(nbr), kvol, n_out, ptr(dw), stream_ptr()), "conv_wgrad"),
+        flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * c_in * c_out,
+        nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * (c_in + c_out))
     return dw
 
 
@@ -152,7 +198,8 @@ def colstats(x):
     lib = _lib_or_raise()
     _cuda(x, torch.bfloat16, "x")
     sums = torch.zeros(2 * x.shape[1], dtype=torch.float64, device=x.device)
-    check(lib.b2m_colstats(ptr(x), x.shape[0], x.shape[1], ptr(sums), stream_ptr()), "colstats")
+    _run("colstats", 1, lambda: check(lib.b2m_colstats(ptr(x), x.shape[0], x.shape[1], ptr(sums), stream_ptr()),
+                                      "colstats"), nbytes=2 * x.numel())
     return sums
 
 
@@ -164,9 +211,11 @@ def bn_forward(x, sums, gamma, beta, running_mean, running_var, momentum, eps, t
     out = torch.empty_like(x)
     save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
     save_invstd = torch.empty(c, dtype=torch.float32, device=x.device)
-    check(lib.b2m_bn_forward(ptr(x), n, n if n_stat is None else int(n_stat), c, ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
-                             float(momentum), float(eps), int(bool(training)), ptr(residual), int(bool(relu)), ptr(out),
-                             ptr(save_mean), ptr(save_invstd), stream_ptr()), "bn_forward")
+    _run("bn_forward", 2, lambda: check(lib.b2m_bn_forward(
+        ptr(x), n, n if n_stat is None else int(n_stat), c, ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean),
+        ptr(running_var), float(momentum), float(eps), int(bool(training)), ptr(residual), int(bool(relu)), ptr(out),
+        ptr(save_mean), ptr(save_invstd), stream_ptr()), "bn_forward"),
+        nbytes=2 * x.numel() * (3 if residual is not None else 2))
     return out, save_mean, save_invstd
 
 
@@ -175,17 +224,19 @@ def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, wan
     lib = _lib_or_raise()
     n, c = x.shape
     red = torch.zeros(2 * c, dtype=torch.float64, device=x.device)
-    check(lib.b2m_bn_backward_reduce(ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd),
-                                     int(bool(relu)), ptr(red), stream_ptr()), "bn_backward_reduce")
+    _run("bn_backward_reduce", 1, lambda: check(lib.b2m_bn_backward_reduce(
+        ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd), int(bool(relu)), ptr(red), stream_ptr()),
+        "bn_backward_reduce"), nbytes=2 * x.numel() * (3 if relu else 2))
     if reduce_hook is not None:
         reduce_hook(red)  # SyncBN: all-reduce (sum_g, sum_g*xhat) over ranks
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dresidual else None
     dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
     dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
-    check(lib.b2m_bn_backward_apply(ptr(x), ptr(out), ptr(dout), n, n if n_stat is None else int(n_stat), c, ptr(save_mean), ptr(save_invstd), ptr(gamma),
-                                    ptr(red), int(bool(relu)), int(bool(training)), ptr(dx), ptr(dres), ptr(dgamma),
-                                    ptr(dbeta), stream_ptr()), "bn_backward_apply")
+    _run("bn_backward_apply", 1, lambda: check(lib.b2m_bn_backward_apply(
+        ptr(x), ptr(out), ptr(dout), n, n if n_stat is None else int(n_stat), c, ptr(save_mean), ptr(save_invstd),
+        ptr(gamma), ptr(red), int(bool(relu)), int(bool(training)), ptr(dx), ptr(dres), ptr(dgamma), ptr(dbeta),
+        stream_ptr()), "bn_backward_apply"), nbytes=2 * x.numel() * ((3 if relu else 2) + (2 if want_dresidual else 1)))
     return dx, dres, dgamma, dbeta
 
 
@@ -198,8 +249,9 @@ def segment_mean_forward(f, ids, s):
     _cuda(ids, torch.int64, "ids")
     out = torch.empty((s, f.shape[1]), dtype=torch.float32, device=f.device)
     counts = torch.empty(s, dtype=torch.float32, device=f.device)
-    check(lib.b2m_segment_mean_forward(ptr(f), ptr(ids), f.shape[0], f.shape[1], s, ptr(out), ptr(counts),
-                                       stream_ptr()), "segment_mean_forward")
+    _run("segment_mean_forward", 2, lambda: check(lib.b2m_segment_mean_forward(
+        ptr(f), ptr(ids), f.shape[0], f.shape[1], s, ptr(out), ptr(counts), stream_ptr()), "segment_mean_forward"),
+        nbytes=2 * f.numel() + 8 * f.shape[0] + 4 * s * f.shape[1])
     return out, counts
 
 
@@ -207,8 +259,9 @@ def segment_mean_backward(dout, ids, counts, n):
     lib = _lib_or_raise()
     _cuda(dout, torch.float32, "dout")
     df = torch.empty((n, dout.shape[1]), dtype=torch.bfloat16, device=dout.device)
-    check(lib.b2m_segment_mean_backward(ptr(dout), ptr(ids), ptr(counts), n, dout.shape[1], ptr(df), stream_ptr()),
-          "segment_mean_backward")
+    _run("segment_mean_backward", 1, lambda: check(lib.b2m_segment_mean_backward(
+        ptr(dout), ptr(ids), ptr(counts), n, dout.shape[1], ptr(df), stream_ptr()), "segment_mean_backward"),
+        nbytes=2 * n * dout.shape[1] + 8 * n + 4 * dout.numel())
     return df
 
 

@@ -1,0 +1,133 @@
+"""GPU parity of the whole network: product SelectionNet (CUDA, bf16 activations) against
+ (a) golden vectors produced by the reference's own model code in fp32 (tests/golden/selection_net_small.npz),
+ (b) the CPU oracle with bf16 emulation at the same storage points (tight), forward, losses and gradients."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from box2mask_b200.model import Model  # noqa: E402
+from box2mask_b200.selection_net import default_config  # noqa: E402
+from box2mask_b200.synthetic import label_maps  # noqa: E402
+from oracle.selection_net import OracleNet, detection_loss, seeded_state_dict  # noqa: E402
+
+DEV = "cuda"
+
+
+def _cos(a, b):
+    return float(torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0))
+
+
+@pytest.fixture(scope="module")
+def setup(golden_dir):
+    g = np.load(os.path.join(golden_dir, "selection_net_small.npz"))
+    batch = {k: torch.from_numpy(g[k]) for k in ("vox_coords", "vox_features", "pooling_ids", "input_location",
+                                                   "gt_bb_offsets", "gt_bb_bounds", "gt_semantics", "fg_instances")}
+    cfg = default_config(mlp_bb_scores_start_epoch=0)
+    valid, id2idx, is_fg = label_maps(20)
+    model = Model(cfg, valid, id2idx, None, is_fg, device=DEV)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert list(shapes.keys()) == g["keys"].tolist()
+    sd = seeded_state_dict(shapes, seed=0)
+    model.load_state_dict(sd)
+    return g, batch, cfg, model, sd, id2idx
+
+
+def test_eval_forward_vs_reference_golden_and_oracle(setup):
+    g, batch, cfg, model, sd, _ = setup
+    model.eval()
+    pred = model.get_prediction(batch, with_grad=False, to_cpu=True, min_size=False)
+    with torch.no_grad():
+        emu = OracleNet(sd, cfg, training=False, emulate_bf16=True).forward(
+            batch["vox_coords"].numpy(), batch["vox_features"], batch["pooling_ids"])
+    for head in cfg.network_heads:
+        ref = torch.from_numpy(g["eval_" + head])
+        scale = float(ref.abs().max())
+        # vs fp32 reference code: bf16 storage through ~80 layers. Stated tolerance: cosine >= 0.999 and
+        # max abs error <= 3% of the output range.
+        assert _cos(pred[head], ref) >= 0.999, (head, _cos(pred[head], ref))
+        assert float((pred[head] - ref).abs().max()) <= 0.03 * scale, (head, float((pred[head] - ref).abs().max()), scale)
+        # vs the oracle rounding at the same points: only accumulation order differs
+        assert _cos(pred[head], emu[head]) >= 0.9999, (head, _cos(pred[head], emu[head]))
+        assert float((pred[head] - emu[head]).abs().max()) <= 0.01 * scale, (head, float((pred[head] - emu[head]).abs().max()))
+
+
+def test_train_forward_loss_backward_vs_oracle(setup):
+    g, batch, cfg, model, sd, id2idx = setup
+    model.load_state_dict(sd)
+    model.train()
+    for p in model.parameters():
+        p.grad = None
+    losses, pred = model.compute_loss_detection(batch, epoch=0)
+    losses["optimization_loss"].backward()
+    osd = {k: v.clone() for k, v in sd.items()}
+    for k, v in osd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    out = OracleNet(osd, cfg, training=True, emulate_bf16=True).forward(
+        batch["vox_coords"].numpy(), batch["vox_features"], batch["pooling_ids"])
+    ol = detection_loss(out, batch, cfg, 0, id2idx)
+    ol["optimization_loss"].backward()
+    report = {}
+    for head in cfg.network_heads:
+        report[head] = _cos(pred[head].detach().cpu(), out[head].detach())
+    # training-mode BatchNorm over the 2-6 rows of the deepest levels amplifies rounding; tolerance is looser
+    for head, c in report.items():
+        assert c >= 0.99, report
+    for k in ("optimization_loss", "offset_loss", "bounds_loss", "bb_score_loss", "semantics_loss"):
+        a, b = float(losses[k]), float(ol[k])
+        assert abs(a - b) <= 0.03 * max(1.0, abs(b)), (k, a, b)
+        # and the reference code's own fp32 loss
+        assert abs(a - float(g["loss_" + k])) <= 0.05 * max(1.0, abs(float(g["loss_" + k]))), (k, a, float(g["loss_" + k]))
+    params = dict(model.net.named_parameters())
+    coss = {}
+    for key in ("conv0p1s1.kernel", "block1.0.conv1.kernel", "block8.1.conv2.kernel", "convtr7p2s2.kernel",
+                "conv2p2s2.kernel", "block2.0.downsample.0.kernel", "bn0.bn.weight", "block8.1.norm2.bn.bias",
+                "mlp_offsets.6.kernel", "block5.0.conv1.kernel", "added_block1.0.conv1.kernel"):
+        coss[key] = _cos(params[key].grad.cpu(), osd[key].grad)
+    print("grad cosines:", coss)
+    for key, c in coss.items():
+        assert c >= 0.97, coss
+    # running statistics were updated like BatchNorm1d does
+    assert int(model.net.bn0.bn.num_batches_tracked) == 1
+    assert float((model.net.bn0.bn.running_mean.cpu() - sd["bn0.bn.running_mean"]).abs().max()) > 0
+
+
+def test_drop_in_module_surface(setup):
+    """The reference-style module-by-module call sequence (conv -> bn -> relu, `out += residual`, ME.cat,
+    re-keyed SparseTensor + global pooling) gives the same result as the fused path."""
+    import box2mask_b200
+    ME = box2mask_b200.install_as_minkowski_engine()
+    g, batch, cfg, model, sd, _ = setup
+    net = model.net
+    net.eval()
+    with torch.no_grad():
+        x = ME.SparseTensor(batch["vox_features"], batch["vox_coords"], device=DEV)
+        out = net.relu(net.bn0(net.conv0p1s1(x)))
+        fused = ME.conv_bn_act(net.conv0p1s1, net.bn0, x, relu=True)
+        assert torch.equal(out.F, fused.F)
+        o2 = net.relu(net.bn1(net.conv1p1s2(out)))
+        blk = net.block1[0]
+        r = blk.relu(blk.norm1(blk.conv1(o2)))
+        r = blk.norm2(blk.conv2(r))
+        r += o2
+        r = blk.relu(r)
+        assert float((r.F.float() - blk(o2).F.float()).abs().max()) <= 0.02 * float(r.F.float().abs().max())
+        coarse = ME.SparseTensor(torch.randn(len(o2), 96, device=DEV).to(torch.bfloat16),
+                                 coordinate_manager=o2.coordinate_manager, tensor_stride=2)
+        up = net.relu(net.bntr7(net.convtr7p2s2(coarse)))
+        assert up.F.shape == (len(x), 96) and up.tensor_stride == [1, 1, 1]
+        cat = ME.cat(up, out)
+        assert cat.F.shape[1] == 128
+        # re-keyed tensor + global average pooling == segment mean (detection_net.py:345-352)
+        feats = net.block8(cat)
+        feats.C[:, 0] = batch["pooling_ids"].to(DEV).int()
+        pooled = net.global_avg_pool(ME.SparseTensor(feats.F, feats.C, device=DEV))
+        s = int(batch["pooling_ids"].max()) + 1
+        assert pooled.F.shape == (s, 96)
+        ref = torch.zeros(s, 96, device=DEV).index_add_(0, batch["pooling_ids"].to(DEV), feats.F.float())
+        ref = ref / torch.bincount(batch["pooling_ids"].to(DEV), minlength=s)[:, None]
+        assert torch.allclose(pooled.F, ref, rtol=1e-4, atol=1e-5)
