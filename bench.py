@@ -250,7 +250,7 @@ def main():
     torch.cuda.synchronize()
     ops.Profile.enabled = False
     agg = {}
-    for kind, fl, by, a, b_ in ops.Profile.records:
+    for kind, fl, by, a, b_, _tag in ops.Profile.records:
         d = agg.setdefault(kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
         d["ms"] += a.elapsed_time(b_); d["flops"] += fl; d["bytes"] += by; d["launches"] += 1
     pk = peaks()

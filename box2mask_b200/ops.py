@@ -31,7 +31,7 @@ class Profile:
         return cls._pairs[key]
 
 
-def _run(kind, n_kernels, call, flops=None, nbytes=None):
+def _run(kind, n_kernels, call, flops=None, nbytes=None, tag=""):
     Profile.launches += n_kernels
     if not Profile.enabled:
         return call()
@@ -41,7 +41,7 @@ def _run(kind, n_kernels, call, flops=None, nbytes=None):
     e0.record()
     r = call()
     e1.record()
-    Profile.records.append((kind, f or 0, b or 0, e0, e1))
+    Profile.records.append((kind, f or 0, b or 0, e0, e1, tag))
     return r
 
 
@@ -174,7 +174,8 @@ def conv_forward(x, nbr, packed_w, kvol, n_out, c_n, colsum=None):
     _run("conv_forward", 1, lambda: check(lib.b2m_conv_forward(
         ptr(x), x.shape[0], x.shape[1], ptr(nbr), kvol, n_out, ptr(packed_w), c_n, ptr(y), ptr(colsum), stream_ptr()),
         "conv_forward"), flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] * c_n,
-        nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] + 2.0 * n_out * c_n)
+        nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] + 2.0 * n_out * c_n,
+        tag="k%d %d->%d n_in=%d n_out=%d" % (kvol, x.shape[1], c_n, x.shape[0], n_out))
     return y
 
 
@@ -187,7 +188,8 @@ def conv_wgrad(x, dy, nbr, kvol, n_out):
     _run("conv_wgrad", 1, lambda: check(lib.b2m_conv_wgrad(
         ptr(x), x.shape[0], c_in, ptr(dy), c_out, ptr(nbr), kvol, n_out, ptr(dw), stream_ptr()), "conv_wgrad"),
         flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * c_in * c_out,
-        nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * (c_in + c_out))
+        nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * (c_in + c_out),
+        tag="k%d %d->%d n_in=%d n_out=%d" % (kvol, c_in, c_out, x.shape[0], n_out))
     return dw
 
 

@@ -1,0 +1,56 @@
+"""One training step of the bench workload between cudaProfilerStart/Stop (for ncu --profile-from-start off),
+plus a per-launch CUDA-event dump of every C-ABI call (kind, shape tag, ms, algorithmic TFLOP/s or GB/s).
+
+    python tools/profile_step.py [--scenes 8] [--scale 0.84] [--dump gpurun_out/launches.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from box2mask_b200 import ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scenes", type=int, default=8)
+ap.add_argument("--scale", type=float, default=0.84)
+ap.add_argument("--dump", default=None)
+ap.add_argument("--warm", type=int, default=2)
+args = ap.parse_args()
+
+dev = "cuda:0"
+scenes = bench.make_scenes(args.scenes, seed=10, scale=args.scale)
+rng = np.random.default_rng(0)
+model, opt, cfg = bench.build_model(dev, multigpu=False)
+batch = bench.jitter_batch(scenes, rng)
+batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+for _ in range(args.warm):
+    bench.train_step(model, opt, batch)
+torch.cuda.synchronize()
+if args.dump:
+    ops.Profile.reset()
+    ops.Profile.enabled = True
+torch.cuda.profiler.start()
+bench.train_step(model, opt, batch)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+if args.dump:
+    ops.Profile.enabled = False
+    rows = []
+    for rec in ops.Profile.records:
+        kind, fl, by, a, b = rec[:5]
+        ms = a.elapsed_time(b)
+        rows.append({"kind": kind, "tag": rec[5] if len(rec) > 5 else "", "ms": ms,
+                     "tflops": fl / (ms * 1e-3) / 1e12 if fl and ms else None,
+                     "gbs": by / (ms * 1e-3) / 1e9 if by and ms else None, "gflop": fl / 1e9})
+    json.dump(rows, open(args.dump, "w"))
+    rows.sort(key=lambda r: -r["ms"])
+    print("total ms in C-ABI calls: %.2f over %d calls" % (sum(r["ms"] for r in rows), len(rows)))
+    for r in rows[:45]:
+        print("%-22s %-44s %8.3f ms  %s" % (r["kind"], r["tag"], r["ms"],
+              ("%.1f TF/s" % r["tflops"]) if r["tflops"] else (("%.0f GB/s" % r["gbs"]) if r["gbs"] else "")))
