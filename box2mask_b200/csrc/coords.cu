@@ -145,6 +145,53 @@ __global__ void kmap_count_kernel(const int32_t* __restrict__ nbr, int64_t n_out
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(counts + k, local);
 }
 
+// ---- kernel-map sorting: rows ordered by (block of rows, occupancy bit mask) so that the rows of a 128-row
+// ---- MMA tile share their set of present offsets (whole (tile, offset) blocks can then be skipped) ----
+__global__ void kmap_rowmask_kernel(const int32_t* __restrict__ nbr, int kvol, int64_t n_out, int block_rows,
+                                    unsigned long long* __restrict__ keys, int32_t* __restrict__ idx) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  unsigned int m = 0;
+  for (int k = 0; k < kvol; ++k) m |= (unsigned int)(__ldg(nbr + (int64_t)k * n_out + o) >= 0) << k;
+  keys[o] = ((unsigned long long)(o / block_rows) << 32) | m;
+  idx[o] = (int32_t)o;
+}
+
+__global__ void kmap_permute_kernel(const int32_t* __restrict__ nbr, int kvol, int64_t n_out,
+                                    const int32_t* __restrict__ order, int32_t* __restrict__ nbr_sorted) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_out * kvol) return;
+  const int64_t j = gid % n_out;
+  const int64_t k = gid / n_out;
+  nbr_sorted[gid] = __ldg(nbr + k * n_out + __ldg(order + j));
+}
+
+// group_mask[g][w]: bit (k % 32) of word (k / 32) set iff some row of the 64-row group g has offset k
+__global__ void kmap_groupmask_kernel(const int32_t* __restrict__ nbr_sorted, int kvol, int64_t n_out, int words,
+                                      uint32_t* __restrict__ group_mask) {
+  const int64_t g = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  __shared__ uint32_t sm[4];
+  if (threadIdx.x < 4) sm[threadIdx.x] = 0;
+  __syncthreads();
+  for (int k = warp; k < kvol; k += nwarps) {
+    const int64_t r = g * 64 + lane;
+    bool v = false;
+    if (r < n_out) v = __ldg(nbr_sorted + (int64_t)k * n_out + r) >= 0;
+    if (r + 32 < n_out) v = v || (__ldg(nbr_sorted + (int64_t)k * n_out + r + 32) >= 0);
+    const unsigned any = __ballot_sync(0xffffffffu, v);
+    if (lane == 0 && any) atomicOr(&sm[k >> 5], 1u << (k & 31));
+  }
+  __syncthreads();
+  if (threadIdx.x < words) group_mask[g * words + threadIdx.x] = sm[threadIdx.x];
+}
+
+__global__ void iota_kernel(int32_t* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)i;
+}
+
 struct DownsampleWs {
   size_t off_keys_in, off_keys_out, off_idx_in, off_idx_out, off_flags, off_rank, off_status, off_cub, cub_bytes, total;
 };
@@ -286,7 +333,48 @@ extern "C" int b2m_kernel_map_count(const int32_t* nbr, int32_t kvol, int64_t n_
   return B2M_OK;
 }
 
-extern "C" int b2m_version(void) { return 1; }
+extern "C" size_t b2m_kernel_map_sort_workspace_bytes(int64_t n_out) { return downsample_ws(n_out < 1 ? 1 : n_out).total; }
+
+extern "C" int b2m_kernel_map_sort(const int32_t* nbr, int32_t kvol, int64_t n_out, int32_t block_rows, int32_t* order,
+                                   int32_t* nbr_sorted, uint32_t* group_mask, void* workspace, size_t workspace_bytes,
+                                   b2m_stream_t stream) {
+  if (n_out == 0) return B2M_OK;
+  if (!nbr || !order || !nbr_sorted || !group_mask || kvol <= 0 || kvol > 128 || n_out < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (n_out >= (int64_t)1 << 31) return B2M_ERR_UNSUPPORTED_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int words = (kvol + 31) / 32;
+  const int blocks = cdiv(n_out, 256);
+  const bool do_sort = block_rows > 0 && kvol <= 32;
+  if (do_sort) {
+    if (!workspace) return B2M_ERR_INVALID_ARGUMENT;
+    const DownsampleWs w = downsample_ws(n_out);
+    if (workspace_bytes < w.total) return B2M_ERR_WORKSPACE_TOO_SMALL;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    auto* keys_in = reinterpret_cast<unsigned long long*>(ws + w.off_keys_in);
+    auto* keys_out = reinterpret_cast<unsigned long long*>(ws + w.off_keys_out);
+    auto* idx_in = reinterpret_cast<int32_t*>(ws + w.off_idx_in);
+    kmap_rowmask_kernel<<<blocks, 256, 0, st>>>(nbr, kvol, n_out, block_rows, keys_in, idx_in);
+    B2M_CHECK_LAUNCH();
+    int64_t nblk = (n_out + block_rows - 1) / block_rows;
+    int end_bit = 32;
+    while (((int64_t)1 << (end_bit - 32)) < nblk) ++end_bit;
+    size_t cub_bytes = w.cub_bytes;
+    if (cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, keys_in, keys_out, idx_in, order, (int)n_out, 0, end_bit, st) != cudaSuccess)
+      return B2M_ERR_CUDA_LAUNCH;
+    kmap_permute_kernel<<<cdiv(n_out * kvol, 256), 256, 0, st>>>(nbr, kvol, n_out, order, nbr_sorted);
+    B2M_CHECK_LAUNCH();
+  } else {
+    iota_kernel<<<blocks, 256, 0, st>>>(order, n_out);
+    B2M_CHECK_LAUNCH();
+    if (nbr_sorted != nbr)
+      if (cudaMemcpyAsync(nbr_sorted, nbr, (size_t)kvol * n_out * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  }
+  kmap_groupmask_kernel<<<(unsigned)((n_out + 63) / 64), 256, 0, st>>>(nbr_sorted, kvol, n_out, words, group_mask);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" int b2m_version(void) { return 2; }
 
 extern "C" const char* b2m_error_string(int code) {
   switch (code) {

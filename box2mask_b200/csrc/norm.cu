@@ -57,23 +57,41 @@ colreduce_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ ou
     for (int i = 0; i < 8; ++i) { mu[i] = mean[g * 8 + i]; is[i] = invstd[g * 8 + i]; }
   }
   if (rl < rpp) {
-    for (int64_t r = (int64_t)blockIdx.x * rpp + rl; r < n; r += (int64_t)gridDim.x * rpp) {
-      float xv[8];
-      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + r * c) + g), xv);
-      if (MODE == 0) {
+    const int64_t rstep = (int64_t)gridDim.x * rpp;
+    for (int64_t r0 = (int64_t)blockIdx.x * rpp + rl; r0 < n; r0 += 2 * rstep) {
+      uint4 xr[2], gr[2], orr[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a[i] += xv[i]; b[i] = fmaf(xv[i], xv[i], b[i]); }
-      } else {
-        float gv[8];
-        bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(dout + r * c) + g), gv);
-        if (relu) {
-          float ov[8];
-          bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(out + r * c) + g), ov);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) if (!(ov[i] > 0.f)) gv[i] = 0.f;
+      for (int u = 0; u < 2; ++u) {
+        const int64_t r = r0 + u * rstep;
+        if (r < n) {
+          xr[u] = __ldg(reinterpret_cast<const uint4*>(x + r * c) + g);
+          if (MODE == 1) {
+            gr[u] = __ldg(reinterpret_cast<const uint4*>(dout + r * c) + g);
+            if (relu) orr[u] = __ldg(reinterpret_cast<const uint4*>(out + r * c) + g);
+          }
         }
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a[i] += gv[i]; b[i] = fmaf(gv[i], (xv[i] - mu[i]) * is[i], b[i]); }
+      for (int u = 0; u < 2; ++u) {
+        const int64_t r = r0 + u * rstep;
+        if (r >= n) continue;
+        float xv[8];
+        bf16x8_to_float(xr[u], xv);
+        if (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a[i] += xv[i]; b[i] = fmaf(xv[i], xv[i], b[i]); }
+        } else {
+          float gv[8];
+          bf16x8_to_float(gr[u], gv);
+          if (relu) {
+            float ov[8];
+            bf16x8_to_float(orr[u], ov);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (!(ov[i] > 0.f)) gv[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a[i] += gv[i]; b[i] = fmaf(gv[i], (xv[i] - mu[i]) * is[i], b[i]); }
+        }
       }
     }
 #pragma unroll
@@ -126,27 +144,43 @@ bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int c, const float* _
                 const uint16_t* __restrict__ residual, int relu, uint16_t* __restrict__ out) {
   const int G = c / 8;
   const int64_t total = n * G;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(v % G);
-    float xv[8], o[8];
-    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x) + v), xv);
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < total;
+       base += (int64_t)gridDim.x * blockDim.x * U) {
+    uint4 xr[U], rr[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int j = g * 8 + i;
-      const float sc = __ldg(gamma + j) * __ldg(invstd + j);
-      o[i] = fmaf(xv[i] - __ldg(mean + j), sc, __ldg(beta + j));
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + (int64_t)u * blockDim.x;
+      if (v < total) {
+        xr[u] = __ldg(reinterpret_cast<const uint4*>(x) + v);
+        if (residual) rr[u] = __ldg(reinterpret_cast<const uint4*>(residual) + v);
+      }
     }
-    if (residual) {
-      float rv[8];
-      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(residual) + v), rv);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += rv[i];
-    }
-    if (relu) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + (int64_t)u * blockDim.x;
+      if (v >= total) continue;
+      const int g = (int)(v % G);
+      float xv[8], o[8];
+      bf16x8_to_float(xr[u], xv);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+      for (int i = 0; i < 8; ++i) {
+        const int j = g * 8 + i;
+        const float sc = __ldg(gamma + j) * __ldg(invstd + j);
+        o[i] = fmaf(xv[i] - __ldg(mean + j), sc, __ldg(beta + j));
+      }
+      if (residual) {
+        float rv[8];
+        bf16x8_to_float(rr[u], rv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += rv[i];
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+      }
+      reinterpret_cast<uint4*>(out)[v] = float_to_bf16x8(o);
     }
-    reinterpret_cast<uint4*>(out)[v] = float_to_bf16x8(o);
   }
 }
 
@@ -165,33 +199,50 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__
     }
   }
   const float inv_n = 1.f / (float)n_stat;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(v % G);
-    float xv[8], gv[8], o[8];
-    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x) + v), xv);
-    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(dout) + v), gv);
-    if (relu) {
-      float ov[8];
-      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(out) + v), ov);
+  constexpr int U = 2;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < total;
+       base += (int64_t)gridDim.x * blockDim.x * U) {
+    uint4 xr[U], gr[U], orr[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) if (!(ov[i] > 0.f)) gv[i] = 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int j = g * 8 + i;
-      const float is = __ldg(invstd + j);
-      const float sc = __ldg(gamma + j) * is;
-      if (training) {
-        const float xh = (xv[i] - __ldg(mean + j)) * is;
-        const float sg = (float)red[j] * inv_n;
-        const float sgx = (float)red[c + j] * inv_n;
-        o[i] = sc * (gv[i] - sg - xh * sgx);
-      } else {
-        o[i] = sc * gv[i];
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + (int64_t)u * blockDim.x;
+      if (v < total) {
+        xr[u] = __ldg(reinterpret_cast<const uint4*>(x) + v);
+        gr[u] = __ldg(reinterpret_cast<const uint4*>(dout) + v);
+        if (relu) orr[u] = __ldg(reinterpret_cast<const uint4*>(out) + v);
       }
     }
-    reinterpret_cast<uint4*>(dx)[v] = float_to_bf16x8(o);
-    if (dres) reinterpret_cast<uint4*>(dres)[v] = float_to_bf16x8(gv);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + (int64_t)u * blockDim.x;
+      if (v >= total) continue;
+      const int g = (int)(v % G);
+      float xv[8], gv[8], o[8];
+      bf16x8_to_float(xr[u], xv);
+      bf16x8_to_float(gr[u], gv);
+      if (relu) {
+        float ov[8];
+        bf16x8_to_float(orr[u], ov);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (!(ov[i] > 0.f)) gv[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = g * 8 + i;
+        const float is = __ldg(invstd + j);
+        const float sc = __ldg(gamma + j) * is;
+        if (training) {
+          const float xh = (xv[i] - __ldg(mean + j)) * is;
+          const float sg = (float)__ldg(red + j) * inv_n;
+          const float sgx = (float)__ldg(red + c + j) * inv_n;
+          o[i] = sc * (gv[i] - sg - xh * sgx);
+        } else {
+          o[i] = sc * gv[i];
+        }
+      }
+      reinterpret_cast<uint4*>(dx)[v] = float_to_bf16x8(o);
+      if (dres) reinterpret_cast<uint4*>(dres)[v] = float_to_bf16x8(gv);
+    }
   }
 }
 
@@ -203,7 +254,7 @@ static int reduce_grid(int64_t n, int c) {
   return (int)blocks;
 }
 static int apply_grid(int64_t total_vec) {
-  int64_t blocks = (total_vec + kNormThreads - 1) / kNormThreads;
+  int64_t blocks = (total_vec + kNormThreads * 4 - 1) / (kNormThreads * 4);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   return (int)blocks;

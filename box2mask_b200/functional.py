@@ -12,8 +12,8 @@ class SparseConvFn(torch.autograd.Function):
     """y = sum_k x[nbr_fwd[k]] @ W[k]  (reference: MinkowskiConvolution / MinkowskiConvolutionTranspose forward,
     /root/reference/models/detection_net.py:235-337; backward = autograd of the same, models/training.py:68).
 
-    nbr_fwd : dense neighbour table of the forward map [K, n_out] (None = identity, K == 1)
-    nbr_bwd : table of the transposed relation [K, n_in] used for dgrad
+    nbr_fwd : sorted KernelMap (ops.KernelMap) of the forward relation over n_out rows (None = identity, K == 1)
+    nbr_bwd : sorted KernelMap of the transposed relation over n_in rows, used for dgrad
     dgrad_mode : weight packing for dgrad (1 = mirrored offsets, same coordinates; 2 = strided / transposed)
     Returns (y bf16 [n_out, c_out], colsum f64 [2*c_out] = per-column (sum, sum of squares) of y).
     """

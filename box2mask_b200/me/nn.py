@@ -74,14 +74,14 @@ class _ConvBase(nn.Module):
                 return nbr, nbr, 1, len(x), ts
             if s == 2 and k == 2:
                 nbr_down, nbr_up = cm.stride2_maps(ts)
-                return nbr_down, nbr_up, 2, nbr_down.shape[1], 2 * ts
+                return nbr_down, nbr_up, 2, nbr_down.n_out, 2 * ts
         else:
             if s == 2 and k == 2:
                 if ts % 2 != 0 or (ts // 2) not in cm.stride2:
                     raise RuntimeError("transposed convolution needs the cached finer coordinate map "
                                        "(the encoder's stride-%d level)" % (ts // 2))
                 nbr_down, nbr_up = cm.stride2[ts // 2]
-                return nbr_up, nbr_down, 2, nbr_up.shape[1], ts // 2
+                return nbr_up, nbr_down, 2, nbr_up.n_out, ts // 2
         raise NotImplementedError("convolution kernel_size=%d stride=%d transpose=%s is not on the Box2Mask path"
                                   % (k, s, self.is_transpose))
 

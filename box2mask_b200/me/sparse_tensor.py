@@ -17,8 +17,8 @@ class CoordinateManager:
     def __init__(self, coords):
         self.levels = {1: coords}       # stride -> int32 [N,4] on device
         self.tables = {}                # stride -> ops.HashTable
-        self.sub_maps = {}              # (stride, ksize) -> nbr [K^3, N]
-        self.stride2 = {}               # fine stride -> (parent_row, nbr_down, nbr_up)
+        self.sub_maps = {}              # (stride, ksize) -> sorted ops.KernelMap over the level's rows
+        self.stride2 = {}               # fine stride -> (KernelMap down [8, N_coarse], KernelMap up [8, N_fine])
 
     def coords(self, stride):
         return self.levels[stride]
@@ -32,17 +32,18 @@ class CoordinateManager:
     def submanifold_map(self, stride, ksize):
         key = (stride, ksize)
         if key not in self.sub_maps:
-            self.sub_maps[key] = ops.kernel_map_submanifold(self.levels[stride], stride, ksize, self.table(stride))
+            nbr = ops.kernel_map_submanifold(self.levels[stride], stride, ksize, self.table(stride))
+            self.sub_maps[key] = ops.sort_kernel_map(nbr)
         return self.sub_maps[key]
 
     def stride2_maps(self, fine_stride):
-        """Creates the coarse level (2*fine_stride) if needed; returns (nbr_down [8,Nc], nbr_up [8,Nf])."""
+        """Creates the coarse level (2*fine_stride) if needed; returns (KernelMap down, KernelMap up)."""
         if fine_stride not in self.stride2:
             fine = self.levels[fine_stride]
             coarse, parent = ops.downsample_coords(fine, 2 * fine_stride)
             self.levels[2 * fine_stride] = coarse
             nbr_down, nbr_up = ops.kernel_map_stride2(fine, parent, coarse.shape[0], fine_stride)
-            self.stride2[fine_stride] = (nbr_down, nbr_up)
+            self.stride2[fine_stride] = (ops.sort_kernel_map(nbr_down), ops.sort_kernel_map(nbr_up))
         return self.stride2[fine_stride]
 
 

@@ -130,6 +130,37 @@ def kernel_map_stride2(fine_coords, parent_row, n_coarse, fine_stride):
     return nbr_down, nbr_up
 
 
+class KernelMap:
+    """Sorted kernel map consumed by the convolutions: nbr int32[K, n_out] (already permuted), order int32[n_out]
+    (position -> output row), gmask uint32-as-int32 [groups, words]. `raw` keeps the unsorted table (tests)."""
+    __slots__ = ("nbr", "order", "gmask", "kvol", "n_out", "raw")
+
+    def __init__(self, nbr, order, gmask, kvol, n_out, raw=None):
+        self.nbr, self.order, self.gmask, self.kvol, self.n_out, self.raw = nbr, order, gmask, kvol, n_out, raw
+
+
+SORT_BLOCK_ROWS = 32768
+
+
+def sort_kernel_map(nbr, block_rows=None, keep_raw=False):
+    lib = _lib_or_raise()
+    _cuda(nbr, torch.int32, "nbr")
+    kvol, n_out = nbr.shape
+    if block_rows is None:
+        block_rows = SORT_BLOCK_ROWS
+    words = (kvol + 31) // 32
+    order = torch.empty(n_out, dtype=torch.int32, device=nbr.device)
+    do_sort = block_rows > 0 and kvol <= 32
+    nbr_sorted = torch.empty_like(nbr) if do_sort else nbr
+    gmask = torch.empty(((n_out + 63) // 64, words), dtype=torch.int32, device=nbr.device)
+    ws_bytes = lib.b2m_kernel_map_sort_workspace_bytes(n_out) if do_sort else 0
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=nbr.device)
+    _run("kernel_map_sort", 5, lambda: check(lib.b2m_kernel_map_sort(
+        ptr(nbr), kvol, n_out, int(block_rows), ptr(order), ptr(nbr_sorted), ptr(gmask), ptr(ws), ws_bytes, stream_ptr()),
+        "kernel_map_sort"), nbytes=12 * n_out * kvol + 16 * n_out)
+    return KernelMap(nbr_sorted, order, gmask, kvol, n_out, nbr if keep_raw else None)
+
+
 def kernel_map_count(nbr):
     lib = _lib_or_raise()
     counts = torch.empty(nbr.shape[0], dtype=torch.int32, device=nbr.device)
@@ -166,27 +197,35 @@ def pack_weights(kernel, mode):
     return packed
 
 
-def conv_forward(x, nbr, packed_w, kvol, n_out, c_n, colsum=None):
-    """y bf16[n_out, c_n] = sum_k x[nbr[k]] @ B[k]; colsum f64[2*c_n] (zeroed by the caller) optional."""
+def conv_forward(x, kmap, packed_w, kvol, n_out, c_n, colsum=None):
+    """y bf16[n_out, c_n] = sum_k x[nbr[k]] @ B[k] over a sorted KernelMap (None = identity, kvol 1);
+    colsum f64[2*c_n] (zeroed by the caller) optional."""
     lib = _lib_or_raise()
     _cuda(x, torch.bfloat16, "x")
+    nbr = kmap.nbr if kmap is not None else None
+    order = kmap.order if kmap is not None else None
+    gmask = kmap.gmask if kmap is not None else None
     y = torch.empty((n_out, c_n), dtype=torch.bfloat16, device=x.device)
     _run("conv_forward", 1, lambda: check(lib.b2m_conv_forward(
-        ptr(x), x.shape[0], x.shape[1], ptr(nbr), kvol, n_out, ptr(packed_w), c_n, ptr(y), ptr(colsum), stream_ptr()),
-        "conv_forward"), flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] * c_n,
+        ptr(x), x.shape[0], x.shape[1], ptr(nbr), ptr(order), ptr(gmask), kvol, n_out, ptr(packed_w), c_n, ptr(y),
+        ptr(colsum), stream_ptr()), "conv_forward"), flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] * c_n,
         nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] + 2.0 * n_out * c_n,
         tag="k%d %d->%d n_in=%d n_out=%d" % (kvol, x.shape[1], c_n, x.shape[0], n_out))
     return y
 
 
-def conv_wgrad(x, dy, nbr, kvol, n_out):
+def conv_wgrad(x, dy, kmap, kvol, n_out):
     lib = _lib_or_raise()
     _cuda(x, torch.bfloat16, "x")
     _cuda(dy, torch.bfloat16, "dy")
+    nbr = kmap.nbr if kmap is not None else None
+    order = kmap.order if kmap is not None else None
+    gmask = kmap.gmask if kmap is not None else None
     c_in, c_out = x.shape[1], dy.shape[1]
     dw = torch.zeros((kvol, c_in, c_out), dtype=torch.float32, device=x.device)
     _run("conv_wgrad", 1, lambda: check(lib.b2m_conv_wgrad(
-        ptr(x), x.shape[0], c_in, ptr(dy), c_out, ptr(nbr), kvol, n_out, ptr(dw), stream_ptr()), "conv_wgrad"),
+        ptr(x), x.shape[0], c_in, ptr(dy), c_out, ptr(nbr), ptr(order), ptr(gmask), kvol, n_out, ptr(dw), stream_ptr()),
+        "conv_wgrad"),
         flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * c_in * c_out,
         nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * (c_in + c_out),
         tag="k%d %d->%d n_in=%d n_out=%d" % (kvol, c_in, c_out, x.shape[0], n_out))

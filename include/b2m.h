@@ -92,6 +92,19 @@ int b2m_kernel_map_stride2(const int32_t* fine_coords, int64_t n_fine, const int
 int b2m_kernel_map_count(const int32_t* nbr, int32_t kvol, int64_t n_out, int32_t* counts,
                          b2m_stream_t stream);
 
+/* Sorted kernel map, the form the convolutions consume. Rows are ordered by (row / block_rows, occupancy bit
+ * mask of the row) with a stable radix sort, so that the 128 rows of an MMA tile share their set of present
+ * offsets and (tile, offset) blocks without any pair are skipped. Outputs:
+ *   order      int32[n_out]        position -> original output row
+ *   nbr_sorted int32[K, n_out]     nbr_sorted[k][j] = nbr[k][order[j]]
+ *   group_mask uint32[ceil(n_out/64), ceil(K/32)]  offsets present in each 64-row group of the sorted order
+ * block_rows <= 0 or K > 32 keeps the original order (identity `order`), masks are still produced.
+ * The set of (k, in, out) pairs is unchanged — this is a traversal order, not a different map. */
+size_t b2m_kernel_map_sort_workspace_bytes(int64_t n_out);
+int b2m_kernel_map_sort(const int32_t* nbr, int32_t kvol, int64_t n_out, int32_t block_rows, int32_t* order,
+                        int32_t* nbr_sorted, uint32_t* group_mask, void* workspace, size_t workspace_bytes,
+                        b2m_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Sparse convolution (gather -> tcgen05 implicit GEMM, fp32 accumulation in TMEM)
  * reference: MinkowskiConvolution.forward / MinkowskiConvolutionTranspose.forward and their autograd
@@ -104,21 +117,25 @@ int b2m_cast_pad_bf16(const float* x, int64_t n, int32_t c, int32_t c_pad, uint1
  * mode 0: forward operand   B[k]  = W[k]            (reduction dim = c_in,  N = c_out)
  * mode 1: dgrad, same-coords B[k]  = W[kvol-1-k]^T  (reduction dim = c_out, N = c_in)
  * mode 2: dgrad, strided     B[k]  = W[k]^T         (reduction dim = c_out, N = c_in)
- * c_red (the reduction dim) is padded to a multiple of 64 with zeros. */
+ * c_red (the reduction dim) is padded to a multiple of 64 with zeros; for c_red in {16, 32} the slices are
+ * "flat": 64 / c_red consecutive offsets share one 64-wide slice (what b2m_conv_forward expects). */
 size_t b2m_packed_weight_bytes(int32_t kvol, int32_t c_in, int32_t c_out, int32_t mode);
 int b2m_pack_weights(const float* kernel, int32_t kvol, int32_t c_in, int32_t c_out, int32_t mode,
                      uint16_t* packed, b2m_stream_t stream);
-/* y[o, :] = sum_k x[nbr[k][o], :] * B[k]   (rows with nbr < 0 contribute zero; nbr == NULL means the
- * identity map with kvol == 1). x bf16[n_in, c_red], y bf16[n_out, c_n]. c_red % 16 == 0,
- * c_n % 16 == 0, c_n <= 512. colsum (optional, double[2*c_n], caller-zeroed) accumulates per-column
- * sum and sum of squares of the fp32 results (BatchNorm batch statistics). */
-int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, const int32_t* nbr, int32_t kvol,
-                     int64_t n_out, const uint16_t* packed_w, int32_t c_n, uint16_t* y, double* colsum,
-                     b2m_stream_t stream);
-/* dw[k, ci, co] += sum_o x[nbr[k][o], ci] * dy[o, co]   (fp32, caller-zeroed, atomically accumulated)
- * x bf16[n_in, c_in], dy bf16[n_out, c_out]; c_in % 16 == 0, c_out % 16 == 0, c_out <= 256. */
+/* y[order[j], :] = sum_k x[nbr[k][j], :] * B[k]   (entries < 0 contribute zero). (nbr, order, group_mask) is a
+ * sorted kernel map from b2m_kernel_map_sort; nbr == NULL means the identity map with kvol == 1 (order and
+ * group_mask ignored). x bf16[n_in, c_red], y bf16[n_out, c_n]. c_red % 16 == 0, c_n % 16 == 0, c_n <= 512.
+ * colsum (optional, double[2*c_n], caller-zeroed) accumulates per-column sum and sum of squares of the fp32
+ * results (BatchNorm batch statistics). */
+int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, const int32_t* nbr, const int32_t* order,
+                     const uint32_t* group_mask, int32_t kvol, int64_t n_out, const uint16_t* packed_w,
+                     int32_t c_n, uint16_t* y, double* colsum, b2m_stream_t stream);
+/* dw[k, ci, co] += sum_j x[nbr[k][j], ci] * dy[order[j], co]   (fp32, caller-zeroed, atomically accumulated)
+ * over a sorted kernel map. x bf16[n_in, c_in], dy bf16[n_out, c_out]; c_in % 8 == 0, c_out % 16 == 0,
+ * c_out <= 256. */
 int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t* dy, int32_t c_out,
-                   const int32_t* nbr, int32_t kvol, int64_t n_out, float* dw, b2m_stream_t stream);
+                   const int32_t* nbr, const int32_t* order, const uint32_t* group_mask, int32_t kvol,
+                   int64_t n_out, float* dw, b2m_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm (+ residual, + ReLU) over rows          reference: MinkowskiBatchNorm -> BatchNorm1d

@@ -17,11 +17,11 @@ def test_library_builds_and_exports_header():
     build.build()
     lib = _lib.load()
     syms = _header_symbols()
-    assert len(syms) >= 25
+    assert len(syms) >= 27
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(_lib.SIGNATURES) == syms            # the ctypes table mirrors the header one to one
-    assert lib.b2m_version() == 1
+    assert lib.b2m_version() == 2
     assert lib.b2m_error_string(-4) == b"unsupported shape"
     assert lib.b2m_hash_capacity(1000) == 2048 and lib.b2m_hash_capacity(0) == 1024
     assert lib.b2m_packed_weight_bytes(27, 96, 128, 0) == 27 * 2 * 128 * 64 * 2

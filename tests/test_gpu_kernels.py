@@ -84,6 +84,36 @@ def test_strided_levels_bit_exact(scene_coords):
         assert np.array_equal(nbr.cpu().numpy(), so.kernel_map_submanifold(cur_np, ts, 3)), level
 
 
+@pytest.mark.parametrize("block_rows", [4096, 0])
+def test_sorted_kernel_map(scene_coords, block_rows):
+    """b2m_kernel_map_sort: a permutation of the rows, stable inside (block, mask) classes; the pair set is unchanged."""
+    nbr_np = so.kernel_map_submanifold(scene_coords, 1, 3)
+    n = nbr_np.shape[1]
+    km = ops.sort_kernel_map(torch.from_numpy(nbr_np).to(DEV), block_rows=block_rows)
+    order = km.order.cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(n))
+    assert np.array_equal(km.nbr.cpu().numpy(), nbr_np[:, order])
+    mask = np.zeros(n, np.uint64)
+    for k in range(27):
+        mask |= (nbr_np[k] >= 0).astype(np.uint64) << np.uint64(k)
+    if block_rows:
+        ref_order = np.lexsort((np.arange(n), mask, np.arange(n) // block_rows))
+        assert np.array_equal(order, ref_order)
+    else:
+        assert np.array_equal(order, np.arange(n))
+    g = (n + 63) // 64
+    pad = g * 64 - n
+    gm = np.bitwise_or.reduce(np.pad(mask[order], (0, pad)).reshape(g, 64), axis=1).astype(np.uint32)
+    assert np.array_equal(km.gmask.cpu().numpy().view(np.uint32)[:, 0], gm)
+    # 125-offset map: never sorted, 4 mask words
+    nbr5 = so.kernel_map_submanifold(scene_coords[:3000], 1, 5)
+    km5 = ops.sort_kernel_map(torch.from_numpy(nbr5).to(DEV))
+    assert np.array_equal(km5.order.cpu().numpy(), np.arange(3000)) and km5.gmask.shape == (47, 4)
+    bits = np.unpackbits(km5.gmask.cpu().numpy().view(np.uint8).reshape(47, 16), axis=1, bitorder="little")[:, :125]
+    ref_bits = np.pad(nbr5 >= 0, ((0, 0), (0, 47 * 64 - 3000))).reshape(125, 47, 64).any(2).T
+    assert np.array_equal(bits.astype(bool), ref_bits)
+
+
 def test_kernel_map_negative_and_unsorted():
     rng = np.random.default_rng(5)
     xyz = np.unique(rng.integers(-20, 20, (3000, 3)), axis=0)
@@ -124,7 +154,7 @@ def _conv_case(kvol, c_in, c_out, n, seed, real_map=None):
 def test_conv_forward(kvol, c_in, c_out, n):
     nbr_np, x, w, n = _conv_case(kvol, c_in, c_out, n, seed=kvol + c_in)
     ref = so.sparse_conv(x.double(), nbr_np, w.double(), n_out=n)
-    nbr = torch.from_numpy(nbr_np).to(DEV) if nbr_np is not None else None
+    nbr = ops.sort_kernel_map(torch.from_numpy(nbr_np).to(DEV)) if nbr_np is not None else None
     colsum = torch.zeros(2 * c_out, dtype=torch.float64, device=DEV)
     y = ops.conv_forward(x.to(DEV).to(torch.bfloat16), nbr, ops.pack_weights(w.to(DEV), 0), kvol, n, c_out, colsum)
     err = (y.float().cpu().double() - ref).abs()
@@ -146,7 +176,7 @@ def test_conv_forward_real_maps_and_dgrad(scene_coords):
     y = so.sparse_conv(x, nbr3, w)
     dy = so.bf16_round(torch.randn(n, 96)).double()
     y.backward(dy)
-    dev_nbr = torch.from_numpy(nbr3).to(DEV)
+    dev_nbr = ops.sort_kernel_map(torch.from_numpy(nbr3).to(DEV))
     got = ops.conv_forward(x.detach().float().to(DEV).to(torch.bfloat16), dev_nbr, ops.pack_weights(w.detach().float().to(DEV), 0), 27, n, 96)
     assert bool(((got.float().cpu().double() - y.detach()).abs() <= 8e-3 * y.detach().abs() + 2e-2).all())
     dx = ops.conv_forward(dy.float().to(DEV).to(torch.bfloat16), dev_nbr, ops.pack_weights(w.detach().float().to(DEV), 1), 27, n, 64)
@@ -159,7 +189,7 @@ def test_conv_forward_real_maps_and_dgrad(scene_coords):
     ys = so.sparse_conv(xs, nbr_down, ws)
     dys = so.bf16_round(torch.randn(len(coarse), 64)).double()
     ys.backward(dys)
-    d_down, d_up = torch.from_numpy(nbr_down).to(DEV), torch.from_numpy(nbr_up).to(DEV)
+    d_down, d_up = ops.sort_kernel_map(torch.from_numpy(nbr_down).to(DEV)), ops.sort_kernel_map(torch.from_numpy(nbr_up).to(DEV))
     got = ops.conv_forward(xs.detach().float().to(DEV).to(torch.bfloat16), d_down, ops.pack_weights(ws.detach().float().to(DEV), 0), 8, len(coarse), 64)
     assert bool(((got.float().cpu().double() - ys.detach()).abs() <= 8e-3 * ys.detach().abs() + 2e-2).all())
     dxs = ops.conv_forward(dys.float().to(DEV).to(torch.bfloat16), d_up, ops.pack_weights(ws.detach().float().to(DEV), 2), 8, n, 32)
@@ -182,7 +212,7 @@ def test_conv_wgrad(kvol, c_in, c_out, n):
         for k, (i, o) in enumerate(so.map_to_pairs(nbr_np)):
             if len(i):
                 ref[k] = x.double()[i].t() @ dy.double()[o]
-    nbr = torch.from_numpy(nbr_np).to(DEV) if nbr_np is not None else None
+    nbr = ops.sort_kernel_map(torch.from_numpy(nbr_np).to(DEV)) if nbr_np is not None else None
     dw = ops.conv_wgrad(x.to(DEV).to(torch.bfloat16), dy.to(DEV).to(torch.bfloat16), nbr, kvol, n)
     # fp32 accumulation over up to 7e4 products + fp32 atomics across CTAs: rel 2e-3 of the largest entry
     assert torch.allclose(dw.cpu().double(), ref, rtol=2e-3, atol=2e-3 * float(ref.abs().max()) + 1e-4)
@@ -233,6 +263,30 @@ def test_bn_forward_backward(n, c, relu, res):
     assert torch.allclose(dbeta.cpu(), b_.grad, rtol=1e-3, atol=1e-3 * float(b_.grad.abs().max()) + 1e-2)
     if res:
         assert torch.allclose(dres.float().cpu(), rr.grad, rtol=8e-3, atol=1e-3)
+
+
+def test_bn_backward_with_correlated_gradient():
+    """Upstream gradients with a non-zero mean and a component along x-hat, so that the batch-statistics terms of
+    the BatchNorm backward matter (they vanish for white-noise gradients)."""
+    torch.manual_seed(1)
+    n, c = 30000, 96
+    x = so.bf16_round(torch.randn(n, c) * 1.5 + 0.3)
+    gamma, beta = torch.rand(c) + 0.5, torch.randn(c)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.batch_norm(xr, None, None, gamma, beta, True, 0.1, 1e-5)
+    xhat = ((x - x.mean(0)) / x.std(0, unbiased=False))
+    dout = so.bf16_round(0.5 + 0.7 * xhat + 0.2 * torch.randn(n, c))
+    ref.backward(dout)
+    xd = x.to(DEV).to(torch.bfloat16)
+    out, sm, si = ops.bn_forward(xd, ops.colstats(xd), gamma.to(DEV), beta.to(DEV), torch.zeros(c, device=DEV),
+                                 torch.ones(c, device=DEV), 0.1, 1e-5, True, None, False)
+    dx, _, dgamma, dbeta = ops.bn_backward(xd, out, dout.to(DEV).to(torch.bfloat16), sm, si, gamma.to(DEV), False, True, False)
+    # dx is what is left after removing the mean and x-hat components: small, and it must still be right
+    err = (dx.float().cpu() - xr.grad).abs()
+    assert float(err.max()) <= 8e-3 * float(xr.grad.abs().max()) + 2e-3
+    cos = torch.nn.functional.cosine_similarity(dx.float().cpu().flatten(), xr.grad.flatten(), dim=0)
+    assert float(cos) > 0.999
+    assert torch.allclose(dbeta.cpu(), dout.sum(0), rtol=1e-4) and torch.allclose(dgamma.cpu(), (dout * xhat).sum(0), rtol=2e-3, atol=1.0)
 
 
 def test_bn_eval_mode():

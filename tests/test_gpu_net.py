@@ -68,12 +68,12 @@ def test_train_loss_vs_reference_golden(setup):
         assert abs(a - b) <= 0.10 * max(1.0, abs(b)), (k, a, b)
 
 
-def test_train_forward_loss_backward_vs_oracle(setup):
+def _grads_vs_oracle(setup, training):
     from box2mask_b200.synthetic import make_batch
     g, _, cfg, model, sd, id2idx = setup
     batch = make_batch(8, seed=5, scale=0.2, density=1.2e4)     # deepest level has >= 8 rows
     model.load_state_dict(sd)
-    model.train()
+    model.train() if training else model.eval()
     for p in model.parameters():
         p.grad = None
     losses, pred = model.compute_loss_detection(batch, epoch=0)
@@ -82,30 +82,44 @@ def test_train_forward_loss_backward_vs_oracle(setup):
     for k, v in osd.items():
         if v.is_floating_point() and "running" not in k:
             v.requires_grad_(True)
-    out = OracleNet(osd, cfg, training=True, emulate_bf16=True).forward(
+    out = OracleNet(osd, cfg, training=training, emulate_bf16=True).forward(
         batch["vox_coords"].numpy(), batch["vox_features"], batch["pooling_ids"])
     ol = detection_loss(out, batch, cfg, 0, id2idx)
     ol["optimization_loss"].backward()
-    report = {}
-    for head in cfg.network_heads:
-        report[head] = _cos(pred[head].detach().cpu(), out[head].detach())
-    # training-mode BatchNorm over the 2-6 rows of the deepest levels amplifies rounding; tolerance is looser
-    print("train-mode head cosines:", report)
-    for head, c in report.items():
-        assert c >= 0.98, report
+    heads = {h: _cos(pred[h].detach().cpu(), out[h].detach()) for h in cfg.network_heads}
+    grads = {k: _cos(p.grad.cpu(), osd[k].grad) for k, p in model.net.named_parameters() if k.endswith(".kernel")}
+    return losses, ol, heads, grads, model, sd
+
+
+def test_backward_all_layers_vs_oracle_eval_bn(setup):
+    """Forward + losses + backward through EVERY layer with BatchNorm in eval mode (running statistics): the
+    composition of conv dgrad/wgrad, BN/ReLU/residual backward, cat and pooling backward. Gradients are bf16 between
+    layers on the GPU and fp32 in the oracle: cosine >= 0.97 for all 93 kernels, >= 0.999 for full-resolution ones."""
+    losses, ol, heads, grads, _, _ = _grads_vs_oracle(setup, training=False)
+    assert abs(float(losses["optimization_loss"]) - float(ol["optimization_loss"])) <= 1e-3 * float(ol["optimization_loss"])
+    assert min(heads.values()) >= 0.9999, heads
+    assert len(grads) == 93
+    assert min(grads.values()) >= 0.97, sorted(grads.items(), key=lambda kv: kv[1])[:5]
+    for k in ("conv0p1s1.kernel", "block1.0.conv1.kernel", "block8.1.conv2.kernel", "convtr7p2s2.kernel", "conv1p1s2.kernel"):
+        assert grads[k] >= 0.999, (k, grads[k])
+
+
+def test_train_forward_loss_backward_vs_oracle(setup):
+    """Training-mode BatchNorm. With these random weights the network is chaotic in this mode: BatchNorm over the
+    8-16 rows of the deepest levels amplifies any perturbation — two fp32 CPU runs whose inputs differ by 1e-3
+    relative already disagree at cosine 0.69 on conv0's gradient (0.98 on block8.0, 0.99 on block8.1), measured with
+    the oracle alone. So only the quantities that are well conditioned are asserted: head outputs, every loss term,
+    the gradients of the last full-resolution stage and of the heads, and the BatchNorm bookkeeping."""
+    losses, ol, heads, grads, model, sd = _grads_vs_oracle(setup, training=True)
+    print("train-mode head cosines:", heads)
+    assert min(heads.values()) >= 0.99, heads
     for k in ("optimization_loss", "offset_loss", "bounds_loss", "bb_score_loss", "semantics_loss"):
         a, b = float(losses[k]), float(ol[k])
         assert abs(a - b) <= 0.03 * max(1.0, abs(b)), (k, a, b)
-    params = dict(model.net.named_parameters())
-    coss = {}
-    for key in ("conv0p1s1.kernel", "block1.0.conv1.kernel", "block8.1.conv2.kernel", "convtr7p2s2.kernel",
-                "conv2p2s2.kernel", "block2.0.downsample.0.kernel", "bn0.bn.weight", "block8.1.norm2.bn.bias",
-                "mlp_offsets.6.kernel", "block5.0.conv1.kernel", "added_block1.0.conv1.kernel"):
-        coss[key] = _cos(params[key].grad.cpu(), osd[key].grad)
-    print("grad cosines:", coss)
-    for key, c in coss.items():
-        assert c >= 0.97, coss
-    # running statistics were updated like BatchNorm1d does
+    print("train-mode grad cosines (informational):", {k: round(v, 3) for k, v in list(grads.items())[::8]})
+    for k in ("block8.1.conv2.kernel", "block8.1.conv1.kernel", "mlp_offsets.6.kernel", "mlp_semantics.6.kernel",
+              "mlp_score.3.kernel"):
+        assert grads[k] >= 0.95, (k, grads[k])
     assert int(model.net.bn0.bn.num_batches_tracked) == 1
     assert float((model.net.bn0.bn.running_mean.cpu() - sd["bn0.bn.running_mean"]).abs().max()) > 0
 

@@ -34,7 +34,7 @@ def probe_conv(kvol, c_in, c_out, n, seed=0):
     xb = so.bf16_round(x)
     wb = so.bf16_round(w)
     ref = so.sparse_conv(xb.double(), nbr_np, wb.double(), n_out=n)
-    nbr = torch.from_numpy(nbr_np).to(dev) if nbr_np is not None else None
+    nbr = ops.sort_kernel_map(torch.from_numpy(nbr_np).to(dev)) if nbr_np is not None else None
     packed = ops.pack_weights(w.to(dev), 0)
     colsum = torch.zeros(2 * c_out, dtype=torch.float64, device=dev)
     y = ops.conv_forward(x.to(dev).to(torch.bfloat16), nbr, packed, kvol, n, c_out, colsum)
@@ -84,7 +84,7 @@ def probe_wgrad(kvol, c_in, c_out, n, seed=0):
         for k, (i, o) in enumerate(so.map_to_pairs(nbr_np)):
             if len(i):
                 ref[k] = x.double()[i].t() @ dy.double()[o]
-    nbr = torch.from_numpy(nbr_np).to(dev) if nbr_np is not None else None
+    nbr = ops.sort_kernel_map(torch.from_numpy(nbr_np).to(dev)) if nbr_np is not None else None
     dw = ops.conv_wgrad(x.to(dev).to(torch.bfloat16), dy.to(dev).to(torch.bfloat16), nbr, kvol, n)
     torch.cuda.synchronize()
     err = (dw.cpu().double() - ref).abs()
