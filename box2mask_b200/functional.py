@@ -66,9 +66,7 @@ class BatchNormFn(torch.autograd.Function):
             if sums is None:
                 sums = ops.colstats(x)
             if sync_group is not None:
-                packed = torch.cat([sums, torch.tensor([float(n)], dtype=torch.float64, device=x.device)])
-                torch.distributed.all_reduce(packed, group=sync_group)
-                sums, n_stat = packed[:-1].contiguous(), int(round(float(packed[-1].item())))
+                sums, n_stat = sync_bn_stats(sums, n, sync_group)
             if n_stat <= 1:
                 raise ValueError("Expected more than 1 value per channel when training")
         out, save_mean, save_invstd = ops.bn_forward(x, sums, gamma.detach(), beta.detach(), running_mean, running_var,
@@ -86,6 +84,47 @@ class BatchNormFn(torch.autograd.Function):
         dx, dres, dgamma, dbeta = ops.bn_backward(x, out, dout.contiguous(), save_mean, save_invstd, gamma.detach(),
                                                   ctx.relu, ctx.training, ctx.has_res, ctx.n_stat, hook)
         return dx, None, dgamma, dbeta, None, None, None, None, None, dres, None, None
+
+
+def sync_bn_stats(sums, n, group):
+    """All-reduce the per-column (sum, sum of squares) and the row count over the ranks of `group`.
+    Returns (global sums, global n). One collective of 2C+1 doubles (SyncBN forward, models/model.py:25)."""
+    packed = torch.cat([sums, torch.tensor([float(n)], dtype=sums.dtype, device=sums.device)])
+    torch.distributed.all_reduce(packed, group=group)
+    return packed[:-1].contiguous(), int(round(float(packed[-1].item())))
+
+
+class SyncBatchNormFp32Fn(torch.autograd.Function):
+    """Synchronised BatchNorm for the small fp32 tensors of the MLP heads (S superpoint rows): plain torch
+    arithmetic around two tiny all-reduces; device-agnostic (gloo on CPU in the tests, NCCL on GPUs)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, group):
+        xd = x.double()
+        sums = torch.cat([xd.sum(0), (xd * xd).sum(0)])
+        sums, n = sync_bn_stats(sums, x.shape[0], group)
+        c = x.shape[1]
+        mean = sums[:c] / n
+        var = (sums[c:] / n - mean * mean).clamp_(min=0)
+        invstd = torch.rsqrt(var + eps)
+        with torch.no_grad():
+            running_mean.mul_(1 - momentum).add_(momentum * mean.to(running_mean.dtype))
+            running_var.mul_(1 - momentum).add_(momentum * (var * n / max(n - 1, 1)).to(running_var.dtype))
+        xhat = ((xd - mean) * invstd).to(x.dtype)
+        ctx.save_for_backward(xhat, gamma, invstd.to(x.dtype))
+        ctx.n, ctx.group = n, group
+        return xhat * gamma + beta
+
+    @staticmethod
+    def backward(ctx, dout):
+        xhat, gamma, invstd = ctx.saved_tensors
+        red = torch.cat([dout.sum(0), (dout * xhat).sum(0)]).double()
+        dgamma, dbeta = red[xhat.shape[1]:].to(dout.dtype), red[:xhat.shape[1]].to(dout.dtype)
+        torch.distributed.all_reduce(red, group=ctx.group)
+        c = xhat.shape[1]
+        sg, sgx = (red[:c] / ctx.n).to(dout.dtype), (red[c:] / ctx.n).to(dout.dtype)
+        dx = gamma * invstd * (dout - sg - xhat * sgx)
+        return dx, dgamma, dbeta, None, None, None, None, None
 
 
 class SegmentMeanFn(torch.autograd.Function):

@@ -144,7 +144,13 @@ def _bn_act(mod, x, residual=None, relu=False):
     feats = x.F
     if feats.dtype != torch.bfloat16:
         # fp32 rows (the MLP heads on S superpoint rows): torch's BatchNorm1d, fp32
-        out = bn(feats)
+        group = getattr(mod, "process_group", None)
+        if group is not None and group != "default" and bn.training and torch.distributed.is_initialized():
+            bn.num_batches_tracked += 1
+            out = Fn.SyncBatchNormFp32Fn.apply(feats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                               bn.momentum, bn.eps, group)
+        else:
+            out = bn(feats)
         if residual is not None:
             out = out + residual.F
         if relu:

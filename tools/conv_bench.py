@@ -1,0 +1,71 @@
+"""Micro-benchmark of the two convolution kernels on a REAL kernel map (k3 at full resolution of a synthetic
+ScanNet-shape batch). For ncu: python tools/conv_bench.py --scenes 8 --cin 128 --cout 96 --iters 3"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from box2mask_b200 import ops  # noqa: E402
+from box2mask_b200.synthetic import batched_coordinates, make_scene  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scenes", type=int, default=8)
+ap.add_argument("--scale", type=float, default=0.84)
+ap.add_argument("--cin", type=int, default=128)
+ap.add_argument("--cout", type=int, default=96)
+ap.add_argument("--ksize", type=int, default=3)
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--block-rows", type=int, default=None)
+ap.add_argument("--which", default="fwd,wgrad")
+args = ap.parse_args()
+
+dev = "cuda"
+cache = "/tmp/conv_bench_coords_%d_%.2f.npy" % (args.scenes, args.scale)
+if os.path.exists(cache):
+    coords_np = np.load(cache)
+else:
+    coords_np = batched_coordinates([make_scene(10000 + i, scale=args.scale)["vox_coords"] for i in range(args.scenes)]).numpy()
+    np.save(cache, coords_np)
+coords = torch.from_numpy(coords_np).to(dev)
+n = coords.shape[0]
+t0 = time.time()
+table = ops.hash_build(coords)
+nbr = ops.kernel_map_submanifold(coords, 1, args.ksize, table)
+km = ops.sort_kernel_map(nbr, block_rows=args.block_rows)
+torch.cuda.synchronize()
+kvol = args.ksize ** 3
+pairs = int((nbr >= 0).sum())
+gm = km.gmask.cpu().numpy().view(np.uint32)
+bits = np.unpackbits(gm.view(np.uint8).reshape(gm.shape[0], -1), axis=1, bitorder="little")[:, :kvol]
+print("rows %d pairs/row %.2f  non-empty (64-row group, offset) blocks: %.3f  density in them: %.3f" % (
+    n, pairs / n, bits.mean(), pairs / (bits.sum() * 64.0)))
+x = torch.randn(n, args.cin, device=dev).to(torch.bfloat16)
+dy = torch.randn(n, args.cout, device=dev).to(torch.bfloat16)
+w = torch.randn(kvol, args.cin, args.cout, device=dev) * 0.05
+packed = ops.pack_weights(w, 0)
+flops = 2.0 * pairs * args.cin * args.cout
+
+
+def bench(fn, name):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.iters
+    print("%-6s k%d %d->%d rows %d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (name, kvol, args.cin, args.cout, n, ms, flops / ms / 1e9))
+
+
+if "fwd" in args.which:
+    colsum = torch.zeros(2 * args.cout, dtype=torch.float64, device=dev)
+    bench(lambda: ops.conv_forward(x, km, packed, kvol, n, args.cout, colsum), "fwd")
+if "wgrad" in args.which:
+    bench(lambda: ops.conv_wgrad(x, dy, km, kvol, n), "wgrad")
