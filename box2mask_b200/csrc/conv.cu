@@ -1,4 +1,4 @@
-// Sparse convolution on sm_100a: gather -> tcgen05.mma (UMMA) implicit GEMM with TMEM accumulators.
+// Sparse convolution on sm_100a: TMA row gather -> tcgen05.mma (UMMA) implicit GEMM with TMEM accumulators.
 //
 // Replaces MinkowskiConvolution / MinkowskiConvolutionTranspose forward+backward
 // (reference call sites: /root/reference/models/detection_net.py:235-337, models/resnet.py:70-83).
@@ -6,14 +6,20 @@
 // Both kernels consume a SORTED kernel map (b2m_kernel_map_sort): output rows are visited in `order`
 // (rows grouped by their neighbour-occupancy bit mask inside blocks of rows), nbr is already permuted to
 // that order and group_mask[g] says which offsets occur in each 64-row group, so whole (tile, offset)
-// blocks without pairs are never touched.
+// blocks without pairs are never touched. Tables have a row pitch of b2m_map_pitch(n_out) (-1 padded).
+//
+// Feature rows are fetched by the TMA engine in its row-gather mode (cp.async.bulk.tensor.2d ...
+// tile::gather4): one instruction moves 4 arbitrary rows x one column box (<= 64 bf16) of the [rows, channels]
+// tensor into shared memory with the swizzle the UMMA descriptors expect; rows with index -1 (no neighbour) and
+// columns past the channel count are zero-filled by the hardware at no memory traffic. The box width follows
+// the reduction width: 64 channels -> SWIZZLE_128B tiles, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B.
 //
 //  conv_fwd_kernel   persistent, warp-specialised, output-stationary implicit GEMM.
 //      work item  = T (1 or 2) tiles of 128 output rows x <=256 output columns, accumulators in TMEM,
 //                   double-buffered across work items so the epilogue overlaps the next main loop.
-//      producers  = 8 warps, one A stage each: gather 128 neighbour rows x 64 reduction elements with
-//                   cp.async (16 B) into a 128B-swizzled K-major tile; missing neighbours are zero-stored.
-//                   For c_red in {16, 32} a stage packs 4 / 2 kernel offsets along K (no K padding waste).
+//      A stage    = 128 gathered rows x 64 (or the 32-wide remainder) reduction elements of one kernel offset;
+//                   for c_red in {16, 32} a stage holds 4 / 2 offsets as separate SW32 / SW64 sub-tiles.
+//      producers  = 12 warps, stage s belongs to warp s % 12: one 16-byte index load + one gather4 per lane.
 //      B loader   = one thread: 1-D bulk copies (TMA engine) of pre-swizzled weight slices; a slice is
 //                   shared by the T tiles of the work item.
 //      MMA issuer = one thread: tcgen05.mma.cta_group::1.kind::f16, M=128, N=ntile, K=16.
@@ -22,158 +28,153 @@
 //      The same kernel computes dgrad (weights packed transposed / mirrored).
 //  conv_wgrad_kernel dW[k] = X_gathered^T * dY.  M = input channels (several offsets packed into the 128 M
 //      rows when c_in <= 64), N = c_out, reduction over output rows in 64-row stages, both operands
-//      MN-major. One CTA owns up to G accumulators (G*N <= 512 TMEM columns) = G offset groups and a range
-//      of row groups; a dY stage is shared by the G gathers. fp32 vector atomics into dW at the end.
+//      MN-major (a gathered row IS a run of M / N elements). One CTA owns up to G accumulators (G*N <= 512 TMEM
+//      columns) = G offset groups and a range of row groups; a dY stage is shared by the G gathers. fp32 vector
+//      atomics into dW at the end.
 #include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
 namespace b2m {
 
 // ------------------------------------------------------------------------------------------------
 // weight packing
 // ------------------------------------------------------------------------------------------------
-// Reduction index of B: per-offset layout  R = (k, c) with c padded to a multiple of 64 per offset, or the
-// "flat" layout (c_red in {16,32}) where 64/c_red offsets share one 64-wide slice. packed[slice][n][64], the
-// eight 16-byte groups of a row XOR-swizzled with (n & 7) (UMMA SWIZZLE_128B image of a K-major tile).
+// Reduction layout of B per offset group kg:
+//   c_red in {16, 32} ("flat"): 64 / c_red consecutive offsets share ONE 64-wide SW128 slice [c_n][64].
+//   otherwise: c_red is cut into chunks of 64 (SW128 slices [c_n][64]); a remainder of exactly 32 becomes a
+//   SW64 slice [c_n][32]; remainders of 16 / 48 are zero-padded to a full chunk.
+// A slice row is 128 (64) bytes; its 16-byte groups are XOR-swizzled with n & 7 ((n >> 1) & 3).
 __host__ __device__ inline int conv_kpack(int c_red) { return (c_red == 16 || c_red == 32) ? 64 / c_red : 1; }
+__host__ __device__ inline int conv_rem(int c_red) { return (conv_kpack(c_red) == 1 && (c_red % 64) == 32) ? 1 : 0; }
+__host__ __device__ inline int conv_nfull(int c_red) {
+  if (conv_kpack(c_red) > 1) return 1;
+  return c_red / 64 + (((c_red % 64) == 16 || (c_red % 64) == 48) ? 1 : 0);
+}
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, int kvol, int c_in, int c_out, int mode,
                                     uint16_t* __restrict__ packed) {
   const int c_red = (mode == 0) ? c_in : c_out;
   const int c_n = (mode == 0) ? c_out : c_in;
-  const int kpack = conv_kpack(c_red);
-  const int nchunks = (kpack > 1) ? 1 : (c_red + 63) / 64;
+  const int kpack = conv_kpack(c_red), nfull = conv_nfull(c_red), rem = conv_rem(c_red);
   const int nkg = (kvol + kpack - 1) / kpack;
-  const int64_t total = (int64_t)nkg * nchunks * c_n * 8;  // one thread per 16-byte group
-  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int n = (int)(gid % c_n);
-  int64_t rest = gid / c_n;
-  const int g = (int)(rest % 8);
-  rest /= 8;
-  const int chunk = (int)(rest % nchunks);
-  const int kg = (int)(rest / nchunks);
+  const int64_t groups_kg = (int64_t)c_n * (nfull * 8 + rem * 4);  // 16-byte groups per offset group
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= groups_kg * nkg) return;
+  const int kg = (int)(gid / groups_kg);
+  int64_t r = gid % groups_kg;
+  int n, g, chunk;
+  if (r < (int64_t)c_n * nfull * 8) {
+    chunk = (int)(r / ((int64_t)c_n * 8));
+    r %= (int64_t)c_n * 8;
+    n = (int)(r / 8);
+    g = (int)(r % 8) ^ (n & 7);
+  } else {
+    chunk = nfull;
+    r -= (int64_t)c_n * nfull * 8;
+    n = (int)(r / 4);
+    g = (int)(r % 4) ^ ((n >> 1) & 3);
+  }
   __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int p = g * 8 + e;  // position inside the 64-wide slice
-    int k, r;
-    if (kpack > 1) { k = kg * kpack + p / c_red; r = p % c_red; } else { k = kg; r = chunk * 64 + p; }
+    const int p = g * 8 + e;  // position inside the slice
+    int k, ch;
+    if (kpack > 1) { k = kg * kpack + p / c_red; ch = p % c_red; } else { k = kg; ch = chunk * 64 + p; }
     float f = 0.f;
-    if (k < kvol && r < c_red) {
+    if (k < kvol && ch < c_red) {
       const int ksrc = (mode == 1) ? (kvol - 1 - k) : k;
-      f = (mode == 0) ? w[((int64_t)ksrc * c_in + r) * c_out + n] : w[((int64_t)ksrc * c_in + n) * c_out + r];
+      f = (mode == 0) ? w[((int64_t)ksrc * c_in + ch) * c_out + n] : w[((int64_t)ksrc * c_in + n) * c_out + ch];
     }
     v[e] = __float2bfloat16_rn(f);
   }
-  const int64_t row_base = (((int64_t)kg * nchunks + chunk) * c_n + n) * 64;
-  const int pg = g ^ (n & 7);
-  *reinterpret_cast<uint4*>(packed + row_base + pg * 8) = *reinterpret_cast<const uint4*>(v);
+  // threads write consecutive 16-byte groups: the packed image is exactly gid * 16 bytes in
+  *reinterpret_cast<uint4*>(packed + gid * 8) = *reinterpret_cast<const uint4*>(v);
 }
 
-struct MaskBits { uint32_t w[4]; };
-
-__device__ __forceinline__ bool mask_any(const MaskBits& m, int k0, int cnt, int kvol) {
-  bool any = false;
-  for (int j = 0; j < cnt; ++j) {
-    const int k = k0 + j;
-    if (k < kvol) any = any || ((m.w[k >> 5] >> (k & 31)) & 1u);
-  }
-  return any;
+struct MaskBits { uint32_t w0, w1, w2, w3; };
+__device__ __forceinline__ uint32_t mask_word(const MaskBits& m, int i) { return i == 0 ? m.w0 : (i == 1 ? m.w1 : (i == 2 ? m.w2 : m.w3)); }
+// the `cnt` (1, 2 or 4; divides 32) mask bits starting at offset k0
+__device__ __forceinline__ uint32_t mask_bits(const MaskBits& m, int k0, int cnt) {
+  return (mask_word(m, k0 >> 5) >> (k0 & 31)) & ((1u << cnt) - 1u);
 }
-__device__ __forceinline__ void st_shared_zero16(uint32_t addr) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0) : "memory");
+__device__ __forceinline__ MaskBits mask_zero() { MaskBits m; m.w0 = m.w1 = m.w2 = m.w3 = 0; return m; }
+__device__ __forceinline__ MaskBits mask_load(const uint32_t* __restrict__ gmask, int64_t g, int mwords) {
+  MaskBits m = mask_zero();
+  const uint32_t* p = gmask + g * mwords;
+  m.w0 = __ldg(p);
+  if (mwords > 1) m.w1 = __ldg(p + 1);
+  if (mwords > 2) m.w2 = __ldg(p + 2);
+  if (mwords > 3) m.w3 = __ldg(p + 3);
+  return m;
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // forward / dgrad kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kEpiWarps = 4;
-constexpr int kFwdProd = 8;                                   // producer warps == A ring slots
-constexpr int kFwdThreads = (kEpiWarps + 2 + kFwdProd) * 32;  // 448
+// Gather warps; A stage s is produced by warp s % kFwdProd. Issuing one gather4 per lane costs the issuing warp
+// ~76 cycles per lane (ELECT + R2UR loop around UTMALDG; tools/tma_gather_bench.cu) whatever the box size, and
+// scales linearly with the number of warps, so the TMA engine is fed by many warps.
+constexpr int kFwdProd = 12;
+constexpr int kFwdThreads = (kEpiWarps + 2 + kFwdProd) * 32;  // 576
 constexpr int kTileM = 128;
 constexpr int kStagePitch = 33;
+constexpr int kASlotBytes = kTileM * 128;
 
 struct FwdArgs {
-  const uint16_t* x; const int32_t* nbr; const int32_t* order; const uint32_t* gmask; const uint16_t* w;
+  const int32_t* nbr; const int32_t* order; const uint32_t* gmask; const uint8_t* w;
   uint16_t* y; double* colsum;
-  int64_t n_out;
-  int c_red, kvol, c_n, ntile, T, kpack, nkg, nchunks, mwords, colstride, n_tiles, n_work, b_slots, b_bytes;
+  int64_t n_out, n_pitch;
+  int c_red, kvol, c_n, ntile, T, kpack, nkg, nfull, rem, wa, mwords, colstride, n_tiles, n_work;
+  int a_slots, b_slots, b_bytes, kg_bytes;
   int off_b, off_stage, off_bars, tmem_cols;
 };
 
-__device__ __forceinline__ void fwd_tile_mask(const FwdArgs& a, int tile, MaskBits& m) {
-#pragma unroll
-  for (int w = 0; w < 4; ++w) m.w[w] = 0;
+__device__ __forceinline__ MaskBits fwd_tile_mask(const FwdArgs& a, int tile) {
+  MaskBits m = mask_zero();
   if (tile < a.n_tiles) {
-    if (a.gmask == nullptr) { m.w[0] = 1u; return; }  // identity map (kvol == 1)
+    if (a.gmask == nullptr) { m.w0 = 1u; return m; }  // identity map (kvol == 1)
     const int64_t ngroups = (a.n_out + 63) / 64;
     const int64_t g0 = 2 * (int64_t)tile;
-    for (int w = 0; w < a.mwords; ++w) {
-      uint32_t v = __ldg(a.gmask + g0 * a.mwords + w);
-      if (g0 + 1 < ngroups) v |= __ldg(a.gmask + (g0 + 1) * a.mwords + w);
-      m.w[w] = v;
+    m = mask_load(a.gmask, g0, a.mwords);
+    if (g0 + 1 < ngroups) {
+      const MaskBits m2 = mask_load(a.gmask, g0 + 1, a.mwords);
+      m.w0 |= m2.w0; m.w1 |= m2.w1; m.w2 |= m2.w2; m.w3 |= m2.w3;
     }
   }
+  return m;
 }
 
-__device__ __forceinline__ void fwd_gather_stage(const FwdArgs& a, uint32_t a_s, int tile, int kg, int c, int lane) {
-  const int sub = lane & 7, rb = lane >> 3;  // this lane copies 16-byte group `sub` of rows 4*it + rb
-  int k, ch, kc;
-  if (a.kpack > 1) {
-    const int cpr = a.c_red >> 3;  // 16-byte groups per offset
-    k = kg * a.kpack + sub / cpr;
-    ch = (sub % cpr) * 8;
-    kc = 64;
-  } else {
-    k = kg;
-    ch = c * 64 + sub * 8;
-    kc = min(64, a.c_red - c * 64);
-  }
-  if (sub * 8 >= kc) return;
-  const bool lane_on = k < a.kvol;
-  const int32_t* nb = (a.nbr && lane_on) ? a.nbr + (int64_t)k * a.n_out : nullptr;
-  const int64_t row0 = (int64_t)tile * kTileM;
-#pragma unroll 1
-  for (int it0 = 0; it0 < 32; it0 += 8) {
-    int32_t idx[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int64_t o = row0 + 4 * (it0 + u) + rb;
-      int32_t v = -1;
-      if (lane_on && o < a.n_out) v = nb ? __ldg(nb + o) : (int32_t)o;
-      idx[u] = v;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int row = 4 * (it0 + u) + rb;
-      const uint32_t dst = a_s + row * 128 + ((sub ^ (row & 7)) << 4);
-      if (idx[u] >= 0) cp_async16(dst, a.x + (int64_t)idx[u] * a.c_red + ch, 16u);
-      else st_shared_zero16(dst);
-    }
-  }
-}
+struct Ring {
+  int slot; uint32_t phase; int n;
+  __device__ __forceinline__ void init(int n_) { slot = 0; phase = 0; n = n_; }
+  __device__ __forceinline__ void next() { if (++slot == n) { slot = 0; phase ^= 1u; } }
+};
 
-__global__ void __launch_bounds__(kFwdThreads, 1) conv_fwd_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(kFwdThreads, 1)
+conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_rem, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int P = kFwdProd, SB = a.b_slots;
+  const int SA = a.a_slots, SB = a.b_slots;
   const uint32_t bars = smem_base + a.off_bars;
-  const uint32_t a_full = bars, a_empty = bars + 8 * P;
-  const uint32_t b_full = bars + 16 * P, b_empty = b_full + 8 * SB;
+  const uint32_t a_full = bars, a_empty = bars + 8 * SA;
+  const uint32_t b_full = bars + 16 * SA, b_empty = b_full + 8 * SB;
   const uint32_t acc_full = b_empty + 8 * SB, acc_empty = acc_full + 16;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + a.off_bars + 16 * P + 16 * SB + 32);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + a.off_bars + 16 * SA + 16 * SB + 32);
   const int n0 = blockIdx.y * a.ntile;
+  const int nch = a.nfull + a.rem;
 
   if (warp == 4 && lane == 0) {
-    for (int s = 0; s < P; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full + 8 * s, 1); mbar_init(acc_empty + 8 * s, kEpiWarps); }
     mbar_fence_init();
   }
   if (warp == 5) { tmem_alloc(smem_u32(tmem_ptr_s), (uint32_t)a.tmem_cols); tmem_relinquish(); }
+  if (warp == 6 && lane == 0) { tma_prefetch_desc(&tm_main); tma_prefetch_desc(&tm_rem); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -190,9 +191,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_fwd_kernel(const FwdArgs 
       for (int t = 0; t < a.T; ++t) {
         const int tile = w * a.T + t;
         if (tile >= a.n_tiles) break;
-        MaskBits m;
-        fwd_tile_mask(a, tile, m);
-        const bool has_acc = (m.w[0] | m.w[1] | m.w[2] | m.w[3]) != 0;
+        const MaskBits m = fwd_tile_mask(a, tile);
+        const bool has_acc = (m.w0 | m.w1 | m.w2 | m.w3) != 0;
         const int64_t pos = (int64_t)tile * kTileM + warp * 32 + lane;  // this lane's row (position in `order`)
         int32_t orow = -1;
         if (pos < a.n_out) orow = a.order ? __ldg(a.order + pos) : (int32_t)pos;
@@ -248,40 +248,54 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_fwd_kernel(const FwdArgs 
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(kTileM, a.ntile, 0, 0);
-      int ai = 0, bi = 0, wi = 0;
+      Ring ra, rb;
+      ra.init(SA); rb.init(SB);
+      int wi = 0;
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
         const int par = wi & 1;
         mbar_wait(acc_empty + 8 * par, ((uint32_t)(wi >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        MaskBits m[2];
-        bool started[2] = {false, false};
-        for (int t = 0; t < a.T; ++t) fwd_tile_mask(a, w * a.T + t, m[t]);
+        const MaskBits m0 = fwd_tile_mask(a, w * a.T);
+        const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
+        uint32_t started = 0;
         for (int kg = 0; kg < a.nkg; ++kg) {
-          bool act[2];
-          act[0] = mask_any(m[0], kg * a.kpack, a.kpack, a.kvol);
-          act[1] = (a.T > 1) && mask_any(m[1], kg * a.kpack, a.kpack, a.kvol);
-          if (!(act[0] || act[1])) continue;
-          for (int c = 0; c < a.nchunks; ++c, ++bi) {
-            const int bs = bi % SB;
-            mbar_wait(b_full + 8 * bs, (uint32_t)(bi / SB) & 1u);
-            const uint32_t b_s = smem_base + a.off_b + bs * a.b_bytes;
-            const int kc = (a.kpack > 1) ? 64 : min(64, a.c_red - c * 64);
+          const uint32_t s0 = mask_bits(m0, kg * a.kpack, a.kpack), s1 = mask_bits(m1, kg * a.kpack, a.kpack);
+          if (!(s0 | s1)) continue;
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(b_full + 8 * rb.slot, rb.phase);
+            const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
             for (int t = 0; t < a.T; ++t) {
-              if (!act[t]) continue;
-              const int as = ai % P;
-              mbar_wait(a_full + 8 * as, (uint32_t)(ai / P) & 1u);
+              const uint32_t sub = t ? s1 : s0;
+              if (!sub) continue;
+              mbar_wait(a_full + 8 * ra.slot, ra.phase);
               tc_fence_after();
-              const uint32_t a_s = smem_base + as * (kTileM * 128);
+              const uint32_t a_s = smem_base + ra.slot * kASlotBytes;
               const uint32_t d = tmem_base + (uint32_t)((par * a.T + t) * a.colstride);
-              for (int ks = 0; ks < kc / 16; ++ks) {
-                umma_bf16(d, umma_desc_sw128(a_s + ks * 32, 16, 1024), umma_desc_sw128(b_s + ks * 32, 16, 1024), idesc,
-                          (started[t] || ks > 0) ? 1u : 0u);
+              uint32_t acc = (started >> t) & 1u;
+              if (a.kpack == 1) {
+                const uint32_t wc = (c < a.nfull) ? 128u : 64u;
+                const int kc = (c < a.nfull) ? min(64, a.c_red - c * 64) : 32;
+                for (int ks = 0; ks < kc / 16; ++ks) {
+                  umma_bf16(d, umma_desc_sw(a_s + ks * 32, 16, 8 * wc, wc), umma_desc_sw(b_s + ks * 32, 16, 8 * wc, wc), idesc, acc);
+                  acc = 1u;
+                }
+              } else {
+                const uint32_t wa = (uint32_t)a.wa;
+                for (int j = 0; j < a.kpack; ++j) {
+                  if (!((sub >> j) & 1u)) continue;
+                  for (uint32_t ks = 0; ks < wa / 32; ++ks) {
+                    umma_bf16(d, umma_desc_sw(a_s + j * kTileM * wa + ks * 32, 16, 8 * wa, wa),
+                              umma_desc_sw(b_s + j * wa + ks * 32, 16, 1024, 128), idesc, acc);
+                    acc = 1u;
+                  }
+                }
               }
-              started[t] = true;
-              umma_commit(a_empty + 8 * as);
-              ++ai;
+              started |= 1u << t;
+              umma_commit(a_empty + 8 * ra.slot);
+              ra.next();
             }
-            umma_commit(b_empty + 8 * bs);
+            umma_commit(b_empty + 8 * rb.slot);
+            rb.next();
           }
         }
         umma_commit(acc_full + 8 * par);
@@ -291,50 +305,91 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_fwd_kernel(const FwdArgs 
   } else if (warp == 5) {
     // ================= B loader: bulk copies of pre-swizzled weight slices =================
     if (lane == 0) {
-      int bi = 0;
+      Ring rb;
+      rb.init(SB);
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
-        MaskBits m[2];
-        for (int t = 0; t < a.T; ++t) fwd_tile_mask(a, w * a.T + t, m[t]);
+        const MaskBits m0 = fwd_tile_mask(a, w * a.T);
+        const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
         for (int kg = 0; kg < a.nkg; ++kg) {
-          const bool act = mask_any(m[0], kg * a.kpack, a.kpack, a.kvol) ||
-                           ((a.T > 1) && mask_any(m[1], kg * a.kpack, a.kpack, a.kvol));
-          if (!act) continue;
-          for (int c = 0; c < a.nchunks; ++c, ++bi) {
-            const int bs = bi % SB;
-            mbar_wait(b_empty + 8 * bs, ((uint32_t)(bi / SB) & 1u) ^ 1u);
-            const uint32_t b_s = smem_base + a.off_b + bs * a.b_bytes;
-            const uint16_t* src = a.w + (((int64_t)kg * a.nchunks + c) * a.c_n + n0) * 64;
-            mbar_arrive_expect_tx(b_full + 8 * bs, (uint32_t)a.b_bytes);
-            bulk_g2s(b_s, src, (uint32_t)a.b_bytes, b_full + 8 * bs);
+          if (!(mask_bits(m0, kg * a.kpack, a.kpack) | mask_bits(m1, kg * a.kpack, a.kpack))) continue;
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u);
+            const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
+            const int wb = (c < a.nfull) ? 128 : 64;
+            const uint32_t bytes = (uint32_t)(a.ntile * wb);
+            const uint8_t* src = a.w + (int64_t)kg * a.kg_bytes + (int64_t)min(c, a.nfull) * a.c_n * 128 + (int64_t)n0 * wb;
+            mbar_arrive_expect_tx(b_full + 8 * rb.slot, bytes);
+            bulk_g2s(b_s, src, bytes, b_full + 8 * rb.slot);
+            rb.next();
           }
         }
       }
     }
     __syncwarp();
   } else {
-    // ================= producer warps: one A stage each =================
+    // ================= gather warps: A stage s is produced by warp s % kFwdProd =================
+    // Stage s is produced by warp s % np with np <= SA: a warp then never runs more than one use of a slot ahead
+    // of the consumer, which is what waiting on an mbarrier phase PARITY requires.
     const int p = warp - (kEpiWarps + 2);
-    int ai = 0;
+    const int np = min(kFwdProd, SA);
+    Ring ra;
+    ra.init(SA);
+    int turn = 0;  // stage counter modulo np
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
-      MaskBits m[2];
-      for (int t = 0; t < a.T; ++t) fwd_tile_mask(a, w * a.T + t, m[t]);
+      const MaskBits m0 = fwd_tile_mask(a, w * a.T);
+      const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
       for (int kg = 0; kg < a.nkg; ++kg) {
-        bool act[2];
-        act[0] = mask_any(m[0], kg * a.kpack, a.kpack, a.kvol);
-        act[1] = (a.T > 1) && mask_any(m[1], kg * a.kpack, a.kpack, a.kvol);
-        if (!(act[0] || act[1])) continue;
-        for (int c = 0; c < a.nchunks; ++c) {
+        const uint32_t s0 = mask_bits(m0, kg * a.kpack, a.kpack), s1 = mask_bits(m1, kg * a.kpack, a.kpack);
+        if (!(s0 | s1)) continue;
+        for (int c = 0; c < nch; ++c) {
           for (int t = 0; t < a.T; ++t) {
-            if (!act[t]) continue;
-            if (ai % P == p) {
-              mbar_wait(a_empty + 8 * p, ((uint32_t)(ai / P) & 1u) ^ 1u);
-              fwd_gather_stage(a, smem_base + p * (kTileM * 128), w * a.T + t, kg, c, lane);
-              cp_async_wait_all();
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(a_full + 8 * p);
+            const uint32_t sub = t ? s1 : s0;
+            if (!sub) continue;
+            if (turn == p) {
+              const int64_t pos0 = (int64_t)(w * a.T + t) * kTileM + 4 * lane;  // this lane gathers rows pos0 .. pos0+3
+              const uint32_t a_s = smem_base + ra.slot * kASlotBytes;
+              const uint32_t full = a_full + 8 * ra.slot;
+              if (a.kpack == 1) {
+                int4 idx;
+                if (a.nbr) {
+                  idx = ld_nc_int4(a.nbr + (int64_t)kg * a.n_pitch + pos0);
+                } else {
+                  idx.x = pos0 < a.n_out ? (int)pos0 : -1;
+                  idx.y = pos0 + 1 < a.n_out ? (int)pos0 + 1 : -1;
+                  idx.z = pos0 + 2 < a.n_out ? (int)pos0 + 2 : -1;
+                  idx.w = pos0 + 3 < a.n_out ? (int)pos0 + 3 : -1;
+                }
+                const uint32_t wc = (c < a.nfull) ? 128u : 64u;
+                mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u);
+                if (lane == 0) mbar_arrive_expect_tx(full, kTileM * wc);
+                __syncwarp();
+                tma_gather4(a_s + lane * 4 * wc, (c < a.nfull) ? &tm_main : &tm_rem, full, c * 64, idx.x, idx.y, idx.z, idx.w);
+              } else {
+                const uint32_t wa = (uint32_t)a.wa;
+                int4 idx[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (j < a.kpack && ((sub >> j) & 1u)) {
+                    if (a.nbr) {
+                      idx[j] = ld_nc_int4(a.nbr + (int64_t)(kg * a.kpack + j) * a.n_pitch + pos0);
+                    } else {  // identity map (kvol == 1): only j == 0 is ever set
+                      idx[j].x = pos0 < a.n_out ? (int)pos0 : -1;
+                      idx[j].y = pos0 + 1 < a.n_out ? (int)pos0 + 1 : -1;
+                      idx[j].z = pos0 + 2 < a.n_out ? (int)pos0 + 2 : -1;
+                      idx[j].w = pos0 + 3 < a.n_out ? (int)pos0 + 3 : -1;
+                    }
+                  }
+                mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u);
+                if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)__popc(sub) * kTileM * wa);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (j < a.kpack && ((sub >> j) & 1u))
+                    tma_gather4(a_s + j * kTileM * wa + lane * 4 * wa, &tm_main, full, 0, idx[j].x, idx[j].y, idx[j].z, idx[j].w);
+              }
             }
-            ++ai;
+            ra.next();
+            turn = (turn + 1 == np) ? 0 : turn + 1;
           }
         }
       }
@@ -352,36 +407,35 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_fwd_kernel(const FwdArgs 
 // ------------------------------------------------------------------------------------------------
 // wgrad kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kWgBProd = 4;                                    // warps 0-3: dY producers, then epilogue
-constexpr int kWgAProd = 6;                                    // A ring slots == gather warps
-constexpr int kWgThreads = (kWgBProd + 1 + kWgAProd) * 32;     // 352
+constexpr int kWgEpi = 4;                                       // warps 0-3: epilogue (TMEM lane quarters)
+constexpr int kWgAProd = 10;                                    // gather warps for the X operand
+constexpr int kWgBProd = 2;                                     // gather warps for the dY operand
+constexpr int kWgThreads = (kWgEpi + 1 + kWgBProd + kWgAProd) * 32;   // 544
 constexpr int kWgRows = 64;
+constexpr int kWgASlotBytes = 128 * kWgRows * 2;                // 16 KB: M = 128 x 64 reduction rows
 
 struct WgArgs {
-  const uint16_t* x; const uint16_t* dy; const int32_t* nbr; const int32_t* order; const uint32_t* gmask; float* dw;
-  int64_t n_out;
-  int c_in, c_out, kvol, mwords, cpad, pk, G, colstride, groups_per_cta, b_bytes, off_b, off_bars, tmem_cols;
+  const int32_t* nbr; const int32_t* order; const uint32_t* gmask; float* dw;
+  int64_t n_out, n_pitch;
+  int c_in, c_out, kvol, mwords, cpad, pk, G, colstride, groups_per_cta;
+  int wa, nab;    // X operand: row bytes of a block (128 / 64 / 32) and blocks per A stage (nab * wa / 2 == 128 M rows)
+  int wb, nbb;    // dY operand: row bytes of a block and number of column blocks
+  int a_slots, b_slots, b_bytes, off_b, off_bars, tmem_cols;
 };
 
-__device__ __forceinline__ void wg_group_mask(const WgArgs& a, int64_t g, MaskBits& m) {
-#pragma unroll
-  for (int w = 0; w < 4; ++w) m.w[w] = 0;
-  if (a.gmask == nullptr) { m.w[0] = 1u; return; }
-  for (int w = 0; w < a.mwords; ++w) m.w[w] = __ldg(a.gmask + g * a.mwords + w);
-}
-
-__global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgArgs a) {
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy, const WgArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int PA = kWgAProd, SB = kWgBProd;
+  const int SA = a.a_slots, SB = a.b_slots;
   const uint32_t bars = smem_base + a.off_bars;
-  const uint32_t a_full = bars, a_empty = bars + 8 * PA;
-  const uint32_t b_full = bars + 16 * PA, b_empty = b_full + 8 * SB;
-  const uint32_t accum_bar = b_empty + 8 * SB, flags_bar = accum_bar + 8;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + a.off_bars + 16 * PA + 16 * SB + 16);
-  uint8_t* used_s = smem + a.off_bars + 16 * PA + 16 * SB + 32;  // [16]
+  const uint32_t a_full = bars, a_empty = bars + 8 * SA;
+  const uint32_t b_full = bars + 16 * SA, b_empty = b_full + 8 * SB;
+  const uint32_t accum_bar = b_empty + 8 * SB;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + a.off_bars + 16 * SA + 16 * SB + 16);
+  uint32_t* used_s = tmem_ptr_s + 1;
 
   const int col = blockIdx.x;             // which G offset groups
   const int mt = blockIdx.z;              // M tile (input-channel block of 128) when c_in > 128
@@ -389,64 +443,51 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgArgs 
   const int64_t g_begin = (int64_t)blockIdx.y * a.groups_per_cta;
   const int64_t g_end = min(total_groups, g_begin + a.groups_per_cta);
   const int kbase = col * a.G * a.pk;     // first kernel offset of accumulator 0
+  const int nq = min(a.G, (a.kvol - kbase + a.pk - 1) / a.pk);   // accumulators of this CTA that hold real offsets
 
-  if (warp == kWgBProd && lane == 0) {
-    for (int s = 0; s < PA; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
+  if (warp == kWgEpi && lane == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
     mbar_init(accum_bar, 1);
-    mbar_init(flags_bar, 1);
     mbar_fence_init();
   }
-  if (warp == kWgBProd + 1) { tmem_alloc(smem_u32(tmem_ptr_s), (uint32_t)a.tmem_cols); tmem_relinquish(); }
-  if (tid < 16) used_s[tid] = 0;
+  if (warp == kWgEpi + 1) { tmem_alloc(smem_u32(tmem_ptr_s), (uint32_t)a.tmem_cols); tmem_relinquish(); }
+  if (warp == kWgEpi + 1 + kWgBProd && lane == 0) { tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_dy); }
+  if (tid == 0) *used_s = 0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
+  // offsets of accumulator q that occur in a row group with mask m (bit j = offset kbase + q*pk + j)
+  auto acc_bits = [&](const MaskBits& m, int q) -> uint32_t {
+    if (a.gmask == nullptr) return 1u;
+    const int k0 = kbase + q * a.pk;
+    uint32_t bits = 0;
+    for (int j0 = 0; j0 < a.pk; j0 += 4) bits |= mask_bits(m, k0 + j0, min(4, a.pk)) << j0;  // pk in {1,2,4,8}; k0 % pk == 0
+    return bits;
+  };
+  auto group_mask = [&](int64_t g) -> MaskBits {
+    if (a.gmask == nullptr) { MaskBits m = mask_zero(); m.w0 = 1u; return m; }
+    return mask_load(a.gmask, g, a.mwords);
+  };
   auto group_any = [&](const MaskBits& m) -> bool {
-    return mask_any(m, kbase, min(a.G * a.pk, 128), a.kvol);
+    bool any = false;
+    for (int q = 0; q < nq; ++q) any = any || (acc_bits(m, q) != 0);
+    return any;
   };
 
-  if (warp < kWgBProd) {
-    // ================= dY producers (B operand, MN-major): warp b owns B slot b =================
-    const int bgroups = a.c_out / 8;
-    int bi = 0;
-    for (int64_t g = g_begin; g < g_end; ++g) {
-      MaskBits m;
-      wg_group_mask(a, g, m);
-      if (!group_any(m)) continue;
-      if (bi % SB == warp) {
-        mbar_wait(b_empty + 8 * warp, ((uint32_t)(bi / SB) & 1u) ^ 1u);
-        const uint32_t b_s = smem_base + a.off_b + warp * a.b_bytes;
-        for (int i = lane; i < kWgRows * bgroups; i += 32) {
-          const int row = i / bgroups, jj = i % bgroups;
-          const int64_t pos = g * kWgRows + row;
-          const uint32_t dst = b_s + (jj >> 3) * (kWgRows * 128) + row * 128 + (((jj & 7) ^ (row & 7)) << 4);
-          if (pos < a.n_out) {
-            const int64_t o = a.order ? (int64_t)__ldg(a.order + pos) : pos;
-            cp_async16(dst, a.dy + o * a.c_out + jj * 8, 16u);
-          } else {
-            st_shared_zero16(dst);
-          }
-        }
-        cp_async_wait_all();
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_full + 8 * warp);
-      }
-      ++bi;
-    }
+  if (warp < kWgEpi) {
     // ================= epilogue: TMEM -> fp32 vector atomics into dw =================
     mbar_wait(accum_bar, 0);
-    mbar_wait(flags_bar, 0);
     tc_fence_after();
+    const uint32_t used = *reinterpret_cast<volatile uint32_t*>(used_s);
     const int mrow = warp * 32 + lane;              // TMEM lane == M row
     const int slot = mrow / a.cpad;                 // which packed offset
     const int ci = mrow % a.cpad + mt * 128;
     const int nchunk32 = (a.c_out + 31) / 32;
-    for (int q = 0; q < a.G; ++q) {
-      if (!used_s[q]) continue;
+    for (int q = 0; q < nq; ++q) {
+      if (!((used >> q) & 1u)) continue;
       const int k = kbase + q * a.pk + slot;
       const bool ok = slot < a.pk && k < a.kvol && ci < a.c_in;
       for (int cc = 0; cc < nchunk32; ++cc) {
@@ -468,100 +509,141 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgArgs 
         }
       }
     }
-  } else if (warp == kWgBProd) {
+  } else if (warp == kWgEpi) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, a.c_out, 1, 1);
-      bool used[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) used[q] = false;
-      int ai = 0, bi = 0;
+      const uint32_t wa = (uint32_t)a.wa, wb = (uint32_t)a.wb;
+      uint32_t used = 0;
+      Ring ra, rb;
+      ra.init(SA); rb.init(SB);
       for (int64_t g = g_begin; g < g_end; ++g) {
-        MaskBits m;
-        wg_group_mask(a, g, m);
+        const MaskBits m = group_mask(g);
         if (!group_any(m)) continue;
-        const int bs = bi % SB;
-        mbar_wait(b_full + 8 * bs, (uint32_t)(bi / SB) & 1u);
-        const uint32_t b_s = smem_base + a.off_b + bs * a.b_bytes;
+        mbar_wait(b_full + 8 * rb.slot, rb.phase);
+        const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
 #pragma unroll 1
-        for (int q = 0; q < a.G; ++q) {
-          if (!mask_any(m, kbase + q * a.pk, a.pk, a.kvol)) continue;
-          const int as = ai % PA;
-          mbar_wait(a_full + 8 * as, (uint32_t)(ai / PA) & 1u);
+        for (int q = 0; q < nq; ++q) {
+          if (!acc_bits(m, q)) continue;
+          mbar_wait(a_full + 8 * ra.slot, ra.phase);
           tc_fence_after();
-          const uint32_t a_s = smem_base + as * (2 * kWgRows * 128);
+          const uint32_t a_s = smem_base + ra.slot * kWgASlotBytes;
           const uint32_t d = tmem_base + (uint32_t)(q * a.colstride);
+          uint32_t acc = (used >> q) & 1u;
 #pragma unroll
           for (int ks = 0; ks < kWgRows / 16; ++ks) {
-            // MN-major SW128: LBO = stride between 64-element MN blocks, SBO = stride between 8-row K groups
-            umma_bf16(d, umma_desc_sw128(a_s + ks * 2048, kWgRows * 128, 1024),
-                      umma_desc_sw128(b_s + ks * 2048, kWgRows * 128, 1024), idesc, (used[q] || ks > 0) ? 1u : 0u);
+            // MN-major: LBO = stride between blocks (64-row x row_bytes each), SBO = stride between 8-row K groups
+            umma_bf16(d, umma_desc_sw(a_s + ks * 16 * wa, kWgRows * wa, 8 * wa, wa),
+                      umma_desc_sw(b_s + ks * 16 * wb, kWgRows * wb, 8 * wb, wb), idesc, acc);
+            acc = 1u;
           }
-          used[q] = true;
-          umma_commit(a_empty + 8 * as);
-          ++ai;
+          used |= 1u << q;
+          umma_commit(a_empty + 8 * ra.slot);
+          ra.next();
         }
-        umma_commit(b_empty + 8 * bs);
-        ++bi;
+        umma_commit(b_empty + 8 * rb.slot);
+        rb.next();
       }
-      umma_commit(accum_bar);
-#pragma unroll
-      for (int q = 0; q < 16; ++q) used_s[q] = used[q] ? 1 : 0;
+      *reinterpret_cast<volatile uint32_t*>(used_s) = used;
       __threadfence_block();
-      mbar_arrive(flags_bar);
+      umma_commit(accum_bar);
     }
     __syncwarp();
-  } else {
-    // ================= gather warps (A operand = X rows, MN-major): warp p owns A slot p =================
-    const int p = warp - (kWgBProd + 1);
-    const int j16 = lane & 15, rsel = lane >> 4;         // 16-byte group j16 of rows 2*it + rsel
-    const int m0 = j16 * 8;                               // first M row covered by this lane's group
-    const int slot = m0 / a.cpad;
-    const int ci = m0 % a.cpad + mt * 128;
-    int ai = 0;
+  } else if (warp <= kWgEpi + kWgBProd) {
+    // ================= dY producers (B operand, MN-major): gather rows order[g*64 ..]; stage s by warp s % kWgBProd ====
+    const int pb = warp - (kWgEpi + 1);
+    Ring rb;
+    rb.init(SB);
+    int turn = 0;
+    const int items = a.nbb * 16;   // (column block, 4-row quad)
     for (int64_t g = g_begin; g < g_end; ++g) {
-      MaskBits m;
-      wg_group_mask(a, g, m);
+      const MaskBits m = group_mask(g);
       if (!group_any(m)) continue;
-      for (int q = 0; q < a.G; ++q) {
-        if (!mask_any(m, kbase + q * a.pk, a.pk, a.kvol)) continue;
-        if (ai % PA == p) {
-          mbar_wait(a_empty + 8 * p, ((uint32_t)(ai / PA) & 1u) ^ 1u);
-          const uint32_t a_s = smem_base + p * (2 * kWgRows * 128);
-          const int k = kbase + q * a.pk + slot;
-          const bool lane_on = slot < a.pk && k < a.kvol && ci < a.c_in;
-          const int32_t* nb = (a.nbr && lane_on) ? a.nbr + (int64_t)k * a.n_out : nullptr;
-#pragma unroll 1
-          for (int it0 = 0; it0 < 32; it0 += 8) {
-            int32_t idx[8];
+      const bool mine = (turn == pb);
+      turn = (turn + 1 == kWgBProd) ? 0 : turn + 1;
+      if (!mine) { rb.next(); continue; }
+      const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
+      const uint32_t full = b_full + 8 * rb.slot;
+      const int64_t pos0 = g * kWgRows + 4 * (lane & 15);
+      int4 idx;
+      if (a.order) {
+        idx = ld_nc_int4(a.order + pos0);
+      } else {
+        idx.x = pos0 < a.n_out ? (int)pos0 : -1;
+        idx.y = pos0 + 1 < a.n_out ? (int)pos0 + 1 : -1;
+        idx.z = pos0 + 2 < a.n_out ? (int)pos0 + 2 : -1;
+        idx.w = pos0 + 3 < a.n_out ? (int)pos0 + 3 : -1;
+      }
+      mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u);
+      if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(a.nbb * kWgRows * a.wb));
+      __syncwarp();
+      for (int it = lane; it < items; it += 32) {
+        const int blk = it >> 4;
+        tma_gather4(b_s + blk * (kWgRows * a.wb) + (it & 15) * 4 * a.wb, &tm_dy, full, blk * 64, idx.x, idx.y, idx.z, idx.w);
+      }
+      rb.next();
+    }
+  } else {
+    // ================= gather warps (A operand = X rows, MN-major): A stage s is produced by warp s % kWgAProd ====
+    const int p = warp - (kWgEpi + 1 + kWgBProd);
+    const int np = min(kWgAProd, SA);   // <= SA, see conv_fwd_kernel
+    Ring ra;
+    ra.init(SA);
+    int turn = 0;
+    const int items = a.nab * 16;   // (block, 4-row quad); pk > 1: block == packed offset slot, else channel block
+    for (int64_t g = g_begin; g < g_end; ++g) {
+      const MaskBits m = group_mask(g);
+      if (!group_any(m)) continue;
+      for (int q = 0; q < nq; ++q) {
+        if (!acc_bits(m, q)) continue;
+        if (turn == p) {
+          const uint32_t a_s = smem_base + ra.slot * kWgASlotBytes;
+          const uint32_t full = a_full + 8 * ra.slot;
+          const int k0 = kbase + q * a.pk;
+          const int nslots = min(a.pk, a.kvol - k0);            // packed offsets that exist
+          const int64_t pos0 = g * kWgRows + 4 * (lane & 15);
+          // index quads: lane handles items it = lane, lane + 32, ...; for pk == 1 every block uses offset k0
+          int4 idx[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int64_t pos = g * kWgRows + 2 * (it0 + u) + rsel;
-              int32_t v = -1;
-              if (lane_on && pos < a.n_out) v = nb ? __ldg(nb + pos) : (int32_t)pos;
-              idx[u] = v;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int row = 2 * (it0 + u) + rsel;
-              const uint32_t dst = a_s + (j16 >> 3) * (kWgRows * 128) + row * 128 + (((j16 & 7) ^ (row & 7)) << 4);
-              if (idx[u] >= 0) cp_async16(dst, a.x + (int64_t)idx[u] * a.c_in + ci, 16u);
-              else st_shared_zero16(dst);
+          for (int u = 0; u < 4; ++u) {
+            const int it = lane + 32 * u;
+            const int blk = it >> 4;
+            if (it < items) {
+              const int k = (a.pk > 1) ? k0 + blk : k0;
+              if (a.pk > 1 && blk >= nslots) continue;
+              if (a.nbr) {
+                idx[u] = ld_nc_int4(a.nbr + (int64_t)k * a.n_pitch + pos0);
+              } else {
+                idx[u].x = pos0 < a.n_out ? (int)pos0 : -1;
+                idx[u].y = pos0 + 1 < a.n_out ? (int)pos0 + 1 : -1;
+                idx[u].z = pos0 + 2 < a.n_out ? (int)pos0 + 2 : -1;
+                idx[u].w = pos0 + 3 < a.n_out ? (int)pos0 + 3 : -1;
+              }
             }
           }
-          cp_async_wait_all();
-          fence_proxy_async();
+          mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u);
+          const int nblk = (a.pk > 1) ? nslots : a.nab;
+          if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(nblk * kWgRows * a.wa));
           __syncwarp();
-          if (lane == 0) mbar_arrive(a_full + 8 * p);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = lane + 32 * u;
+            const int blk = it >> 4;
+            if (it < items && !(a.pk > 1 && blk >= nslots)) {
+              const int colx = (a.pk > 1) ? 0 : mt * 128 + blk * 64;
+              tma_gather4(a_s + blk * (kWgRows * a.wa) + (it & 15) * 4 * a.wa, &tm_x, full, colx, idx[u].x, idx[u].y, idx[u].z, idx[u].w);
+            }
+          }
         }
-        ++ai;
+        ra.next();
+        turn = (turn + 1 == np) ? 0 : turn + 1;
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kWgBProd + 1) {
+  if (warp == kWgEpi + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
@@ -571,6 +653,31 @@ static int pow2_cols(int need) {
   int c = 32;
   while (c < need) c <<= 1;
   return c;
+}
+
+// ---- tensor maps (driver entry point resolved through the runtime, no link-time libcuda dependency) ----
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+static bool resolve_encode() {
+  if (g_encode_tiled) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return false;
+  g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return true;
+}
+// [rows, cols] bf16 row-major tensor, box = {box_cols, 1} for the row-gather mode, swizzle span = box bytes
+static bool make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int cols, int box_cols) {
+  if (!resolve_encode()) return false;
+  if (rows < 1) rows = 1;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, 1};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  return g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace b2m
@@ -595,16 +702,16 @@ extern "C" size_t b2m_packed_weight_bytes(int32_t kvol, int32_t c_in, int32_t c_
   const int c_red = (mode == 0) ? c_in : c_out;
   const int c_n = (mode == 0) ? c_out : c_in;
   const int kpack = conv_kpack(c_red);
-  const int nchunks = (kpack > 1) ? 1 : (c_red + 63) / 64;
   const int nkg = (kvol + kpack - 1) / kpack;
-  return (size_t)nkg * nchunks * c_n * 64 * sizeof(uint16_t);
+  return (size_t)nkg * c_n * (conv_nfull(c_red) * 128 + conv_rem(c_red) * 64);
 }
 
 extern "C" int b2m_pack_weights(const float* kernel, int32_t kvol, int32_t c_in, int32_t c_out, int32_t mode,
                                 uint16_t* packed, b2m_stream_t stream) {
   if (!kernel || !packed || kvol <= 0 || c_in <= 0 || c_out <= 0 || mode < 0 || mode > 2) return B2M_ERR_INVALID_ARGUMENT;
+  const int c_red = (mode == 0) ? c_in : c_out;
   const int c_n = (mode == 0) ? c_out : c_in;
-  if (c_n % 8 != 0) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (c_n % 8 != 0 || c_red % 16 != 0) return B2M_ERR_UNSUPPORTED_SHAPE;
   const int64_t total = (int64_t)(b2m_packed_weight_bytes(kvol, c_in, c_out, mode) / 16);
   pack_weights_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(kernel, kvol, c_in, c_out, mode, packed);
   B2M_CHECK_LAUNCH();
@@ -614,25 +721,29 @@ extern "C" int b2m_pack_weights(const float* kernel, int32_t kvol, int32_t c_in,
 extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, const int32_t* nbr, const int32_t* order,
                                 const uint32_t* group_mask, int32_t kvol, int64_t n_out, const uint16_t* packed_w,
                                 int32_t c_n, uint16_t* y, double* colsum, b2m_stream_t stream) {
-  (void)n_in;
-  if (!x || !packed_w || !y || kvol <= 0 || n_out < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (!x || !packed_w || !y || kvol <= 0 || n_out < 0 || n_in < 0) return B2M_ERR_INVALID_ARGUMENT;
   if (!nbr && kvol != 1) return B2M_ERR_INVALID_ARGUMENT;
   if (nbr && !group_mask) return B2M_ERR_INVALID_ARGUMENT;
   if (c_red <= 0 || c_red % 16 != 0 || c_n <= 0 || c_n % 16 != 0 || c_n > 512 || kvol > 128) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n_out == 0) return B2M_OK;
-  if (n_out >= ((int64_t)1 << 31) - 256) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (n_out >= ((int64_t)1 << 31) - 256 || n_in >= ((int64_t)1 << 31) - 256) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return B2M_ERR_INVALID_ARGUMENT;
   int ntiles_n = 1;
   while (c_n / ntiles_n > 256 || (c_n % ntiles_n) != 0 || ((c_n / ntiles_n) % 16) != 0) {
     ++ntiles_n;
     if (ntiles_n > 8) return B2M_ERR_UNSUPPORTED_SHAPE;
   }
   FwdArgs a;
-  a.x = x; a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr; a.w = packed_w; a.y = y;
-  a.colsum = colsum; a.n_out = n_out; a.c_red = c_red; a.kvol = kvol; a.c_n = c_n;
+  a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr;
+  a.w = reinterpret_cast<const uint8_t*>(packed_w); a.y = y;
+  a.colsum = colsum; a.n_out = n_out; a.n_pitch = b2m_map_pitch(n_out); a.c_red = c_red; a.kvol = kvol; a.c_n = c_n;
   a.ntile = c_n / ntiles_n;
   a.kpack = conv_kpack(c_red);
   a.nkg = (kvol + a.kpack - 1) / a.kpack;
-  a.nchunks = (a.kpack > 1) ? 1 : (c_red + 63) / 64;
+  a.nfull = conv_nfull(c_red);
+  a.rem = conv_rem(c_red);
+  a.wa = (a.kpack > 1) ? c_red * 2 : 128;
+  a.kg_bytes = c_n * (a.nfull * 128 + a.rem * 64);
   a.mwords = (kvol + 31) / 32;
   a.colstride = (a.ntile + 31) / 32 * 32;
   a.n_tiles = (int)((n_out + kTileM - 1) / kTileM);
@@ -640,15 +751,24 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   a.T = (a.ntile <= 128 && a.n_tiles >= 4 * sms) ? 2 : 1;
   a.n_work = (a.n_tiles + a.T - 1) / a.T;
   a.b_bytes = a.ntile * 128;
-  a.b_slots = (a.b_bytes >= 32768) ? 2 : 3;
-  a.off_b = kFwdProd * kTileM * 128;
+  a.b_slots = (a.b_bytes >= 32768) ? 2 : (a.b_bytes >= 16384 ? 3 : 4);
+  const int stage_bytes = kEpiWarps * 32 * kStagePitch * 4;
+  const int budget = 227 * 1024 - 1024 - 256 - stage_bytes - a.b_slots * a.b_bytes;
+  a.a_slots = budget / kASlotBytes;
+  if (a.a_slots > 10) a.a_slots = 10;
+  if (a.a_slots < 2) return B2M_ERR_UNSUPPORTED_SHAPE;
+  a.off_b = a.a_slots * kASlotBytes;
   a.off_stage = a.off_b + a.b_slots * a.b_bytes;
-  a.off_bars = a.off_stage + kEpiWarps * 32 * kStagePitch * 4;
+  a.off_bars = a.off_stage + stage_bytes;
   a.off_bars = (a.off_bars + 15) / 16 * 16;
   a.tmem_cols = pow2_cols(2 * a.T * a.colstride);
   if (a.tmem_cols > 512) return B2M_ERR_UNSUPPORTED_SHAPE;
-  const int smem_bytes = a.off_bars + 16 * kFwdProd + 16 * a.b_slots + 64 + 1024;
+  const int smem_bytes = a.off_bars + 16 * a.a_slots + 16 * a.b_slots + 64 + 1024;
   if (smem_bytes > 227 * 1024) return B2M_ERR_UNSUPPORTED_SHAPE;
+  CUtensorMap tm_main, tm_rem;
+  if (!make_row_map(&tm_main, x, n_in, c_red, a.kpack > 1 ? c_red : 64)) return B2M_ERR_CUDA_LAUNCH;
+  if (a.rem) { if (!make_row_map(&tm_rem, x, n_in, c_red, 32)) return B2M_ERR_CUDA_LAUNCH; }
+  else tm_rem = tm_main;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
@@ -659,7 +779,7 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   if (ntiles_n > 1) gx = (gx + ntiles_n - 1) / ntiles_n;   // keep the total CTA count near one per SM
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)ntiles_n);
-  conv_fwd_kernel<<<grid, kFwdThreads, smem_bytes, (cudaStream_t)stream>>>(a);
+  conv_fwd_kernel<<<grid, kFwdThreads, smem_bytes, (cudaStream_t)stream>>>(tm_main, tm_rem, a);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }
@@ -667,17 +787,22 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
 extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t* dy, int32_t c_out,
                               const int32_t* nbr, const int32_t* order, const uint32_t* group_mask, int32_t kvol,
                               int64_t n_out, float* dw, b2m_stream_t stream) {
-  (void)n_in;
-  if (!x || !dy || !dw || kvol <= 0 || n_out < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (!x || !dy || !dw || kvol <= 0 || n_out < 0 || n_in < 0) return B2M_ERR_INVALID_ARGUMENT;
   if (!nbr && kvol != 1) return B2M_ERR_INVALID_ARGUMENT;
   if (nbr && !group_mask) return B2M_ERR_INVALID_ARGUMENT;
   if (c_in <= 0 || c_in % 8 != 0 || c_out <= 0 || c_out % 16 != 0 || c_out > 256 || kvol > 128) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n_out == 0) return B2M_OK;
+  if (n_out >= ((int64_t)1 << 31) - 256 || n_in >= ((int64_t)1 << 31) - 256) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) != 0) return B2M_ERR_INVALID_ARGUMENT;
   WgArgs a;
-  a.x = x; a.dy = dy; a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr; a.dw = dw;
-  a.n_out = n_out; a.c_in = c_in; a.c_out = c_out; a.kvol = kvol; a.mwords = (kvol + 31) / 32;
+  a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr; a.dw = dw;
+  a.n_out = n_out; a.n_pitch = b2m_map_pitch(n_out); a.c_in = c_in; a.c_out = c_out; a.kvol = kvol; a.mwords = (kvol + 31) / 32;
   a.cpad = c_in <= 16 ? 16 : (c_in <= 32 ? 32 : (c_in <= 64 ? 64 : 128));
   a.pk = 128 / a.cpad;
+  a.wa = a.cpad >= 64 ? 128 : a.cpad * 2;
+  a.nab = 128 * 2 / a.wa;
+  a.wb = (c_out == 16 || c_out == 32) ? c_out * 2 : 128;
+  a.nbb = (c_out * 2 + a.wb - 1) / a.wb;
   const int mtiles = (c_in + 127) / 128;
   a.colstride = (c_out + 31) / 32 * 32;
   int G = 512 / a.colstride;
@@ -694,11 +819,19 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
   if (splits > total_groups) splits = total_groups;
   a.groups_per_cta = (int)((total_groups + splits - 1) / splits);
   splits = (total_groups + a.groups_per_cta - 1) / a.groups_per_cta;
-  a.b_bytes = ((c_out + 63) / 64) * kWgRows * 128;
-  a.off_b = kWgAProd * 2 * kWgRows * 128;
-  a.off_bars = a.off_b + kWgBProd * a.b_bytes;
-  const int smem_bytes = a.off_bars + 16 * kWgAProd + 16 * kWgBProd + 64 + 1024;
+  a.b_bytes = a.nbb * kWgRows * a.wb;
+  if (a.b_bytes < 1024) a.b_bytes = 1024;
+  a.b_bytes = (a.b_bytes + 1023) / 1024 * 1024;
+  a.b_slots = a.b_bytes >= 32768 ? 3 : 4;
+  a.a_slots = (227 * 1024 - 1024 - 256 - a.b_slots * a.b_bytes) / kWgASlotBytes;
+  if (a.a_slots > 10) a.a_slots = 10;
+  a.off_b = a.a_slots * kWgASlotBytes;
+  a.off_bars = a.off_b + a.b_slots * a.b_bytes;
+  const int smem_bytes = a.off_bars + 16 * a.a_slots + 16 * a.b_slots + 64 + 1024;
   if (smem_bytes > 227 * 1024) return B2M_ERR_UNSUPPORTED_SHAPE;
+  CUtensorMap tm_x, tm_dy;
+  if (!make_row_map(&tm_x, x, n_in, c_in, a.wa / 2)) return B2M_ERR_CUDA_LAUNCH;
+  if (!make_row_map(&tm_dy, dy, n_out, c_out, a.wb / 2)) return B2M_ERR_CUDA_LAUNCH;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
@@ -706,7 +839,7 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
     attr_set = true;
   }
   dim3 grid((unsigned)columns, (unsigned)splits, (unsigned)mtiles);
-  conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>(a);
+  conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>(tm_x, tm_dy, a);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }

@@ -61,12 +61,13 @@ __global__ void hash_query_kernel(const int4* __restrict__ q, int64_t m, const u
 __global__ void kmap_submanifold_kernel(const int4* __restrict__ coords, int64_t n, int ts, int ksize,
                                         const unsigned long long* __restrict__ keys,
                                         const int32_t* __restrict__ vals, uint64_t mask,
-                                        int32_t* __restrict__ nbr) {
+                                        int32_t* __restrict__ nbr, int64_t pitch) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int kvol = ksize * ksize * ksize;
-  if (gid >= n * kvol) return;
-  const int64_t row = gid % n;
-  const int k = (int)(gid / n);
+  if (gid >= pitch * kvol) return;
+  const int64_t row = gid % pitch;
+  const int k = (int)(gid / pitch);
+  if (row >= n) { nbr[gid] = -1; return; }  // padding up to the pitch
   const int h = ksize / 2;
   const int dx = (k % ksize - h) * ts;
   const int dy = ((k / ksize) % ksize - h) * ts;
@@ -118,10 +119,17 @@ __global__ void downsample_emit_kernel(const unsigned long long* __restrict__ so
 }
 
 __global__ void kmap_stride2_kernel(const int4* __restrict__ fine, int64_t n_fine, const int32_t* __restrict__ parent,
-                                    int64_t n_coarse, int fs, int32_t* __restrict__ nbr_down,
-                                    int32_t* __restrict__ nbr_up) {
+                                    int64_t coarse_pitch, int fs, int32_t* __restrict__ nbr_down,
+                                    int32_t* __restrict__ nbr_up, int64_t fine_pitch) {
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= n_fine) return;
+  if (f >= fine_pitch) return;
+  if (f >= n_fine) {
+    if (nbr_up) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) nbr_up[(int64_t)kk * fine_pitch + f] = -1;
+    }
+    return;
+  }
   const int4 c = __ldg(fine + f);
   const int cs = 2 * fs;
   const int ox = (c.y - floor_to_multiple(c.y, cs)) / fs;
@@ -129,45 +137,50 @@ __global__ void kmap_stride2_kernel(const int4* __restrict__ fine, int64_t n_fin
   const int oz = (c.w - floor_to_multiple(c.w, cs)) / fs;
   const int k = ox + 2 * oy + 4 * oz;
   const int32_t p = parent[f];
-  if (nbr_down) nbr_down[(int64_t)k * n_coarse + p] = (int32_t)f;
+  if (nbr_down) nbr_down[(int64_t)k * coarse_pitch + p] = (int32_t)f;
   if (nbr_up) {
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) nbr_up[(int64_t)kk * n_fine + f] = (kk == k) ? p : -1;
+    for (int kk = 0; kk < 8; ++kk) nbr_up[(int64_t)kk * fine_pitch + f] = (kk == k) ? p : -1;
   }
 }
 
-__global__ void kmap_count_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int32_t* __restrict__ counts) {
+__global__ void kmap_count_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int64_t pitch, int32_t* __restrict__ counts) {
   const int k = blockIdx.y;
   int local = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (int64_t)gridDim.x * blockDim.x)
-    local += nbr[(int64_t)k * n_out + i] >= 0;
+    local += nbr[(int64_t)k * pitch + i] >= 0;
   for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(counts + k, local);
 }
 
 // ---- kernel-map sorting: rows ordered by (block of rows, occupancy bit mask) so that the rows of a 128-row
 // ---- MMA tile share their set of present offsets (whole (tile, offset) blocks can then be skipped) ----
-__global__ void kmap_rowmask_kernel(const int32_t* __restrict__ nbr, int kvol, int64_t n_out, int block_rows,
+__global__ void kmap_rowmask_kernel(const int32_t* __restrict__ nbr, int kvol, int64_t n_out, int64_t pitch, int block_rows,
                                     unsigned long long* __restrict__ keys, int32_t* __restrict__ idx) {
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n_out) return;
   unsigned int m = 0;
-  for (int k = 0; k < kvol; ++k) m |= (unsigned int)(__ldg(nbr + (int64_t)k * n_out + o) >= 0) << k;
+  for (int k = 0; k < kvol; ++k) m |= (unsigned int)(__ldg(nbr + (int64_t)k * pitch + o) >= 0) << k;
   keys[o] = ((unsigned long long)(o / block_rows) << 32) | m;
   idx[o] = (int32_t)o;
 }
 
-__global__ void kmap_permute_kernel(const int32_t* __restrict__ nbr, int kvol, int64_t n_out,
-                                    const int32_t* __restrict__ order, int32_t* __restrict__ nbr_sorted) {
+__global__ void kmap_permute_kernel(const int32_t* __restrict__ nbr, int kvol, int64_t n_out, int64_t pitch,
+                                    int32_t* __restrict__ order, int32_t* __restrict__ nbr_sorted) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= n_out * kvol) return;
-  const int64_t j = gid % n_out;
-  const int64_t k = gid / n_out;
-  nbr_sorted[gid] = __ldg(nbr + k * n_out + __ldg(order + j));
+  if (gid >= pitch * kvol) return;
+  const int64_t j = gid % pitch;
+  const int64_t k = gid / pitch;
+  if (j >= n_out) {  // padding up to the pitch: no row, no neighbour
+    nbr_sorted[gid] = -1;
+    if (k == 0) order[j] = -1;
+    return;
+  }
+  nbr_sorted[gid] = __ldg(nbr + k * pitch + order[j]);
 }
 
 // group_mask[g][w]: bit (k % 32) of word (k / 32) set iff some row of the 64-row group g has offset k
-__global__ void kmap_groupmask_kernel(const int32_t* __restrict__ nbr_sorted, int kvol, int64_t n_out, int words,
+__global__ void kmap_groupmask_kernel(const int32_t* __restrict__ nbr_sorted, int kvol, int64_t n_out, int64_t pitch, int words,
                                       uint32_t* __restrict__ group_mask) {
   const int64_t g = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,8 +191,8 @@ __global__ void kmap_groupmask_kernel(const int32_t* __restrict__ nbr_sorted, in
   for (int k = warp; k < kvol; k += nwarps) {
     const int64_t r = g * 64 + lane;
     bool v = false;
-    if (r < n_out) v = __ldg(nbr_sorted + (int64_t)k * n_out + r) >= 0;
-    if (r + 32 < n_out) v = v || (__ldg(nbr_sorted + (int64_t)k * n_out + r + 32) >= 0);
+    if (r < n_out) v = __ldg(nbr_sorted + (int64_t)k * pitch + r) >= 0;
+    if (r + 32 < n_out) v = v || (__ldg(nbr_sorted + (int64_t)k * pitch + r + 32) >= 0);
     const unsigned any = __ballot_sync(0xffffffffu, v);
     if (lane == 0 && any) atomicOr(&sm[k >> 5], 1u << (k & 31));
   }
@@ -187,9 +200,9 @@ __global__ void kmap_groupmask_kernel(const int32_t* __restrict__ nbr_sorted, in
   if (threadIdx.x < words) group_mask[g * words + threadIdx.x] = sm[threadIdx.x];
 }
 
-__global__ void iota_kernel(int32_t* __restrict__ out, int64_t n) {
+__global__ void iota_kernel(int32_t* __restrict__ out, int64_t n, int64_t pitch) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (int32_t)i;
+  if (i < pitch) out[i] = (i < n) ? (int32_t)i : -1;
 }
 
 struct DownsampleWs {
@@ -293,16 +306,19 @@ extern "C" int b2m_downsample_coords(const int32_t* coords, int64_t n, int32_t n
   return B2M_OK;
 }
 
+extern "C" int64_t b2m_map_pitch(int64_t n) { return (n + 127) / 128 * 128; }
+
 extern "C" int b2m_kernel_map_submanifold(const int32_t* coords, int64_t n, int32_t tensor_stride, int32_t kernel_size,
                                           const uint64_t* table_keys, const int32_t* table_vals, int64_t capacity,
                                           int32_t* nbr, b2m_stream_t stream) {
   if (kernel_size != 1 && kernel_size != 3 && kernel_size != 5) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n == 0) return B2M_OK;
   if (!coords || !table_keys || !table_vals || !nbr || n < 0 || tensor_stride <= 0) return B2M_ERR_INVALID_ARGUMENT;
-  const int64_t total = n * kernel_size * kernel_size * kernel_size;
+  const int64_t pitch = b2m_map_pitch(n);
+  const int64_t total = pitch * kernel_size * kernel_size * kernel_size;
   kmap_submanifold_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const int4*>(coords), n, tensor_stride, kernel_size,
-      reinterpret_cast<const unsigned long long*>(table_keys), table_vals, (uint64_t)(capacity - 1), nbr);
+      reinterpret_cast<const unsigned long long*>(table_keys), table_vals, (uint64_t)(capacity - 1), nbr, pitch);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }
@@ -312,11 +328,12 @@ extern "C" int b2m_kernel_map_stride2(const int32_t* fine_coords, int64_t n_fine
                                       b2m_stream_t stream) {
   if (!fine_coords || !parent_row || n_fine < 0 || n_coarse < 0 || fine_stride <= 0) return B2M_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
+  const int64_t coarse_pitch = b2m_map_pitch(n_coarse), fine_pitch = b2m_map_pitch(n_fine);
   if (nbr_down && n_coarse > 0)
-    if (cudaMemsetAsync(nbr_down, 0xFF, (size_t)8 * n_coarse * 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+    if (cudaMemsetAsync(nbr_down, 0xFF, (size_t)8 * coarse_pitch * 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
   if (n_fine == 0) return B2M_OK;
-  kmap_stride2_kernel<<<cdiv(n_fine, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(fine_coords), n_fine, parent_row,
-                                                        n_coarse, fine_stride, nbr_down, nbr_up);
+  kmap_stride2_kernel<<<cdiv(fine_pitch, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(fine_coords), n_fine, parent_row,
+                                                            coarse_pitch, fine_stride, nbr_down, nbr_up, fine_pitch);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }
@@ -328,7 +345,7 @@ extern "C" int b2m_kernel_map_count(const int32_t* nbr, int32_t kvol, int64_t n_
   if (n_out == 0) return B2M_OK;
   int bx = cdiv(n_out, 256 * 8);
   if (bx > 1024) bx = 1024;
-  kmap_count_kernel<<<dim3(bx, kvol), 256, 0, st>>>(nbr, n_out, counts);
+  kmap_count_kernel<<<dim3(bx, kvol), 256, 0, st>>>(nbr, n_out, b2m_map_pitch(n_out), counts);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }
@@ -343,7 +360,8 @@ extern "C" int b2m_kernel_map_sort(const int32_t* nbr, int32_t kvol, int64_t n_o
   if (n_out >= (int64_t)1 << 31) return B2M_ERR_UNSUPPORTED_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   const int words = (kvol + 31) / 32;
-  const int blocks = cdiv(n_out, 256);
+  const int64_t pitch = b2m_map_pitch(n_out);
+  const int blocks = cdiv(pitch, 256);
   const bool do_sort = block_rows > 0 && kvol <= 32;
   if (do_sort) {
     if (!workspace) return B2M_ERR_INVALID_ARGUMENT;
@@ -353,7 +371,7 @@ extern "C" int b2m_kernel_map_sort(const int32_t* nbr, int32_t kvol, int64_t n_o
     auto* keys_in = reinterpret_cast<unsigned long long*>(ws + w.off_keys_in);
     auto* keys_out = reinterpret_cast<unsigned long long*>(ws + w.off_keys_out);
     auto* idx_in = reinterpret_cast<int32_t*>(ws + w.off_idx_in);
-    kmap_rowmask_kernel<<<blocks, 256, 0, st>>>(nbr, kvol, n_out, block_rows, keys_in, idx_in);
+    kmap_rowmask_kernel<<<blocks, 256, 0, st>>>(nbr, kvol, n_out, pitch, block_rows, keys_in, idx_in);
     B2M_CHECK_LAUNCH();
     int64_t nblk = (n_out + block_rows - 1) / block_rows;
     int end_bit = 32;
@@ -361,20 +379,20 @@ extern "C" int b2m_kernel_map_sort(const int32_t* nbr, int32_t kvol, int64_t n_o
     size_t cub_bytes = w.cub_bytes;
     if (cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, keys_in, keys_out, idx_in, order, (int)n_out, 0, end_bit, st) != cudaSuccess)
       return B2M_ERR_CUDA_LAUNCH;
-    kmap_permute_kernel<<<cdiv(n_out * kvol, 256), 256, 0, st>>>(nbr, kvol, n_out, order, nbr_sorted);
+    kmap_permute_kernel<<<cdiv(pitch * kvol, 256), 256, 0, st>>>(nbr, kvol, n_out, pitch, order, nbr_sorted);
     B2M_CHECK_LAUNCH();
   } else {
-    iota_kernel<<<blocks, 256, 0, st>>>(order, n_out);
+    iota_kernel<<<blocks, 256, 0, st>>>(order, n_out, pitch);
     B2M_CHECK_LAUNCH();
     if (nbr_sorted != nbr)
-      if (cudaMemcpyAsync(nbr_sorted, nbr, (size_t)kvol * n_out * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+      if (cudaMemcpyAsync(nbr_sorted, nbr, (size_t)kvol * pitch * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
   }
-  kmap_groupmask_kernel<<<(unsigned)((n_out + 63) / 64), 256, 0, st>>>(nbr_sorted, kvol, n_out, words, group_mask);
+  kmap_groupmask_kernel<<<(unsigned)((n_out + 63) / 64), 256, 0, st>>>(nbr_sorted, kvol, n_out, pitch, words, group_mask);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }
 
-extern "C" int b2m_version(void) { return 2; }
+extern "C" int b2m_version(void) { return 3; }
 
 extern "C" const char* b2m_error_string(int code) {
   switch (code) {

@@ -33,7 +33,7 @@ class CoordinateManager:
         key = (stride, ksize)
         if key not in self.sub_maps:
             nbr = ops.kernel_map_submanifold(self.levels[stride], stride, ksize, self.table(stride))
-            self.sub_maps[key] = ops.sort_kernel_map(nbr)
+            self.sub_maps[key] = ops.sort_kernel_map(nbr, self.levels[stride].shape[0])
         return self.sub_maps[key]
 
     def stride2_maps(self, fine_stride):
@@ -43,7 +43,8 @@ class CoordinateManager:
             coarse, parent = ops.downsample_coords(fine, 2 * fine_stride)
             self.levels[2 * fine_stride] = coarse
             nbr_down, nbr_up = ops.kernel_map_stride2(fine, parent, coarse.shape[0], fine_stride)
-            self.stride2[fine_stride] = (ops.sort_kernel_map(nbr_down), ops.sort_kernel_map(nbr_up))
+            self.stride2[fine_stride] = (ops.sort_kernel_map(nbr_down, coarse.shape[0]),
+                                         ops.sort_kernel_map(nbr_up, fine.shape[0]))
         return self.stride2[fine_stride]
 
 

@@ -109,10 +109,16 @@ def downsample_coords(coords, new_stride):
     return out[:m].contiguous(), parent
 
 
+def map_pitch(n):
+    """Row pitch of every neighbour table / `order` array over n rows (b2m_map_pitch): n rounded up to 128."""
+    return (int(n) + 127) // 128 * 128
+
+
 def kernel_map_submanifold(coords, tensor_stride, kernel_size, table):
+    """-> nbr int32[K^3, pitch(n)] (columns >= n hold -1)."""
     lib = _lib_or_raise()
     n = coords.shape[0]
-    nbr = torch.empty((kernel_size ** 3, n), dtype=torch.int32, device=coords.device)
+    nbr = torch.empty((kernel_size ** 3, map_pitch(n)), dtype=torch.int32, device=coords.device)
     _run("kernel_map_submanifold", 1, lambda: check(lib.b2m_kernel_map_submanifold(
         ptr(coords), n, int(tensor_stride), int(kernel_size), ptr(table.keys), ptr(table.vals), table.capacity, ptr(nbr),
         stream_ptr()), "kernel_map_submanifold"), nbytes=16 * n + 4 * n * kernel_size ** 3)
@@ -122,8 +128,8 @@ def kernel_map_submanifold(coords, tensor_stride, kernel_size, table):
 def kernel_map_stride2(fine_coords, parent_row, n_coarse, fine_stride):
     lib = _lib_or_raise()
     n_fine = fine_coords.shape[0]
-    nbr_down = torch.empty((8, n_coarse), dtype=torch.int32, device=fine_coords.device)
-    nbr_up = torch.empty((8, n_fine), dtype=torch.int32, device=fine_coords.device)
+    nbr_down = torch.empty((8, map_pitch(n_coarse)), dtype=torch.int32, device=fine_coords.device)
+    nbr_up = torch.empty((8, map_pitch(n_fine)), dtype=torch.int32, device=fine_coords.device)
     _run("kernel_map_stride2", 1, lambda: check(lib.b2m_kernel_map_stride2(
         ptr(fine_coords), n_fine, ptr(parent_row), n_coarse, int(fine_stride), ptr(nbr_down), ptr(nbr_up), stream_ptr()),
         "kernel_map_stride2"), nbytes=20 * n_fine + 32 * n_fine + 32 * n_coarse)
@@ -131,8 +137,9 @@ def kernel_map_stride2(fine_coords, parent_row, n_coarse, fine_stride):
 
 
 class KernelMap:
-    """Sorted kernel map consumed by the convolutions: nbr int32[K, n_out] (already permuted), order int32[n_out]
-    (position -> output row), gmask uint32-as-int32 [groups, words]. `raw` keeps the unsorted table (tests)."""
+    """Sorted kernel map consumed by the convolutions: nbr int32[K, pitch(n_out)] (already permuted), order
+    int32[pitch(n_out)] (position -> output row, -1 in the padding), gmask uint32-as-int32 [groups, words].
+    `raw` keeps the unsorted table (tests)."""
     __slots__ = ("nbr", "order", "gmask", "kvol", "n_out", "raw")
 
     def __init__(self, nbr, order, gmask, kvol, n_out, raw=None):
@@ -142,14 +149,27 @@ class KernelMap:
 SORT_BLOCK_ROWS = 32768
 
 
-def sort_kernel_map(nbr, block_rows=None, keep_raw=False):
+def pad_table(nbr):
+    """Unpadded table int32[K, n] (e.g. built on the host by a test) -> int32[K, pitch(n)] with -1 padding."""
+    n = nbr.shape[1]
+    return torch.nn.functional.pad(nbr, (0, map_pitch(n) - n), value=-1).contiguous()
+
+
+def sort_kernel_map(nbr, n_out=None, block_rows=None, keep_raw=False):
+    """nbr int32[K, pitch(n_out)] from kernel_map_submanifold / kernel_map_stride2 -> KernelMap.
+    With n_out=None the table is taken as unpadded int32[K, n_out] and padded first."""
     lib = _lib_or_raise()
     _cuda(nbr, torch.int32, "nbr")
-    kvol, n_out = nbr.shape
+    if n_out is None:
+        n_out = nbr.shape[1]
+        nbr = pad_table(nbr)
+    kvol, pitch = nbr.shape
+    if pitch != map_pitch(n_out):
+        raise _lib.B2MError("neighbour table must have the padded pitch %d, got %d" % (map_pitch(n_out), pitch))
     if block_rows is None:
         block_rows = SORT_BLOCK_ROWS
     words = (kvol + 31) // 32
-    order = torch.empty(n_out, dtype=torch.int32, device=nbr.device)
+    order = torch.empty(pitch, dtype=torch.int32, device=nbr.device)
     do_sort = block_rows > 0 and kvol <= 32
     nbr_sorted = torch.empty_like(nbr) if do_sort else nbr
     gmask = torch.empty(((n_out + 63) // 64, words), dtype=torch.int32, device=nbr.device)
@@ -161,10 +181,11 @@ def sort_kernel_map(nbr, block_rows=None, keep_raw=False):
     return KernelMap(nbr_sorted, order, gmask, kvol, n_out, nbr if keep_raw else None)
 
 
-def kernel_map_count(nbr):
+def kernel_map_count(nbr, n_out):
+    """pairs per offset of a padded table int32[K, pitch(n_out)]."""
     lib = _lib_or_raise()
     counts = torch.empty(nbr.shape[0], dtype=torch.int32, device=nbr.device)
-    check(lib.b2m_kernel_map_count(ptr(nbr), nbr.shape[0], nbr.shape[1], ptr(counts), stream_ptr()), "kernel_map_count")
+    check(lib.b2m_kernel_map_count(ptr(nbr), nbr.shape[0], int(n_out), ptr(counts), stream_ptr()), "kernel_map_count")
     return counts
 
 

@@ -14,7 +14,9 @@
  *    unless stated; re-entrant; no global mutable state.
  *  - return 0 (B2M_OK) or a negative error code; never throws. `b2m_error_string` names a code.
  *  - "bf16" = __nv_bfloat16 bit patterns carried as uint16_t.
- *  - Kernel maps are dense neighbour tables `nbr[K][n_out]` (int32, -1 = no neighbour): entry
+ *  - Kernel maps are dense neighbour tables `nbr[K][pitch]` (int32, -1 = no neighbour), pitch =
+ *    b2m_map_pitch(n_out) = n_out rounded up to 128 (columns >= n_out hold -1, so a 128-row MMA tile and
+ *    the 16-byte index loads of the TMA row gathers never run off a row of the table): entry
  *    (k, o) is the input row whose coordinate equals coord(o) + delta_k. Offsets enumerate with the
  *    first spatial axis fastest, k = ix + K*iy + K*K*iz; odd kernels are centred, even kernels start
  *    at 0 (MinkowskiEngine region-iterator convention).
@@ -72,7 +74,9 @@ int b2m_downsample_coords(const int32_t* coords, int64_t n, int32_t new_stride, 
 /* ------------------------------------------------------------------------------------------------
  * Kernel maps
  * ---------------------------------------------------------------------------------------------- */
-/* stride-1 (submanifold) map for an odd kernel (3 or 5): nbr int32[K^3, n].
+/* row pitch of every neighbour table / `order` array over n output rows: n rounded up to a multiple of 128 */
+int64_t b2m_map_pitch(int64_t n);
+/* stride-1 (submanifold) map for an odd kernel (3 or 5): nbr int32[K^3, pitch(n)].
  * reference: MinkowskiConvolution(kernel_size=3) models/resnet.py:61-65; kernel_size=5
  * models/detection_net.py:37 */
 int b2m_kernel_map_submanifold(const int32_t* coords, int64_t n, int32_t tensor_stride,
@@ -80,8 +84,8 @@ int b2m_kernel_map_submanifold(const int32_t* coords, int64_t n, int32_t tensor_
                                const int32_t* table_vals, int64_t capacity, int32_t* nbr,
                                b2m_stream_t stream);
 /* kernel 2 / stride 2 maps from the parent relation of b2m_downsample_coords.
- * nbr_down int32[8, n_coarse]: child row of coarse row o at offset k (strided conv, coarse output).
- * nbr_up   int32[8, n_fine]  : parent row if offset(f)==k else -1 (transposed conv, fine output).
+ * nbr_down int32[8, pitch(n_coarse)]: child row of coarse row o at offset k (strided conv, coarse output).
+ * nbr_up   int32[8, pitch(n_fine)]  : parent row if offset(f)==k else -1 (transposed conv, fine output).
  * reference: models/detection_net.py:42-82 (down) and :88-133 (MinkowskiConvolutionTranspose) */
 int b2m_kernel_map_stride2(const int32_t* fine_coords, int64_t n_fine, const int32_t* parent_row,
                            int64_t n_coarse, int32_t fine_stride, int32_t* nbr_down, int32_t* nbr_up,
@@ -95,8 +99,8 @@ int b2m_kernel_map_count(const int32_t* nbr, int32_t kvol, int64_t n_out, int32_
 /* Sorted kernel map, the form the convolutions consume. Rows are ordered by (row / block_rows, occupancy bit
  * mask of the row) with a stable radix sort, so that the 128 rows of an MMA tile share their set of present
  * offsets and (tile, offset) blocks without any pair are skipped. Outputs:
- *   order      int32[n_out]        position -> original output row
- *   nbr_sorted int32[K, n_out]     nbr_sorted[k][j] = nbr[k][order[j]]
+ *   order      int32[pitch]        position -> original output row (-1 in the padding)
+ *   nbr_sorted int32[K, pitch]     nbr_sorted[k][j] = nbr[k][order[j]]
  *   group_mask uint32[ceil(n_out/64), ceil(K/32)]  offsets present in each 64-row group of the sorted order
  * block_rows <= 0 or K > 32 keeps the original order (identity `order`), masks are still produced.
  * The set of (k, in, out) pairs is unchanged — this is a traversal order, not a different map. */

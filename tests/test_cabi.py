@@ -21,10 +21,11 @@ def test_library_builds_and_exports_header():
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(_lib.SIGNATURES) == syms            # the ctypes table mirrors the header one to one
-    assert lib.b2m_version() == 2
+    assert lib.b2m_version() == 3
     assert lib.b2m_error_string(-4) == b"unsupported shape"
     assert lib.b2m_hash_capacity(1000) == 2048 and lib.b2m_hash_capacity(0) == 1024
-    assert lib.b2m_packed_weight_bytes(27, 96, 128, 0) == 27 * 2 * 128 * 64 * 2
+    assert lib.b2m_packed_weight_bytes(27, 96, 128, 0) == 27 * 128 * (128 + 64)   # one SW128 chunk + one SW64 remainder
+    assert lib.b2m_map_pitch(129) == 256 and lib.b2m_map_pitch(0) == 0
 
 
 def test_product_does_not_import_oracle():

@@ -61,8 +61,10 @@ def test_kernel_map_submanifold_bit_exact(scene_coords, ksize, ts):
     c = torch.from_numpy(scene_coords).to(DEV)
     nbr = ops.kernel_map_submanifold(c, ts, ksize, ops.hash_build(c))
     ref = so.kernel_map_submanifold(scene_coords, ts, ksize)
-    assert np.array_equal(nbr.cpu().numpy(), ref)
-    counts = ops.kernel_map_count(nbr).cpu().numpy()
+    n = len(scene_coords)
+    assert nbr.shape == (ksize ** 3, ops.map_pitch(n))          # padded pitch, -1 in the padding
+    assert np.array_equal(nbr.cpu().numpy()[:, :n], ref) and bool((nbr[:, n:] == -1).all())
+    counts = ops.kernel_map_count(nbr, n).cpu().numpy()
     assert np.array_equal(counts, (ref >= 0).sum(1))
 
 
@@ -77,11 +79,13 @@ def test_strided_levels_bit_exact(scene_coords):
         assert np.array_equal(parent.cpu().numpy(), ref_parent), level
         nd, nu = ops.kernel_map_stride2(cur, parent, len(ref_out), ts)
         rd, ru = so.kernel_map_stride2(cur_np, ref_parent, len(ref_out), ts)
-        assert np.array_equal(nd.cpu().numpy(), rd) and np.array_equal(nu.cpu().numpy(), ru), level
+        assert np.array_equal(nd.cpu().numpy()[:, :len(ref_out)], rd), level
+        assert np.array_equal(nu.cpu().numpy()[:, :len(cur_np)], ru), level
+        assert bool((nd[:, len(ref_out):] == -1).all()) and bool((nu[:, len(cur_np):] == -1).all()), level
         ts *= 2
         cur_np, cur = ref_out, out
         nbr = ops.kernel_map_submanifold(cur, ts, 3, ops.hash_build(cur))
-        assert np.array_equal(nbr.cpu().numpy(), so.kernel_map_submanifold(cur_np, ts, 3)), level
+        assert np.array_equal(nbr.cpu().numpy()[:, :len(cur_np)], so.kernel_map_submanifold(cur_np, ts, 3)), level
 
 
 @pytest.mark.parametrize("block_rows", [4096, 0])
@@ -90,9 +94,11 @@ def test_sorted_kernel_map(scene_coords, block_rows):
     nbr_np = so.kernel_map_submanifold(scene_coords, 1, 3)
     n = nbr_np.shape[1]
     km = ops.sort_kernel_map(torch.from_numpy(nbr_np).to(DEV), block_rows=block_rows)
-    order = km.order.cpu().numpy()
+    assert km.order.shape == (ops.map_pitch(n),) and km.nbr.shape == (27, ops.map_pitch(n))
+    assert bool((km.order[n:] == -1).all()) and bool((km.nbr[:, n:] == -1).all())
+    order = km.order.cpu().numpy()[:n]
     assert np.array_equal(np.sort(order), np.arange(n))
-    assert np.array_equal(km.nbr.cpu().numpy(), nbr_np[:, order])
+    assert np.array_equal(km.nbr.cpu().numpy()[:, :n], nbr_np[:, order])
     mask = np.zeros(n, np.uint64)
     for k in range(27):
         mask |= (nbr_np[k] >= 0).astype(np.uint64) << np.uint64(k)
@@ -108,7 +114,7 @@ def test_sorted_kernel_map(scene_coords, block_rows):
     # 125-offset map: never sorted, 4 mask words
     nbr5 = so.kernel_map_submanifold(scene_coords[:3000], 1, 5)
     km5 = ops.sort_kernel_map(torch.from_numpy(nbr5).to(DEV))
-    assert np.array_equal(km5.order.cpu().numpy(), np.arange(3000)) and km5.gmask.shape == (47, 4)
+    assert np.array_equal(km5.order.cpu().numpy()[:3000], np.arange(3000)) and km5.gmask.shape == (47, 4)
     bits = np.unpackbits(km5.gmask.cpu().numpy().view(np.uint8).reshape(47, 16), axis=1, bitorder="little")[:, :125]
     ref_bits = np.pad(nbr5 >= 0, ((0, 0), (0, 47 * 64 - 3000))).reshape(125, 47, 64).any(2).T
     assert np.array_equal(bits.astype(bool), ref_bits)
@@ -120,7 +126,7 @@ def test_kernel_map_negative_and_unsorted():
     c_np = _coords(xyz)[rng.permutation(len(xyz))]
     c = torch.from_numpy(c_np).to(DEV)
     nbr = ops.kernel_map_submanifold(c, 1, 3, ops.hash_build(c))
-    assert np.array_equal(nbr.cpu().numpy(), so.kernel_map_submanifold(c_np, 1, 3))
+    assert np.array_equal(nbr.cpu().numpy()[:, :len(c_np)], so.kernel_map_submanifold(c_np, 1, 3))
     out, parent = ops.downsample_coords(c, 2)
     ro, rp = so.downsample_coords(c_np, 2)
     assert np.array_equal(out.cpu().numpy(), ro) and np.array_equal(parent.cpu().numpy(), rp)
@@ -149,7 +155,8 @@ def _conv_case(kvol, c_in, c_out, n, seed, real_map=None):
 @pytest.mark.parametrize("kvol,c_in,c_out,n", [
     (27, 32, 32, 4000), (27, 64, 64, 3000), (27, 128, 96, 6000), (27, 96, 96, 515), (8, 256, 256, 2000),
     (27, 512, 256, 700), (27, 256, 512, 700), (27, 384, 256, 500), (125, 16, 32, 3000), (1, 32, 64, 300),
-    (1, 256, 256, 129), (27, 192, 128, 1), (8, 96, 96, 127),
+    (1, 256, 256, 129), (27, 192, 128, 1), (8, 96, 96, 127), (8, 48, 32, 500), (27, 80, 64, 300), (27, 160, 16, 260),
+    (1, 96, 128, 40000), (27, 32, 96, 33000),
 ])
 def test_conv_forward(kvol, c_in, c_out, n):
     nbr_np, x, w, n = _conv_case(kvol, c_in, c_out, n, seed=kvol + c_in)
@@ -201,6 +208,7 @@ def test_conv_forward_real_maps_and_dgrad(scene_coords):
 @pytest.mark.parametrize("kvol,c_in,c_out,n", [
     (27, 64, 64, 3000), (27, 128, 96, 6000), (27, 96, 96, 515), (27, 32, 32, 4000), (8, 256, 256, 2000),
     (27, 512, 256, 700), (125, 16, 32, 3000), (1, 64, 64, 1000), (8, 96, 128, 70000), (27, 192, 128, 63),
+    (27, 48, 16, 400), (8, 32, 96, 5000), (27, 16, 16, 900), (1, 128, 96, 20000),
 ])
 def test_conv_wgrad(kvol, c_in, c_out, n):
     nbr_np, x, _, n = _conv_case(kvol, c_in, c_out, n, seed=kvol + c_out)

@@ -36,7 +36,7 @@ n = coords.shape[0]
 t0 = time.time()
 table = ops.hash_build(coords)
 nbr = ops.kernel_map_submanifold(coords, 1, args.ksize, table)
-km = ops.sort_kernel_map(nbr, block_rows=args.block_rows)
+km = ops.sort_kernel_map(nbr, n, block_rows=args.block_rows)
 torch.cuda.synchronize()
 kvol = args.ksize ** 3
 pairs = int((nbr >= 0).sum())

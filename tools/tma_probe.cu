@@ -113,7 +113,6 @@ int main() {
   struct Case { const char* name; int box_cols, box_rows, col, r[4]; uint32_t tx; CUtensorMapSwizzle sw; };
   const Case cases[] = {
       {"box{64,1} sw128 rows 5,17,100,599 tx512", 64, 1, 0, {5, 17, 100, 599}, 512, CU_TENSOR_MAP_SWIZZLE_128B},
-      {"box{64,4} sw128 rows 5,17,100,599 tx512", 64, 4, 0, {5, 17, 100, 599}, 512, CU_TENSOR_MAP_SWIZZLE_128B},
       {"box{64,1} sw128 rows 5,-1,100,600 (oob rows) tx512", 64, 1, 0, {5, -1, 100, 600}, 512, CU_TENSOR_MAP_SWIZZLE_128B},
       {"box{64,1} sw128 col 64 (overhang, c=96) tx512", 64, 1, 64, {5, 17, 100, 599}, 512, CU_TENSOR_MAP_SWIZZLE_128B},
       {"box{32,1} sw64 col 64 tx256", 32, 1, 64, {5, 17, 100, 599}, 256, CU_TENSOR_MAP_SWIZZLE_64B},
