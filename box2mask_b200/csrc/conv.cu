@@ -13,6 +13,9 @@
 // tensor into shared memory with the swizzle the UMMA descriptors expect; rows with index -1 (no neighbour) and
 // columns past the channel count are zero-filled by the hardware at no memory traffic. The box width follows
 // the reduction width: 64 channels -> SWIZZLE_128B tiles, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B.
+// An 8-channel input (the 6-channel colour+normal input of conv0p1s1, models/detection_net.py:37, padded to 8) is
+// one 16-byte piece per (row, offset): those are fetched with cp.async (LDGSTS) instead, 8 (forward) / 16
+// (wgrad) offsets side by side in one SW128 tile, because a TMA request per 16 bytes would be request-bound.
 //
 //  conv_fwd_kernel   persistent, warp-specialised, output-stationary implicit GEMM.
 //      work item  = T (1 or 2) tiles of 128 output rows x <=256 output columns, accumulators in TMEM,
@@ -41,11 +44,11 @@ namespace b2m {
 // weight packing
 // ------------------------------------------------------------------------------------------------
 // Reduction layout of B per offset group kg:
-//   c_red in {16, 32} ("flat"): 64 / c_red consecutive offsets share ONE 64-wide SW128 slice [c_n][64].
+//   c_red in {8, 16, 32} ("flat"): 64 / c_red consecutive offsets share ONE 64-wide SW128 slice [c_n][64].
 //   otherwise: c_red is cut into chunks of 64 (SW128 slices [c_n][64]); a remainder of exactly 32 becomes a
 //   SW64 slice [c_n][32]; remainders of 16 / 48 are zero-padded to a full chunk.
 // A slice row is 128 (64) bytes; its 16-byte groups are XOR-swizzled with n & 7 ((n >> 1) & 3).
-__host__ __device__ inline int conv_kpack(int c_red) { return (c_red == 16 || c_red == 32) ? 64 / c_red : 1; }
+__host__ __device__ inline int conv_kpack(int c_red) { return (c_red == 8 || c_red == 16 || c_red == 32) ? 64 / c_red : 1; }
 __host__ __device__ inline int conv_rem(int c_red) { return (conv_kpack(c_red) == 1 && (c_red % 64) == 32) ? 1 : 0; }
 __host__ __device__ inline int conv_nfull(int c_red) {
   if (conv_kpack(c_red) > 1) return 1;
@@ -92,9 +95,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int kvol, int c
   *reinterpret_cast<uint4*>(packed + gid * 8) = *reinterpret_cast<const uint4*>(v);
 }
 
+__device__ __forceinline__ void st_shared_zero16(uint32_t addr) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 struct MaskBits { uint32_t w0, w1, w2, w3; };
 __device__ __forceinline__ uint32_t mask_word(const MaskBits& m, int i) { return i == 0 ? m.w0 : (i == 1 ? m.w1 : (i == 2 ? m.w2 : m.w3)); }
-// the `cnt` (1, 2 or 4; divides 32) mask bits starting at offset k0
+// the `cnt` (1, 2, 4 or 8; divides 32, k0 % cnt == 0) mask bits starting at offset k0
 __device__ __forceinline__ uint32_t mask_bits(const MaskBits& m, int k0, int cnt) {
   return (mask_word(m, k0 >> 5) >> (k0 & 31)) & ((1u << cnt) - 1u);
 }
@@ -123,7 +131,7 @@ constexpr int kStagePitch = 33;
 constexpr int kASlotBytes = kTileM * 128;
 
 struct FwdArgs {
-  const int32_t* nbr; const int32_t* order; const uint32_t* gmask; const uint8_t* w;
+  const uint16_t* x; const int32_t* nbr; const int32_t* order; const uint32_t* gmask; const uint8_t* w;
   uint16_t* y; double* colsum;
   int64_t n_out, n_pitch;
   int c_red, kvol, c_n, ntile, T, kpack, nkg, nfull, rem, wa, mwords, colstride, n_tiles, n_work;
@@ -279,6 +287,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                   umma_bf16(d, umma_desc_sw(a_s + ks * 32, 16, 8 * wc, wc), umma_desc_sw(b_s + ks * 32, 16, 8 * wc, wc), idesc, acc);
                   acc = 1u;
                 }
+              } else if (a.kpack == 8) {
+                // 8 offsets x 8 channels side by side in one SW128 tile: a K=16 step covers a pair of offsets
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (!((sub >> (2 * ks)) & 3u)) continue;
+                  umma_bf16(d, umma_desc_sw(a_s + ks * 32, 16, 1024, 128), umma_desc_sw(b_s + ks * 32, 16, 1024, 128), idesc, acc);
+                  acc = 1u;
+                }
               } else {
                 const uint32_t wa = (uint32_t)a.wa;
                 for (int j = 0; j < a.kpack; ++j) {
@@ -364,6 +379,41 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                 if (lane == 0) mbar_arrive_expect_tx(full, kTileM * wc);
                 __syncwarp();
                 tma_gather4(a_s + lane * 4 * wc, (c < a.nfull) ? &tm_main : &tm_rem, full, c * 64, idx.x, idx.y, idx.z, idx.w);
+              } else if (a.kpack == 8) {
+                // cp.async path: lane = (offset j of the group, row quad rq); 8 x (one 16-byte index load + 4 copies)
+                const int j = lane & 7, rq = lane >> 3;
+                const int k = kg * 8 + j;
+                const bool on = ((sub >> j) & 1u) != 0;
+                const int32_t* nb = a.nbr ? a.nbr + (int64_t)k * a.n_pitch + (int64_t)(w * a.T + t) * kTileM : nullptr;
+                mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u);
+#pragma unroll 2
+                for (int it = 0; it < 8; ++it) {
+                  const int r0 = 16 * it + 4 * rq;
+                  int4 idx = make_int4(-1, -1, -1, -1);
+                  if (on) {
+                    if (nb) {
+                      idx = ld_nc_int4(nb + r0);
+                    } else {
+                      const int64_t q0 = (int64_t)(w * a.T + t) * kTileM + r0;
+                      idx.x = q0 < a.n_out ? (int)q0 : -1;
+                      idx.y = q0 + 1 < a.n_out ? (int)q0 + 1 : -1;
+                      idx.z = q0 + 2 < a.n_out ? (int)q0 + 2 : -1;
+                      idx.w = q0 + 3 < a.n_out ? (int)q0 + 3 : -1;
+                    }
+                  }
+                  const int iv[4] = {idx.x, idx.y, idx.z, idx.w};
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const int row = r0 + u;
+                    const uint32_t dst = a_s + row * 128 + ((j ^ (row & 7)) << 4);
+                    if (iv[u] >= 0) cp_async16(dst, a.x + (int64_t)iv[u] * 8, 16u);
+                    else st_shared_zero16(dst);
+                  }
+                }
+                cp_async_wait_all();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full);
               } else {
                 const uint32_t wa = (uint32_t)a.wa;
                 int4 idx[4];
@@ -415,7 +465,7 @@ constexpr int kWgRows = 64;
 constexpr int kWgASlotBytes = 128 * kWgRows * 2;                // 16 KB: M = 128 x 64 reduction rows
 
 struct WgArgs {
-  const int32_t* nbr; const int32_t* order; const uint32_t* gmask; float* dw;
+  const uint16_t* x; const int32_t* nbr; const int32_t* order; const uint32_t* gmask; float* dw;
   int64_t n_out, n_pitch;
   int c_in, c_out, kvol, mwords, cpad, pk, G, colstride, groups_per_cta;
   int wa, nab;    // X operand: row bytes of a block (128 / 64 / 32) and blocks per A stage (nab * wa / 2 == 128 M rows)
@@ -464,7 +514,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     if (a.gmask == nullptr) return 1u;
     const int k0 = kbase + q * a.pk;
     uint32_t bits = 0;
-    for (int j0 = 0; j0 < a.pk; j0 += 4) bits |= mask_bits(m, k0 + j0, min(4, a.pk)) << j0;  // pk in {1,2,4,8}; k0 % pk == 0
+    for (int j0 = 0; j0 < a.pk; j0 += 4) bits |= mask_bits(m, k0 + j0, min(4, a.pk)) << j0;  // pk in {1,2,4,8,16}; k0 % pk == 0
     return bits;
   };
   auto group_mask = [&](int64_t g) -> MaskBits {
@@ -596,7 +646,40 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (!group_any(m)) continue;
       for (int q = 0; q < nq; ++q) {
         if (!acc_bits(m, q)) continue;
-        if (turn == p) {
+        if (turn == p && a.cpad == 8) {
+          // cp.async path (8-channel input): lane = (offset slot j of 16, row half rh); one 16-byte piece per (row, offset)
+          const uint32_t a_s = smem_base + ra.slot * kWgASlotBytes;
+          const int j = lane & 15, rh = lane >> 4;
+          const int k = kbase + q * a.pk + j;
+          const int32_t* nb = (a.nbr && k < a.kvol) ? a.nbr + (int64_t)k * a.n_pitch + g * kWgRows : nullptr;
+          mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u);
+#pragma unroll 2
+          for (int it = 0; it < 8; ++it) {
+            const int r0 = 8 * it + 4 * rh;
+            int4 idx = make_int4(-1, -1, -1, -1);
+            if (nb) {
+              idx = ld_nc_int4(nb + r0);
+            } else if (!a.nbr && k < a.kvol) {
+              const int64_t q0 = g * kWgRows + r0;
+              idx.x = q0 < a.n_out ? (int)q0 : -1;
+              idx.y = q0 + 1 < a.n_out ? (int)q0 + 1 : -1;
+              idx.z = q0 + 2 < a.n_out ? (int)q0 + 2 : -1;
+              idx.w = q0 + 3 < a.n_out ? (int)q0 + 3 : -1;
+            }
+            const int iv[4] = {idx.x, idx.y, idx.z, idx.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int row = r0 + u;
+              const uint32_t dst = a_s + (j >> 3) * (kWgRows * 128) + row * 128 + (((j & 7) ^ (row & 7)) << 4);
+              if (iv[u] >= 0) cp_async16(dst, a.x + (int64_t)iv[u] * 8, 16u);
+              else st_shared_zero16(dst);
+            }
+          }
+          cp_async_wait_all();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full + 8 * ra.slot);
+        } else if (turn == p) {
           const uint32_t a_s = smem_base + ra.slot * kWgASlotBytes;
           const uint32_t full = a_full + 8 * ra.slot;
           const int k0 = kbase + q * a.pk;
@@ -674,7 +757,8 @@ static bool make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int co
   cuuint32_t box[2] = {(cuuint32_t)box_cols, 1};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                              : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+                              : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                : (box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
   return g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -711,7 +795,7 @@ extern "C" int b2m_pack_weights(const float* kernel, int32_t kvol, int32_t c_in,
   if (!kernel || !packed || kvol <= 0 || c_in <= 0 || c_out <= 0 || mode < 0 || mode > 2) return B2M_ERR_INVALID_ARGUMENT;
   const int c_red = (mode == 0) ? c_in : c_out;
   const int c_n = (mode == 0) ? c_out : c_in;
-  if (c_n % 8 != 0 || c_red % 16 != 0) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (c_n % 8 != 0 || (c_red % 16 != 0 && c_red != 8)) return B2M_ERR_UNSUPPORTED_SHAPE;
   const int64_t total = (int64_t)(b2m_packed_weight_bytes(kvol, c_in, c_out, mode) / 16);
   pack_weights_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(kernel, kvol, c_in, c_out, mode, packed);
   B2M_CHECK_LAUNCH();
@@ -724,7 +808,7 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   if (!x || !packed_w || !y || kvol <= 0 || n_out < 0 || n_in < 0) return B2M_ERR_INVALID_ARGUMENT;
   if (!nbr && kvol != 1) return B2M_ERR_INVALID_ARGUMENT;
   if (nbr && !group_mask) return B2M_ERR_INVALID_ARGUMENT;
-  if (c_red <= 0 || c_red % 16 != 0 || c_n <= 0 || c_n % 16 != 0 || c_n > 512 || kvol > 128) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (c_red <= 0 || (c_red % 16 != 0 && c_red != 8) || c_n <= 0 || c_n % 16 != 0 || c_n > 512 || kvol > 128) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n_out == 0) return B2M_OK;
   if (n_out >= ((int64_t)1 << 31) - 256 || n_in >= ((int64_t)1 << 31) - 256) return B2M_ERR_UNSUPPORTED_SHAPE;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return B2M_ERR_INVALID_ARGUMENT;
@@ -734,7 +818,7 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
     if (ntiles_n > 8) return B2M_ERR_UNSUPPORTED_SHAPE;
   }
   FwdArgs a;
-  a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr;
+  a.x = x; a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr;
   a.w = reinterpret_cast<const uint8_t*>(packed_w); a.y = y;
   a.colsum = colsum; a.n_out = n_out; a.n_pitch = b2m_map_pitch(n_out); a.c_red = c_red; a.kvol = kvol; a.c_n = c_n;
   a.ntile = c_n / ntiles_n;
@@ -742,7 +826,7 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   a.nkg = (kvol + a.kpack - 1) / a.kpack;
   a.nfull = conv_nfull(c_red);
   a.rem = conv_rem(c_red);
-  a.wa = (a.kpack > 1) ? c_red * 2 : 128;
+  a.wa = (a.kpack > 1 && a.kpack < 8) ? c_red * 2 : 128;
   a.kg_bytes = c_n * (a.nfull * 128 + a.rem * 64);
   a.mwords = (kvol + 31) / 32;
   a.colstride = (a.ntile + 31) / 32 * 32;
@@ -795,11 +879,11 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
   if (n_out >= ((int64_t)1 << 31) - 256 || n_in >= ((int64_t)1 << 31) - 256) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) != 0) return B2M_ERR_INVALID_ARGUMENT;
   WgArgs a;
-  a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr; a.dw = dw;
+  a.x = x; a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr; a.dw = dw;
   a.n_out = n_out; a.n_pitch = b2m_map_pitch(n_out); a.c_in = c_in; a.c_out = c_out; a.kvol = kvol; a.mwords = (kvol + 31) / 32;
-  a.cpad = c_in <= 16 ? 16 : (c_in <= 32 ? 32 : (c_in <= 64 ? 64 : 128));
+  a.cpad = c_in <= 8 ? 8 : (c_in <= 16 ? 16 : (c_in <= 32 ? 32 : (c_in <= 64 ? 64 : 128)));
   a.pk = 128 / a.cpad;
-  a.wa = a.cpad >= 64 ? 128 : a.cpad * 2;
+  a.wa = (a.cpad >= 64 || a.cpad == 8) ? 128 : a.cpad * 2;
   a.nab = 128 * 2 / a.wa;
   a.wb = (c_out == 16 || c_out == 32) ? c_out * 2 : 128;
   a.nbb = (c_out * 2 + a.wb - 1) / a.wb;
@@ -830,7 +914,7 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
   const int smem_bytes = a.off_bars + 16 * a.a_slots + 16 * a.b_slots + 64 + 1024;
   if (smem_bytes > 227 * 1024) return B2M_ERR_UNSUPPORTED_SHAPE;
   CUtensorMap tm_x, tm_dy;
-  if (!make_row_map(&tm_x, x, n_in, c_in, a.wa / 2)) return B2M_ERR_CUDA_LAUNCH;
+  if (!make_row_map(&tm_x, x, n_in, c_in, a.cpad == 8 ? 8 : a.wa / 2)) return B2M_ERR_CUDA_LAUNCH;   // unused when cpad == 8
   if (!make_row_map(&tm_dy, dy, n_out, c_out, a.wb / 2)) return B2M_ERR_CUDA_LAUNCH;
   static bool attr_set = false;
   if (!attr_set) {

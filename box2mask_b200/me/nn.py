@@ -24,7 +24,8 @@ def _as_int(v):
 
 
 def _round16(c):
-    return (c + 15) // 16 * 16
+    """bf16 feature width the kernels accept: 8 (the cp.async path of the 6-channel input) or a multiple of 16."""
+    return 8 if c <= 8 else (c + 15) // 16 * 16
 
 
 class _ConvBase(nn.Module):
@@ -103,8 +104,8 @@ class _ConvBase(nn.Module):
             feats = ops.cast_pad_bf16(feats.contiguous(), _round16(self.in_channels))
         elif feats.dtype != torch.bfloat16:
             raise TypeError("features must be float32 or bfloat16")
-        if feats.shape[1] % 16 != 0:
-            raise NotImplementedError("bf16 feature width must be a multiple of 16")
+        if feats.shape[1] % 16 != 0 and feats.shape[1] != 8:
+            raise NotImplementedError("bf16 feature width must be 8 or a multiple of 16")
         y, colsum = Fn.SparseConvFn.apply(feats.contiguous(), self.kernel, nbr_fwd, nbr_bwd, mode, n_out, self.in_channels)
         out = x._like(y, out_stride)
         if self.bias is not None:

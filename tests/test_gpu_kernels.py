@@ -156,7 +156,7 @@ def _conv_case(kvol, c_in, c_out, n, seed, real_map=None):
     (27, 32, 32, 4000), (27, 64, 64, 3000), (27, 128, 96, 6000), (27, 96, 96, 515), (8, 256, 256, 2000),
     (27, 512, 256, 700), (27, 256, 512, 700), (27, 384, 256, 500), (125, 16, 32, 3000), (1, 32, 64, 300),
     (1, 256, 256, 129), (27, 192, 128, 1), (8, 96, 96, 127), (8, 48, 32, 500), (27, 80, 64, 300), (27, 160, 16, 260),
-    (1, 96, 128, 40000), (27, 32, 96, 33000),
+    (1, 96, 128, 40000), (27, 32, 96, 33000), (125, 8, 32, 3000), (27, 8, 16, 200), (1, 8, 32, 90000),
 ])
 def test_conv_forward(kvol, c_in, c_out, n):
     nbr_np, x, w, n = _conv_case(kvol, c_in, c_out, n, seed=kvol + c_in)
@@ -208,7 +208,7 @@ def test_conv_forward_real_maps_and_dgrad(scene_coords):
 @pytest.mark.parametrize("kvol,c_in,c_out,n", [
     (27, 64, 64, 3000), (27, 128, 96, 6000), (27, 96, 96, 515), (27, 32, 32, 4000), (8, 256, 256, 2000),
     (27, 512, 256, 700), (125, 16, 32, 3000), (1, 64, 64, 1000), (8, 96, 128, 70000), (27, 192, 128, 63),
-    (27, 48, 16, 400), (8, 32, 96, 5000), (27, 16, 16, 900), (1, 128, 96, 20000),
+    (27, 48, 16, 400), (8, 32, 96, 5000), (27, 16, 16, 900), (1, 128, 96, 20000), (125, 8, 32, 3000), (27, 8, 96, 777),
 ])
 def test_conv_wgrad(kvol, c_in, c_out, n):
     nbr_np, x, _, n = _conv_case(kvol, c_in, c_out, n, seed=kvol + c_out)
