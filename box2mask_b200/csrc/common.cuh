@@ -142,9 +142,17 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t alo, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
       ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
 }
-// high word of a SWIZZLE_128B descriptor: SBO (16-byte units) | version 1 (bit 46) | layout 2 (bits 61-63)
-__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes) {
-  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+// high word of a swizzled descriptor: SBO (16-byte units) | version 1 (bit 46) | layout type (bits 61-63) chosen by
+// the row bytes of the tile: 128 -> SWIZZLE_128B (2), 64 -> SWIZZLE_64B (4), 32 -> SWIZZLE_32B (6)
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t row_bytes) {
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+// one lane of the (converged) warp; the same lane every time for a full warp, so MMAs and their commits pair up
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 // low word: start address | LBO, both in 16-byte units
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {

@@ -160,6 +160,9 @@ struct Ring {
   __device__ __forceinline__ void next() { if (++slot == n) { slot = 0; phase ^= 1u; } }
 };
 
+// KPACK = offsets per A stage: 1 (c_red >= 48: 64-wide chunks), 2 / 4 (c_red 32 / 16: SW64 / SW32 sub-tiles),
+// 8 (c_red 8: cp.async path). A template parameter so that the single-thread MMA issue loop has no mode branches.
+template <int KPACK>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_rem, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -254,89 +257,100 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kTileM, a.ntile, 0, 0);
-      Ring ra, rb;
-      ra.init(SA); rb.init(SB);
-      int wi = 0;
-      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
-        const int par = wi & 1;
-        mbar_wait(acc_empty + 8 * par, ((uint32_t)(wi >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const MaskBits m0 = fwd_tile_mask(a, w * a.T);
-        const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
-        uint32_t started = 0;
-        for (int kg = 0; kg < a.nkg; ++kg) {
-          const uint32_t s0 = mask_bits(m0, kg * a.kpack, a.kpack), s1 = mask_bits(m1, kg * a.kpack, a.kpack);
-          if (!(s0 | s1)) continue;
-          for (int c = 0; c < nch; ++c) {
-            mbar_wait(b_full + 8 * rb.slot, rb.phase);
-            const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
-            for (int t = 0; t < a.T; ++t) {
-              const uint32_t sub = t ? s1 : s0;
-              if (!sub) continue;
-              mbar_wait(a_full + 8 * ra.slot, ra.phase);
-              tc_fence_after();
-              const uint32_t a_s = smem_base + ra.slot * kASlotBytes;
-              const uint32_t d = tmem_base + (uint32_t)((par * a.T + t) * a.colstride);
-              uint32_t acc = (started >> t) & 1u;
-              if (a.kpack == 1) {
-                const uint32_t wc = (c < a.nfull) ? 128u : 64u;
-                const int kc = (c < a.nfull) ? min(64, a.c_red - c * 64) : 32;
-                for (int ks = 0; ks < kc / 16; ++ks) {
-                  umma_bf16(d, umma_desc_sw(a_s + ks * 32, 16, 8 * wc, wc), umma_desc_sw(b_s + ks * 32, 16, 8 * wc, wc), idesc, acc);
+    // The whole warp runs the loop (every value below is warp-uniform, so it lives in uniform registers and the
+    // UTCHMMA operands need no per-instruction R2UR); one elected lane issues the MMAs and the commits.
+    const bool lead = elect_one_sync();
+    const uint32_t idesc = umma_idesc_bf16(kTileM, a.ntile, 0, 0);
+    const uint32_t hi128 = umma_desc_hi(1024, 128), hi64 = umma_desc_hi(512, 64), hi32 = umma_desc_hi(256, 32);
+    const uint32_t hia = (KPACK == 2) ? hi64 : (KPACK == 4 ? hi32 : hi128);
+    Ring ra, rb;
+    ra.init(SA); rb.init(SB);
+    int wi = 0;
+    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
+      const int par = wi & 1;
+      mbar_wait(acc_empty + 8 * par, ((uint32_t)(wi >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const MaskBits m0 = fwd_tile_mask(a, w * a.T);
+      const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
+      uint32_t started = 0;
+      for (int kg = 0; kg < a.nkg; ++kg) {
+        const uint32_t s0 = mask_bits(m0, kg * KPACK, KPACK), s1 = mask_bits(m1, kg * KPACK, KPACK);
+        if (!(s0 | s1)) continue;
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(b_full + 8 * rb.slot, rb.phase);
+          const uint32_t b_lo = umma_desc_lo(smem_base + a.off_b + rb.slot * a.b_bytes, 16);
+          for (int t = 0; t < a.T; ++t) {
+            const uint32_t sub = t ? s1 : s0;
+            if (!sub) continue;
+            mbar_wait(a_full + 8 * ra.slot, ra.phase);
+            tc_fence_after();
+            const uint32_t a_lo = umma_desc_lo(smem_base + ra.slot * kASlotBytes, 16);
+            const uint32_t d = tmem_base + (uint32_t)((par * a.T + t) * a.colstride);
+            uint32_t acc = (started >> t) & 1u;
+            if (lead) {
+              if (KPACK == 1) {
+                const bool full_chunk = c < a.nfull;
+                const uint32_t hi = full_chunk ? hi128 : hi64;
+                const int nks = full_chunk ? min(4, (a.c_red - c * 64) >> 4) : 2;
+                for (int ks = 0; ks < nks; ++ks) {     // +32 bytes (2 descriptor units) per K=16 step
+                  umma_bf16_lohi(d, a_lo + 2 * ks, hi, b_lo + 2 * ks, hi, idesc, acc);
                   acc = 1u;
                 }
-              } else if (a.kpack == 8) {
+              } else if (KPACK == 8) {
                 // 8 offsets x 8 channels side by side in one SW128 tile: a K=16 step covers a pair of offsets
+#pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                  if (!((sub >> (2 * ks)) & 3u)) continue;
-                  umma_bf16(d, umma_desc_sw(a_s + ks * 32, 16, 1024, 128), umma_desc_sw(b_s + ks * 32, 16, 1024, 128), idesc, acc);
-                  acc = 1u;
-                }
-              } else {
-                const uint32_t wa = (uint32_t)a.wa;
-                for (int j = 0; j < a.kpack; ++j) {
-                  if (!((sub >> j) & 1u)) continue;
-                  for (uint32_t ks = 0; ks < wa / 32; ++ks) {
-                    umma_bf16(d, umma_desc_sw(a_s + j * kTileM * wa + ks * 32, 16, 8 * wa, wa),
-                              umma_desc_sw(b_s + j * wa + ks * 32, 16, 1024, 128), idesc, acc);
+                  if ((sub >> (2 * ks)) & 3u) {
+                    umma_bf16_lohi(d, a_lo + 2 * ks, hi128, b_lo + 2 * ks, hi128, idesc, acc);
                     acc = 1u;
                   }
                 }
+              } else {
+                constexpr uint32_t wa = 128 / KPACK;               // sub-tile row bytes: 64 (SW64) or 32 (SW32)
+#pragma unroll
+                for (int j = 0; j < KPACK; ++j) {
+                  if ((sub >> j) & 1u) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < wa / 32; ++ks) {
+                      umma_bf16_lohi(d, a_lo + ((j * kTileM * wa) >> 4) + 2 * ks, hia, b_lo + ((j * wa) >> 4) + 2 * ks, hi128, idesc, acc);
+                      acc = 1u;
+                    }
+                  }
+                }
               }
-              started |= 1u << t;
               umma_commit(a_empty + 8 * ra.slot);
-              ra.next();
             }
-            umma_commit(b_empty + 8 * rb.slot);
-            rb.next();
+            started |= 1u << t;
+            ra.next();
           }
+          if (lead) umma_commit(b_empty + 8 * rb.slot);
+          rb.next();
         }
-        umma_commit(acc_full + 8 * par);
       }
+      if (lead) umma_commit(acc_full + 8 * par);
     }
     __syncwarp();
   } else if (warp == 5) {
-    // ================= B loader: bulk copies of pre-swizzled weight slices =================
-    if (lane == 0) {
-      Ring rb;
-      rb.init(SB);
-      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
-        const MaskBits m0 = fwd_tile_mask(a, w * a.T);
-        const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
-        for (int kg = 0; kg < a.nkg; ++kg) {
-          if (!(mask_bits(m0, kg * a.kpack, a.kpack) | mask_bits(m1, kg * a.kpack, a.kpack))) continue;
-          for (int c = 0; c < nch; ++c) {
-            mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u);
+    // ================= B loader: bulk copies of pre-swizzled weight slices (warp-uniform, elected lane issues) ====
+    const bool lead = elect_one_sync();
+    Ring rb;
+    rb.init(SB);
+    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+      const MaskBits m0 = fwd_tile_mask(a, w * a.T);
+      const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
+      for (int kg = 0; kg < a.nkg; ++kg) {
+        if (!(mask_bits(m0, kg * KPACK, KPACK) | mask_bits(m1, kg * KPACK, KPACK))) continue;
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u);
+          if (lead) {
             const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
             const int wb = (c < a.nfull) ? 128 : 64;
             const uint32_t bytes = (uint32_t)(a.ntile * wb);
             const uint8_t* src = a.w + (int64_t)kg * a.kg_bytes + (int64_t)min(c, a.nfull) * a.c_n * 128 + (int64_t)n0 * wb;
             mbar_arrive_expect_tx(b_full + 8 * rb.slot, bytes);
             bulk_g2s(b_s, src, bytes, b_full + 8 * rb.slot);
-            rb.next();
           }
+          rb.next();
         }
       }
     }
@@ -354,7 +368,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       const MaskBits m0 = fwd_tile_mask(a, w * a.T);
       const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
       for (int kg = 0; kg < a.nkg; ++kg) {
-        const uint32_t s0 = mask_bits(m0, kg * a.kpack, a.kpack), s1 = mask_bits(m1, kg * a.kpack, a.kpack);
+        const uint32_t s0 = mask_bits(m0, kg * KPACK, KPACK), s1 = mask_bits(m1, kg * KPACK, KPACK);
         if (!(s0 | s1)) continue;
         for (int c = 0; c < nch; ++c) {
           for (int t = 0; t < a.T; ++t) {
@@ -364,7 +378,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
               const int64_t pos0 = (int64_t)(w * a.T + t) * kTileM + 4 * lane;  // this lane gathers rows pos0 .. pos0+3
               const uint32_t a_s = smem_base + ra.slot * kASlotBytes;
               const uint32_t full = a_full + 8 * ra.slot;
-              if (a.kpack == 1) {
+              if (KPACK == 1) {
                 int4 idx;
                 if (a.nbr) {
                   idx = ld_nc_int4(a.nbr + (int64_t)kg * a.n_pitch + pos0);
@@ -379,7 +393,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                 if (lane == 0) mbar_arrive_expect_tx(full, kTileM * wc);
                 __syncwarp();
                 tma_gather4(a_s + lane * 4 * wc, (c < a.nfull) ? &tm_main : &tm_rem, full, c * 64, idx.x, idx.y, idx.z, idx.w);
-              } else if (a.kpack == 8) {
+              } else if (KPACK == 8) {
                 // cp.async path: lane = (offset j of the group, row quad rq); 8 x (one 16-byte index load + 4 copies)
                 const int j = lane & 7, rq = lane >> 3;
                 const int k = kg * 8 + j;
@@ -415,13 +429,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full);
               } else {
-                const uint32_t wa = (uint32_t)a.wa;
+                constexpr uint32_t wa = 128 / KPACK;
                 int4 idx[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  if (j < a.kpack && ((sub >> j) & 1u)) {
+                  if (j < KPACK && ((sub >> j) & 1u)) {
                     if (a.nbr) {
-                      idx[j] = ld_nc_int4(a.nbr + (int64_t)(kg * a.kpack + j) * a.n_pitch + pos0);
+                      idx[j] = ld_nc_int4(a.nbr + (int64_t)(kg * KPACK + j) * a.n_pitch + pos0);
                     } else {  // identity map (kvol == 1): only j == 0 is ever set
                       idx[j].x = pos0 < a.n_out ? (int)pos0 : -1;
                       idx[j].y = pos0 + 1 < a.n_out ? (int)pos0 + 1 : -1;
@@ -434,7 +448,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  if (j < a.kpack && ((sub >> j) & 1u))
+                  if (j < KPACK && ((sub >> j) & 1u))
                     tma_gather4(a_s + j * kTileM * wa + lane * 4 * wa, &tm_main, full, 0, idx[j].x, idx[j].y, idx[j].z, idx[j].w);
               }
             }
@@ -560,40 +574,45 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
     }
   } else if (warp == kWgEpi) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, a.c_out, 1, 1);
-      const uint32_t wa = (uint32_t)a.wa, wb = (uint32_t)a.wb;
-      uint32_t used = 0;
-      Ring ra, rb;
-      ra.init(SA); rb.init(SB);
-      for (int64_t g = g_begin; g < g_end; ++g) {
-        const MaskBits m = group_mask(g);
-        if (!group_any(m)) continue;
-        mbar_wait(b_full + 8 * rb.slot, rb.phase);
-        const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
+    // ================= MMA issuer (warp-uniform loop, one elected lane issues; see conv_fwd_kernel) =================
+    const bool lead = elect_one_sync();
+    const uint32_t idesc = umma_idesc_bf16(128, a.c_out, 1, 1);
+    const uint32_t wa = (uint32_t)a.wa, wb = (uint32_t)a.wb;
+    // MN-major: LBO = stride between blocks (64 rows x row bytes each), SBO = stride between 8-row K groups
+    const uint32_t hi_a = umma_desc_hi(8 * wa, wa), hi_b = umma_desc_hi(8 * wb, wb);
+    const uint32_t lbo_a = ((kWgRows * wa) >> 4) << 16, lbo_b = ((kWgRows * wb) >> 4) << 16;
+    const uint32_t kstep_a = (16 * wa) >> 4, kstep_b = (16 * wb) >> 4;     // descriptor units per K=16 step
+    uint32_t used = 0;
+    Ring ra, rb;
+    ra.init(SA); rb.init(SB);
+    for (int64_t g = g_begin; g < g_end; ++g) {
+      const MaskBits m = group_mask(g);
+      if (!group_any(m)) continue;
+      mbar_wait(b_full + 8 * rb.slot, rb.phase);
+      const uint32_t b_lo = (((smem_base + a.off_b + rb.slot * a.b_bytes) >> 4) & 0x3FFFu) | lbo_b;
 #pragma unroll 1
-        for (int q = 0; q < nq; ++q) {
-          if (!acc_bits(m, q)) continue;
-          mbar_wait(a_full + 8 * ra.slot, ra.phase);
-          tc_fence_after();
-          const uint32_t a_s = smem_base + ra.slot * kWgASlotBytes;
+      for (int q = 0; q < nq; ++q) {
+        if (!acc_bits(m, q)) continue;
+        mbar_wait(a_full + 8 * ra.slot, ra.phase);
+        tc_fence_after();
+        if (lead) {
+          const uint32_t a_lo = (((smem_base + ra.slot * kWgASlotBytes) >> 4) & 0x3FFFu) | lbo_a;
           const uint32_t d = tmem_base + (uint32_t)(q * a.colstride);
           uint32_t acc = (used >> q) & 1u;
 #pragma unroll
           for (int ks = 0; ks < kWgRows / 16; ++ks) {
-            // MN-major: LBO = stride between blocks (64-row x row_bytes each), SBO = stride between 8-row K groups
-            umma_bf16(d, umma_desc_sw(a_s + ks * 16 * wa, kWgRows * wa, 8 * wa, wa),
-                      umma_desc_sw(b_s + ks * 16 * wb, kWgRows * wb, 8 * wb, wb), idesc, acc);
+            umma_bf16_lohi(d, a_lo + ks * kstep_a, hi_a, b_lo + ks * kstep_b, hi_b, idesc, acc);
             acc = 1u;
           }
-          used |= 1u << q;
           umma_commit(a_empty + 8 * ra.slot);
-          ra.next();
         }
-        umma_commit(b_empty + 8 * rb.slot);
-        rb.next();
+        used |= 1u << q;
+        ra.next();
       }
+      if (lead) umma_commit(b_empty + 8 * rb.slot);
+      rb.next();
+    }
+    if (lead) {
       *reinterpret_cast<volatile uint32_t*>(used_s) = used;
       __threadfence_block();
       umma_commit(accum_bar);
@@ -855,7 +874,10 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   else tm_rem = tm_main;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return B2M_ERR_CUDA_LAUNCH;
     attr_set = true;
   }
@@ -863,7 +885,13 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   if (ntiles_n > 1) gx = (gx + ntiles_n - 1) / ntiles_n;   // keep the total CTA count near one per SM
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)ntiles_n);
-  conv_fwd_kernel<<<grid, kFwdThreads, smem_bytes, (cudaStream_t)stream>>>(tm_main, tm_rem, a);
+  const cudaStream_t st = (cudaStream_t)stream;
+  switch (a.kpack) {
+    case 1: conv_fwd_kernel<1><<<grid, kFwdThreads, smem_bytes, st>>>(tm_main, tm_rem, a); break;
+    case 2: conv_fwd_kernel<2><<<grid, kFwdThreads, smem_bytes, st>>>(tm_main, tm_rem, a); break;
+    case 4: conv_fwd_kernel<4><<<grid, kFwdThreads, smem_bytes, st>>>(tm_main, tm_rem, a); break;
+    default: conv_fwd_kernel<8><<<grid, kFwdThreads, smem_bytes, st>>>(tm_main, tm_rem, a); break;
+  }
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }
