@@ -154,6 +154,26 @@ __device__ __forceinline__ MaskBits fwd_tile_mask(const FwdArgs& a, int tile) {
   return m;
 }
 
+// next offset group >= from that has a pair in the union mask u of the work item's tiles (nkg if none)
+template <int KPACK>
+__device__ __forceinline__ int next_group(const MaskBits& u, int from, int nkg, int mwords) {
+  if (KPACK == 1) {
+    for (int wd = from >> 5; wd < mwords; ++wd) {
+      uint32_t bits = mask_word(u, wd);
+      if (wd == (from >> 5)) bits &= 0xFFFFFFFFu << (from & 31);
+      if (bits) return (wd << 5) + __ffs(bits) - 1;
+    }
+    return nkg;
+  } else {
+    for (int kg = from; kg < nkg; ++kg)
+      if (mask_bits(u, kg * KPACK, KPACK)) return kg;
+    return nkg;
+  }
+}
+__device__ __forceinline__ MaskBits mask_or(const MaskBits& a, const MaskBits& b) {
+  MaskBits m; m.w0 = a.w0 | b.w0; m.w1 = a.w1 | b.w1; m.w2 = a.w2 | b.w2; m.w3 = a.w3 | b.w3; return m;
+}
+
 struct Ring {
   int slot; uint32_t phase; int n;
   __device__ __forceinline__ void init(int n_) { slot = 0; phase = 0; n = n_; }
@@ -272,10 +292,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       tc_fence_after();
       const MaskBits m0 = fwd_tile_mask(a, w * a.T);
       const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
+      const MaskBits mu = mask_or(m0, m1);
       uint32_t started = 0;
-      for (int kg = 0; kg < a.nkg; ++kg) {
+      for (int kg = next_group<KPACK>(mu, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mu, kg + 1, a.nkg, a.mwords)) {
         const uint32_t s0 = mask_bits(m0, kg * KPACK, KPACK), s1 = mask_bits(m1, kg * KPACK, KPACK);
-        if (!(s0 | s1)) continue;
         for (int c = 0; c < nch; ++c) {
           mbar_wait(b_full + 8 * rb.slot, rb.phase);
           const uint32_t b_lo = umma_desc_lo(smem_base + a.off_b + rb.slot * a.b_bytes, 16);
@@ -292,9 +312,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                 const bool full_chunk = c < a.nfull;
                 const uint32_t hi = full_chunk ? hi128 : hi64;
                 const int nks = full_chunk ? min(4, (a.c_red - c * 64) >> 4) : 2;
-                for (int ks = 0; ks < nks; ++ks) {     // +32 bytes (2 descriptor units) per K=16 step
-                  umma_bf16_lohi(d, a_lo + 2 * ks, hi, b_lo + 2 * ks, hi, idesc, acc);
-                  acc = 1u;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {       // +32 bytes (2 descriptor units) per K=16 step
+                  if (ks < nks) {
+                    umma_bf16_lohi(d, a_lo + 2 * ks, hi, b_lo + 2 * ks, hi, idesc, acc);
+                    acc = 1u;
+                  }
                 }
               } else if (KPACK == 8) {
                 // 8 offsets x 8 channels side by side in one SW128 tile: a K=16 step covers a pair of offsets
@@ -338,8 +361,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
       const MaskBits m0 = fwd_tile_mask(a, w * a.T);
       const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
-      for (int kg = 0; kg < a.nkg; ++kg) {
-        if (!(mask_bits(m0, kg * KPACK, KPACK) | mask_bits(m1, kg * KPACK, KPACK))) continue;
+      const MaskBits mu = mask_or(m0, m1);
+      for (int kg = next_group<KPACK>(mu, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mu, kg + 1, a.nkg, a.mwords)) {
         for (int c = 0; c < nch; ++c) {
           mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u);
           if (lead) {
@@ -367,9 +390,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
       const MaskBits m0 = fwd_tile_mask(a, w * a.T);
       const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
-      for (int kg = 0; kg < a.nkg; ++kg) {
+      const MaskBits mu = mask_or(m0, m1);
+      for (int kg = next_group<KPACK>(mu, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mu, kg + 1, a.nkg, a.mwords)) {
         const uint32_t s0 = mask_bits(m0, kg * KPACK, KPACK), s1 = mask_bits(m1, kg * KPACK, KPACK);
-        if (!(s0 | s1)) continue;
         for (int c = 0; c < nch; ++c) {
           for (int t = 0; t < a.T; ++t) {
             const uint32_t sub = t ? s1 : s0;
@@ -473,8 +496,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgEpi = 4;                                       // warps 0-3: epilogue (TMEM lane quarters)
 constexpr int kWgAProd = 10;                                    // gather warps for the X operand
-constexpr int kWgBProd = 2;                                     // gather warps for the dY operand
-constexpr int kWgThreads = (kWgEpi + 1 + kWgBProd + kWgAProd) * 32;   // 544
+constexpr int kWgBProd = 4;                                     // gather warps for the dY operand
+constexpr int kWgThreads = (kWgEpi + 1 + kWgBProd + kWgAProd) * 32;   // 608
 constexpr int kWgRows = 64;
 constexpr int kWgASlotBytes = 128 * kWgRows * 2;                // 16 KB: M = 128 x 64 reduction rows
 
@@ -523,22 +546,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  // offsets of accumulator q that occur in a row group with mask m (bit j = offset kbase + q*pk + j)
-  auto acc_bits = [&](const MaskBits& m, int q) -> uint32_t {
-    if (a.gmask == nullptr) return 1u;
-    const int k0 = kbase + q * a.pk;
-    uint32_t bits = 0;
-    for (int j0 = 0; j0 < a.pk; j0 += 4) bits |= mask_bits(m, k0 + j0, min(4, a.pk)) << j0;  // pk in {1,2,4,8,16}; k0 % pk == 0
-    return bits;
-  };
   auto group_mask = [&](int64_t g) -> MaskBits {
     if (a.gmask == nullptr) { MaskBits m = mask_zero(); m.w0 = 1u; return m; }
     return mask_load(a.gmask, g, a.mwords);
   };
-  auto group_any = [&](const MaskBits& m) -> bool {
-    bool any = false;
-    for (int q = 0; q < nq; ++q) any = any || (acc_bits(m, q) != 0);
-    return any;
+  // bit q set iff accumulator q (offsets kbase + q*pk .. + pk - 1) has a pair in a row group with mask m
+  auto acc_mask = [&](const MaskBits& m) -> uint32_t {
+    if (a.gmask == nullptr) return 1u;
+    if (a.pk == 1) {                       // the nq <= 16 bits starting at kbase, possibly straddling two words
+      const int wd = kbase >> 5;
+      const uint32_t lo = mask_word(m, wd), hi = (wd < 3) ? mask_word(m, wd + 1) : 0u;
+      return __funnelshift_r(lo, hi, kbase & 31) & ((1u << nq) - 1u);
+    }
+    uint32_t out = 0;
+    for (int q = 0; q < nq; ++q) {         // pk in {2,4,8,16} divides 32 and kbase % pk == 0: one word per accumulator
+      const int k0 = kbase + q * a.pk;
+      const uint32_t bits = (mask_word(m, k0 >> 5) >> (k0 & 31)) & ((a.pk == 32 ? 0u : (1u << a.pk)) - 1u);
+      out |= (bits != 0 ? 1u : 0u) << q;
+    }
+    return out;
   };
 
   if (warp < kWgEpi) {
@@ -585,14 +611,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     uint32_t used = 0;
     Ring ra, rb;
     ra.init(SA); rb.init(SB);
+    MaskBits m_next = group_mask(g_begin < g_end ? g_begin : 0);
     for (int64_t g = g_begin; g < g_end; ++g) {
-      const MaskBits m = group_mask(g);
-      if (!group_any(m)) continue;
+      const MaskBits m = m_next;
+      if (g + 1 < g_end) m_next = group_mask(g + 1);   // prefetched: the load latency overlaps this group's work
+      const uint32_t qm = acc_mask(m);
+      if (!qm) continue;
       mbar_wait(b_full + 8 * rb.slot, rb.phase);
       const uint32_t b_lo = (((smem_base + a.off_b + rb.slot * a.b_bytes) >> 4) & 0x3FFFu) | lbo_b;
 #pragma unroll 1
-      for (int q = 0; q < nq; ++q) {
-        if (!acc_bits(m, q)) continue;
+      for (uint32_t rem = qm; rem; rem &= rem - 1) {
+        const int q = __ffs(rem) - 1;
         mbar_wait(a_full + 8 * ra.slot, ra.phase);
         tc_fence_after();
         if (lead) {
@@ -621,15 +650,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   } else if (warp <= kWgEpi + kWgBProd) {
     // ================= dY producers (B operand, MN-major): gather rows order[g*64 ..]; stage s by warp s % kWgBProd ====
     const int pb = warp - (kWgEpi + 1);
+    const int npb = min(kWgBProd, SB);   // <= SB, see conv_fwd_kernel
     Ring rb;
     rb.init(SB);
     int turn = 0;
     const int items = a.nbb * 16;   // (column block, 4-row quad)
+    MaskBits m_next = group_mask(g_begin < g_end ? g_begin : 0);
     for (int64_t g = g_begin; g < g_end; ++g) {
-      const MaskBits m = group_mask(g);
-      if (!group_any(m)) continue;
+      const MaskBits m = m_next;
+      if (g + 1 < g_end) m_next = group_mask(g + 1);   // prefetched: the load latency overlaps this group's work
+      if (!acc_mask(m)) continue;
       const bool mine = (turn == pb);
-      turn = (turn + 1 == kWgBProd) ? 0 : turn + 1;
+      turn = (turn + 1 == npb) ? 0 : turn + 1;
       if (!mine) { rb.next(); continue; }
       const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
       const uint32_t full = b_full + 8 * rb.slot;
@@ -660,11 +692,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     ra.init(SA);
     int turn = 0;
     const int items = a.nab * 16;   // (block, 4-row quad); pk > 1: block == packed offset slot, else channel block
+    MaskBits m_next = group_mask(g_begin < g_end ? g_begin : 0);
     for (int64_t g = g_begin; g < g_end; ++g) {
-      const MaskBits m = group_mask(g);
-      if (!group_any(m)) continue;
-      for (int q = 0; q < nq; ++q) {
-        if (!acc_bits(m, q)) continue;
+      const MaskBits m = m_next;
+      if (g + 1 < g_end) m_next = group_mask(g + 1);   // prefetched: the load latency overlaps this group's work
+      for (uint32_t rem = acc_mask(m); rem; rem &= rem - 1) {
+        const int q = __ffs(rem) - 1;
         if (turn == p && a.cpad == 8) {
           // cp.async path (8-channel input): lane = (offset slot j of 16, row half rh); one 16-byte piece per (row, offset)
           const uint32_t a_s = smem_base + ra.slot * kWgASlotBytes;
