@@ -58,10 +58,11 @@ colreduce_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ ou
   }
   if (rl < rpp) {
     const int64_t rstep = (int64_t)gridDim.x * rpp;
-    for (int64_t r0 = (int64_t)blockIdx.x * rpp + rl; r0 < n; r0 += 2 * rstep) {
-      uint4 xr[2], gr[2], orr[2];
+    constexpr int U = (MODE == 0) ? 4 : 2;   // rows in flight per thread
+    for (int64_t r0 = (int64_t)blockIdx.x * rpp + rl; r0 < n; r0 += U * rstep) {
+      uint4 xr[U], gr[U], orr[U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int64_t r = r0 + u * rstep;
         if (r < n) {
           xr[u] = __ldg(reinterpret_cast<const uint4*>(x + r * c) + g);
@@ -72,7 +73,7 @@ colreduce_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ ou
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int64_t r = r0 + u * rstep;
         if (r >= n) continue;
         float xv[8];
@@ -138,37 +139,45 @@ __global__ void bn_prepare_kernel(const double* __restrict__ sums, int64_t n, in
   (void)gamma; (void)beta;
 }
 
+// Apply kernels: thread (rl, g) owns the 8 columns of group g for rows rl, rl + rows-per-pass, ... so the per-column
+// coefficients live in registers (loaded once) and a warp still reads consecutive 16-byte vectors (row-major rows
+// are contiguous: thread t of a pass reads vector r0 * G + t).
 __global__ void __launch_bounds__(kNormThreads)
 bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int c, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
                 const uint16_t* __restrict__ residual, int relu, uint16_t* __restrict__ out) {
   const int G = c / 8;
-  const int64_t total = n * G;
-  constexpr int U = 4;  // independent 16-byte loads in flight per thread
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < total;
-       base += (int64_t)gridDim.x * blockDim.x * U) {
+  const int rpp = kNormThreads / G;
+  const int g = threadIdx.x % G, rl = threadIdx.x / G;
+  if (rl >= rpp) return;
+  float mu[8], sc[8], be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = g * 8 + i;
+    mu[i] = mean[j];
+    sc[i] = gamma[j] * invstd[j];
+    be[i] = beta[j];
+  }
+  constexpr int U = 4;  // independent rows (16-byte loads) in flight per thread
+  const int64_t rstep = (int64_t)gridDim.x * rpp;
+  for (int64_t r0 = (int64_t)blockIdx.x * rpp + rl; r0 < n; r0 += U * rstep) {
     uint4 xr[U], rr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t v = base + (int64_t)u * blockDim.x;
-      if (v < total) {
-        xr[u] = __ldg(reinterpret_cast<const uint4*>(x) + v);
-        if (residual) rr[u] = __ldg(reinterpret_cast<const uint4*>(residual) + v);
+      const int64_t r = r0 + u * rstep;
+      if (r < n) {
+        xr[u] = __ldg(reinterpret_cast<const uint4*>(x + r * c) + g);
+        if (residual) rr[u] = __ldg(reinterpret_cast<const uint4*>(residual + r * c) + g);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t v = base + (int64_t)u * blockDim.x;
-      if (v >= total) continue;
-      const int g = (int)(v % G);
+      const int64_t r = r0 + u * rstep;
+      if (r >= n) continue;
       float xv[8], o[8];
       bf16x8_to_float(xr[u], xv);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = g * 8 + i;
-        const float sc = __ldg(gamma + j) * __ldg(invstd + j);
-        o[i] = fmaf(xv[i] - __ldg(mean + j), sc, __ldg(beta + j));
-      }
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(xv[i] - mu[i], sc[i], be[i]);
       if (residual) {
         float rv[8];
         bf16x8_to_float(rr[u], rv);
@@ -179,7 +188,7 @@ bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int c, const float* _
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
       }
-      reinterpret_cast<uint4*>(out)[v] = float_to_bf16x8(o);
+      reinterpret_cast<uint4*>(out + r * c)[g] = float_to_bf16x8(o);
     }
   }
 }
@@ -191,32 +200,49 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__
                     uint16_t* __restrict__ dx, uint16_t* __restrict__ dres, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
   const int G = c / 8;
-  const int64_t total = n * G;
   if (blockIdx.x == 0) {
     for (int j = threadIdx.x; j < c; j += blockDim.x) {
       if (dbeta) dbeta[j] = (float)red[j];
       if (dgamma) dgamma[j] = (float)red[c + j];
     }
   }
+  const int rpp = kNormThreads / G;
+  const int g = threadIdx.x % G, rl = threadIdx.x / G;
+  if (rl >= rpp) return;
+  // dx = sc * (g - sg - xhat * sgx), xhat = (x - mean) * invstd  ==  sc * (g - sg - (x - mean) * kx)
   const float inv_n = 1.f / (float)n_stat;
+  float mu[8], sc[8], sg[8], kx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = g * 8 + i;
+    const float is = invstd[j];
+    mu[i] = mean[j];
+    sc[i] = gamma[j] * is;
+    if (training) {
+      sg[i] = (float)red[j] * inv_n;
+      kx[i] = is * ((float)red[c + j] * inv_n);
+    } else {
+      sg[i] = 0.f;
+      kx[i] = 0.f;
+    }
+  }
   constexpr int U = 2;
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < total;
-       base += (int64_t)gridDim.x * blockDim.x * U) {
+  const int64_t rstep = (int64_t)gridDim.x * rpp;
+  for (int64_t r0 = (int64_t)blockIdx.x * rpp + rl; r0 < n; r0 += U * rstep) {
     uint4 xr[U], gr[U], orr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t v = base + (int64_t)u * blockDim.x;
-      if (v < total) {
-        xr[u] = __ldg(reinterpret_cast<const uint4*>(x) + v);
-        gr[u] = __ldg(reinterpret_cast<const uint4*>(dout) + v);
-        if (relu) orr[u] = __ldg(reinterpret_cast<const uint4*>(out) + v);
+      const int64_t r = r0 + u * rstep;
+      if (r < n) {
+        xr[u] = __ldg(reinterpret_cast<const uint4*>(x + r * c) + g);
+        gr[u] = __ldg(reinterpret_cast<const uint4*>(dout + r * c) + g);
+        if (relu) orr[u] = __ldg(reinterpret_cast<const uint4*>(out + r * c) + g);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t v = base + (int64_t)u * blockDim.x;
-      if (v >= total) continue;
-      const int g = (int)(v % G);
+      const int64_t r = r0 + u * rstep;
+      if (r >= n) continue;
       float xv[8], gv[8], o[8];
       bf16x8_to_float(xr[u], xv);
       bf16x8_to_float(gr[u], gv);
@@ -227,21 +253,9 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__
         for (int i = 0; i < 8; ++i) if (!(ov[i] > 0.f)) gv[i] = 0.f;
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int j = g * 8 + i;
-        const float is = __ldg(invstd + j);
-        const float sc = __ldg(gamma + j) * is;
-        if (training) {
-          const float xh = (xv[i] - __ldg(mean + j)) * is;
-          const float sg = (float)__ldg(red + j) * inv_n;
-          const float sgx = (float)__ldg(red + c + j) * inv_n;
-          o[i] = sc * (gv[i] - sg - xh * sgx);
-        } else {
-          o[i] = sc * gv[i];
-        }
-      }
-      reinterpret_cast<uint4*>(dx)[v] = float_to_bf16x8(o);
-      if (dres) reinterpret_cast<uint4*>(dres)[v] = float_to_bf16x8(gv);
+      for (int i = 0; i < 8; ++i) o[i] = sc[i] * (gv[i] - sg[i] - (xv[i] - mu[i]) * kx[i]);
+      reinterpret_cast<uint4*>(dx + r * c)[g] = float_to_bf16x8(o);
+      if (dres) reinterpret_cast<uint4*>(dres + r * c)[g] = float_to_bf16x8(gv);
     }
   }
 }
@@ -249,13 +263,14 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__
 static int reduce_grid(int64_t n, int c) {
   const int rpp = kNormThreads / (c / 8);
   int64_t blocks = (n + rpp * 16 - 1) / (rpp * 16);  // >= 16 rows per thread lane
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
-static int apply_grid(int64_t total_vec) {
-  int64_t blocks = (total_vec + kNormThreads * 4 - 1) / (kNormThreads * 4);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+static int apply_grid(int64_t n, int c) {
+  const int rpp = kNormThreads / (c / 8);
+  int64_t blocks = (n + rpp * 4 - 1) / (rpp * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
@@ -299,7 +314,7 @@ extern "C" int b2m_bn_forward(const uint16_t* x, int64_t n, int64_t n_stat, int3
   bn_prepare_kernel<<<1, 256, 0, st>>>(sums, n_stat, c, gamma, beta, running_mean, running_var, momentum, eps, training,
                                       save_mean, save_invstd);
   B2M_CHECK_LAUNCH();
-  bn_apply_kernel<<<apply_grid(n * (c / 8)), kNormThreads, 0, st>>>(x, n, c, gamma, beta, save_mean, save_invstd,
+  bn_apply_kernel<<<apply_grid(n, c), kNormThreads, 0, st>>>(x, n, c, gamma, beta, save_mean, save_invstd,
                                                                    residual, relu, out);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
@@ -329,7 +344,7 @@ extern "C" int b2m_bn_backward_apply(const uint16_t* x, const uint16_t* out, con
   if (relu && !out) return B2M_ERR_INVALID_ARGUMENT;
   if (!norm_shape_ok(c)) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n == 0) return B2M_OK;
-  bn_bwd_apply_kernel<<<apply_grid(n * (c / 8)), kNormThreads, 0, (cudaStream_t)stream>>>(
+  bn_bwd_apply_kernel<<<apply_grid(n, c), kNormThreads, 0, (cudaStream_t)stream>>>(
       x, out, dout, n, n_stat, c, save_mean, save_invstd, gamma, red, relu, training, dx, dresidual, dgamma, dbeta);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
