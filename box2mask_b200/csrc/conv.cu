@@ -136,7 +136,7 @@ struct FwdArgs {
   int64_t n_out, n_pitch;
   int c_red, kvol, c_n, ntile, T, kpack, nkg, nfull, rem, wa, mwords, colstride, n_tiles, n_work;
   int a_slots, b_slots, b_bytes, kg_bytes;
-  int off_b, off_stage, off_bars, tmem_cols;
+  int off_b, off_stage, off_csum, off_bars, tmem_cols;
 };
 
 __device__ __forceinline__ MaskBits fwd_tile_mask(const FwdArgs& a, int tile) {
@@ -206,14 +206,20 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
   }
   if (warp == 5) { tmem_alloc(smem_u32(tmem_ptr_s), (uint32_t)a.tmem_cols); tmem_relinquish(); }
   if (warp == 6 && lane == 0) { tma_prefetch_desc(&tm_main); tma_prefetch_desc(&tm_rem); }
+  if (warp < kEpiWarps)
+    for (int i = tid; i < 2 * a.ntile; i += kEpiWarps * 32) reinterpret_cast<double*>(smem + a.off_csum)[i] = 0.0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
   if (warp < kEpiWarps) {
-    // ================= epilogue warps: TMEM -> staging -> statistics + stores =================
-    float* stage_s = reinterpret_cast<float*>(smem + a.off_stage) + warp * 32 * kStagePitch;
+    // ================= epilogue warps: TMEM -> registers -> (staging for the column statistics) + row stores ====
+    // A lane owns one output row: its 32 (16) accumulator columns of a chunk go to global memory straight from
+    // registers (64 contiguous bytes per row); the transposed copy in shared memory only feeds the per-column
+    // sum / sum of squares, which accumulate in fp64 in shared memory and reach colsum once per CTA.
+    const uint32_t stage_a = smem_base + a.off_stage + warp * (32 * kStagePitch * 4);
+    const uint32_t csum_a = smem_base + a.off_csum;
     int wi = 0;
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
       const int par = wi & 1;
@@ -227,9 +233,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
         const int64_t pos = (int64_t)tile * kTileM + warp * 32 + lane;  // this lane's row (position in `order`)
         int32_t orow = -1;
         if (pos < a.n_out) orow = a.order ? __ldg(a.order + pos) : (int32_t)pos;
-        const int nchunk32 = (a.ntile + 31) / 32;
+        uint16_t* yrow = a.y + (int64_t)(orow >= 0 ? orow : 0) * a.c_n + n0;
+        const int nchunk32 = (a.ntile + 31) >> 5;
         for (int cc = 0; cc < nchunk32; ++cc) {
-          const int cw = min(32, a.ntile - cc * 32);
+          const int cw = min(32, a.ntile - cc * 32);   // 32 or 16
           uint32_t v[32];
           if (has_acc) {
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) +
@@ -240,32 +247,34 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0u;
           }
+          if (a.colsum != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < cw) stage_s[lane * kStagePitch + j] = __uint_as_float(v[j]);
-          __syncwarp();
-          if (a.colsum != nullptr && lane < cw) {
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const float f = stage_s[r * kStagePitch + lane];
-              s1 += f;
-              s2 = fmaf(f, f, s2);
+            for (int j = 0; j < 32; ++j)
+              if (j < cw) st_shared_f32(stage_a + (lane * kStagePitch + j) * 4, __uint_as_float(v[j]));
+            __syncwarp();
+            if (lane < cw) {
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const float f = ld_shared_f32(stage_a + (r * kStagePitch + lane) * 4);
+                s1 += f;
+                s2 = fmaf(f, f, s2);
+              }
+              red_shared_f64(csum_a + (cc * 32 + lane) * 8, (double)s1);
+              red_shared_f64(csum_a + (a.ntile + cc * 32 + lane) * 8, (double)s2);
             }
-            const int col = n0 + cc * 32 + lane;
-            atomicAdd(a.colsum + col, (double)s1);
-            atomicAdd(a.colsum + a.c_n + col, (double)s2);
           }
-          const int groups = cw / 8;
-          for (int e = lane; e < 32 * groups; e += 32) {
-            const int row = e / groups, g = e % groups;
-            const int32_t r = __shfl_sync(0xffffffffu, orow, row);
-            if (r >= 0) {
-              const float* sp = stage_s + row * kStagePitch + g * 8;
-              __align__(16) __nv_bfloat162 o[4];
+          if (orow >= 0) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) o[q] = __floats2bfloat162_rn(sp[2 * q], sp[2 * q + 1]);
-              *reinterpret_cast<uint4*>(a.y + (int64_t)r * a.c_n + n0 + cc * 32 + g * 8) = *reinterpret_cast<const uint4*>(o);
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < cw) {
+                uint4 o;
+                __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  ob[e] = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+                *reinterpret_cast<uint4*>(yrow + cc * 32 + q * 8) = o;
+              }
             }
           }
           __syncwarp();
@@ -274,6 +283,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * par);
+    }
+    if (a.colsum != nullptr) {
+      named_bar_sync(1, kEpiWarps * 32);   // all four epilogue warps have added their last tile
+      const double* cs = reinterpret_cast<const double*>(smem + a.off_csum);
+      for (int i = tid; i < 2 * a.ntile; i += kEpiWarps * 32) {
+        const int col = (i < a.ntile) ? (n0 + i) : (a.c_n + n0 + i - a.ntile);
+        atomicAdd(a.colsum + col, cs[i]);
+      }
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
@@ -869,6 +886,12 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
     ++ntiles_n;
     if (ntiles_n > 8) return B2M_ERR_UNSUPPORTED_SHAPE;
   }
+  // Few row tiles (the deep, 256-wide levels): split the output columns over more CTAs so that the serial
+  // chain of kvol * chunks stages per tile runs on narrower (faster) MMAs on otherwise idle SMs.
+  {
+    const int64_t row_tiles = (n_out + kTileM - 1) / kTileM;
+    while (row_tiles * ntiles_n * 2 <= num_sms() && (c_n / ntiles_n) % 32 == 0 && c_n / ntiles_n >= 64) ntiles_n *= 2;
+  }
   FwdArgs a;
   a.x = x; a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr;
   a.w = reinterpret_cast<const uint8_t*>(packed_w); a.y = y;
@@ -889,14 +912,15 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   a.b_bytes = a.ntile * 128;
   a.b_slots = (a.b_bytes >= 32768) ? 2 : (a.b_bytes >= 16384 ? 3 : 4);
   const int stage_bytes = kEpiWarps * 32 * kStagePitch * 4;
-  const int budget = 227 * 1024 - 1024 - 256 - stage_bytes - a.b_slots * a.b_bytes;
+  const int csum_bytes = 2 * a.ntile * 8;
+  const int budget = 227 * 1024 - 1024 - 256 - stage_bytes - csum_bytes - a.b_slots * a.b_bytes;
   a.a_slots = budget / kASlotBytes;
   if (a.a_slots > 10) a.a_slots = 10;
   if (a.a_slots < 2) return B2M_ERR_UNSUPPORTED_SHAPE;
   a.off_b = a.a_slots * kASlotBytes;
   a.off_stage = a.off_b + a.b_slots * a.b_bytes;
-  a.off_bars = a.off_stage + stage_bytes;
-  a.off_bars = (a.off_bars + 15) / 16 * 16;
+  a.off_csum = (a.off_stage + stage_bytes + 15) / 16 * 16;
+  a.off_bars = (a.off_csum + csum_bytes + 15) / 16 * 16;
   a.tmem_cols = pow2_cols(2 * a.T * a.colstride);
   if (a.tmem_cols > 512) return B2M_ERR_UNSUPPORTED_SHAPE;
   const int smem_bytes = a.off_bars + 16 * a.a_slots + 16 * a.b_slots + 64 + 1024;
@@ -914,9 +938,9 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
       return B2M_ERR_CUDA_LAUNCH;
     attr_set = true;
   }
-  int gx = a.n_work < sms ? a.n_work : sms;
-  if (ntiles_n > 1) gx = (gx + ntiles_n - 1) / ntiles_n;   // keep the total CTA count near one per SM
+  int gx = sms / ntiles_n;                                  // keep the total CTA count near one per SM
   if (gx < 1) gx = 1;
+  if (gx > a.n_work) gx = a.n_work;
   dim3 grid((unsigned)gx, (unsigned)ntiles_n);
   const cudaStream_t st = (cudaStream_t)stream;
   switch (a.kpack) {

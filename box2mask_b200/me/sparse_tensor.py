@@ -48,6 +48,19 @@ class CoordinateManager:
         return self.stride2[fine_stride]
 
 
+    def prepare(self, n_strided, sub_kernels):
+        """Build every coordinate level and kernel map a network will ask for, up front. Each strided level costs
+        one host sync (its row count); doing them back to back on an otherwise empty stream keeps those waits
+        short and leaves the forward / backward passes free of host syncs, so the host runs ahead of the GPU.
+        n_strided: number of stride-2 levels below the input; sub_kernels: iterable of (tensor_stride, kernel_size)."""
+        s = 1
+        for _ in range(int(n_strided)):
+            self.stride2_maps(s)
+            s *= 2
+        for stride, ksize in sub_kernels:
+            self.submanifold_map(int(stride), int(ksize))
+
+
 class SparseTensor:
     def __init__(self, features, coordinates=None, device=None, coordinate_manager=None, tensor_stride=1,
                  quantization_mode=None, **_unused):

@@ -32,6 +32,14 @@ batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
 for _ in range(args.warm):
     bench.train_step(model, opt, batch)
 torch.cuda.synchronize()
+import time  # noqa: E402
+for _ in range(3):   # host enqueue time vs end-to-end time of a step (how far the host runs ahead of the GPU)
+    t0 = time.perf_counter()
+    bench.train_step(model, opt, batch)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print("step: host returned after %.1f ms, GPU done after %.1f ms" % ((t1 - t0) * 1e3, (t2 - t0) * 1e3))
 if args.dump:
     ops.Profile.reset()
     ops.Profile.enabled = True
