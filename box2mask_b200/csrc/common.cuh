@@ -72,12 +72,36 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok;
 }
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef B2M_DEBUG_WAIT
+// debug builds: a timed-out wait first records {block, thread, barrier address, parity, tag} in mapped host memory
+__device__ unsigned int* g_b2m_dbg = nullptr;
+#define B2M_WAIT_TAG(t) (t)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) { __trap(); }
+    if (++spins > (1u << 20)) {
+      if (g_b2m_dbg && (threadIdx.x & 31) == 0) {
+        const unsigned int slot = atomicAdd(g_b2m_dbg, 1u);
+        if (slot < 255) {
+          volatile unsigned int* e = g_b2m_dbg + 8 + slot * 8;
+          e[0] = blockIdx.x; e[1] = threadIdx.x; e[2] = bar; e[3] = parity; e[4] = tag; e[5] = blockIdx.y;
+        }
+        __threadfence_system();
+      }
+      __nanosleep(2000000);
+      __trap();
+    }
   }
 }
+#else
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
+  (void)tag;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) { __trap(); }
+  }
+}
+#endif
 // cp.async 16 B global->shared, zero-filled when src_bytes == 0
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");

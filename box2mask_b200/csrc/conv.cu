@@ -25,7 +25,8 @@
 //      producers  = 12 warps, stage s belongs to warp s % 12: one 16-byte index load + one gather4 per lane.
 //      B loader   = one thread: 1-D bulk copies (TMA engine) of pre-swizzled weight slices; a slice is
 //                   shared by the T tiles of the work item.
-//      MMA issuer = one thread: tcgen05.mma.cta_group::1.kind::f16, M=128, N=ntile, K=16.
+//      MMA issuers = one elected thread per tile of the work item: tcgen05.mma.cta_group::1.kind::f16, M=128,
+//                   N=ntile, K=16.
 //      epilogue   = 4 warps: tcgen05.ld -> per-warp fp32 staging -> BatchNorm column statistics (fp64 atomics)
 //                   -> bf16 row stores (scattered through `order`).
 //      The same kernel computes dgrad (weights packed transposed / mirrored).
@@ -34,6 +35,9 @@
 //      MN-major (a gathered row IS a run of M / N elements). One CTA owns up to G accumulators (G*N <= 512 TMEM
 //      columns) = G offset groups and a range of row groups; a dY stage is shared by the G gathers. fp32 vector
 //      atomics into dW at the end.
+#ifdef B2M_DEBUG_BUILD
+#define B2M_DEBUG_WAIT
+#endif
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -125,7 +129,12 @@ constexpr int kEpiWarps = 4;
 // ~76 cycles per lane (ELECT + R2UR loop around UTMALDG; tools/tma_gather_bench.cu) whatever the box size, and
 // scales linearly with the number of warps, so the TMA engine is fed by many warps.
 constexpr int kFwdProd = 12;
-constexpr int kFwdThreads = (kEpiWarps + 2 + kFwdProd) * 32;  // 576
+// Warps that share the gathers of ONE stage in the 64-wide-chunk mode (KPACK == 1). A slot is occupied from the moment
+// its producer owns it: the ~76-cycle-per-lane TMA issue loop of a single warp (2400 cycles for 32 row quads) was the
+// largest part of a slot's turnaround; split over kFwdSplit warps the 10-slot ring turns over that much faster.
+constexpr int kFwdSplit = 1;
+constexpr int kFwdMma = 2;                                     // one MMA issuer warp per tile of a work item
+constexpr int kFwdThreads = (kEpiWarps + kFwdMma + 1 + kFwdProd) * 32;  // 608
 constexpr int kTileM = 128;
 constexpr int kStagePitch = 33;
 constexpr int kASlotBytes = kTileM * 128;
@@ -199,13 +208,17 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
   const int nch = a.nfull + a.rem;
 
   if (warp == 4 && lane == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
-    for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + 8 * s, 1); mbar_init(acc_empty + 8 * s, kEpiWarps); }
+    // An A slot is recycled only when EVERY tile's issuer has released it (the owner by tcgen05.commit, the others
+    // by a plain arrive after seeing it full): a parity wait is sound only for a waiter that observes every phase,
+    // so no issuer may be lapped on a slot it merely passes.
+    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, KPACK == 1 ? kFwdSplit : 1); mbar_init(a_empty + 8 * s, a.T); }
+    // every tile's MMA issuer releases a B slot / completes an accumulator set: T arrivals each
+    for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, a.T); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + 8 * s, a.T); mbar_init(acc_empty + 8 * s, kEpiWarps); }
     mbar_fence_init();
   }
-  if (warp == 5) { tmem_alloc(smem_u32(tmem_ptr_s), (uint32_t)a.tmem_cols); tmem_relinquish(); }
-  if (warp == 6 && lane == 0) { tma_prefetch_desc(&tm_main); tma_prefetch_desc(&tm_rem); }
+  if (warp == 6) { tmem_alloc(smem_u32(tmem_ptr_s), (uint32_t)a.tmem_cols); tmem_relinquish(); }
+  if (warp == 7 && lane == 0) { tma_prefetch_desc(&tm_main); tma_prefetch_desc(&tm_rem); }
   if (warp < kEpiWarps)
     for (int i = tid; i < 2 * a.ntile; i += kEpiWarps * 32) reinterpret_cast<double*>(smem + a.off_csum)[i] = 0.0;
   tc_fence_before();
@@ -223,7 +236,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     int wi = 0;
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
       const int par = wi & 1;
-      mbar_wait(acc_full + 8 * par, (uint32_t)(wi >> 1) & 1u);
+      mbar_wait(acc_full + 8 * par, (uint32_t)(wi >> 1) & 1u, 1);
       tc_fence_after();
       for (int t = 0; t < a.T; ++t) {
         const int tile = w * a.T + t;
@@ -292,85 +305,103 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
         atomicAdd(a.colsum + col, cs[i]);
       }
     }
-  } else if (warp == 4) {
-    // ================= MMA issuer =================
-    // The whole warp runs the loop (every value below is warp-uniform, so it lives in uniform registers and the
-    // UTCHMMA operands need no per-instruction R2UR); one elected lane issues the MMAs and the commits.
-    const bool lead = elect_one_sync();
-    const uint32_t idesc = umma_idesc_bf16(kTileM, a.ntile, 0, 0);
-    const uint32_t hi128 = umma_desc_hi(1024, 128), hi64 = umma_desc_hi(512, 64), hi32 = umma_desc_hi(256, 32);
-    const uint32_t hia = (KPACK == 2) ? hi64 : (KPACK == 4 ? hi32 : hi128);
-    Ring ra, rb;
-    ra.init(SA); rb.init(SB);
-    int wi = 0;
-    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
-      const int par = wi & 1;
-      mbar_wait(acc_empty + 8 * par, ((uint32_t)(wi >> 1) & 1u) ^ 1u);
-      tc_fence_after();
-      const MaskBits m0 = fwd_tile_mask(a, w * a.T);
-      const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
-      const MaskBits mu = mask_or(m0, m1);
-      uint32_t started = 0;
-      for (int kg = next_group<KPACK>(mu, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mu, kg + 1, a.nkg, a.mwords)) {
-        const uint32_t s0 = mask_bits(m0, kg * KPACK, KPACK), s1 = mask_bits(m1, kg * KPACK, KPACK);
-        for (int c = 0; c < nch; ++c) {
-          mbar_wait(b_full + 8 * rb.slot, rb.phase);
-          const uint32_t b_lo = umma_desc_lo(smem_base + a.off_b + rb.slot * a.b_bytes, 16);
-          for (int t = 0; t < a.T; ++t) {
-            const uint32_t sub = t ? s1 : s0;
-            if (!sub) continue;
-            mbar_wait(a_full + 8 * ra.slot, ra.phase);
-            tc_fence_after();
-            const uint32_t a_lo = umma_desc_lo(smem_base + ra.slot * kASlotBytes, 16);
-            const uint32_t d = tmem_base + (uint32_t)((par * a.T + t) * a.colstride);
-            uint32_t acc = (started >> t) & 1u;
-            if (lead) {
-              if (KPACK == 1) {
-                const bool full_chunk = c < a.nfull;
-                const uint32_t hi = full_chunk ? hi128 : hi64;
-                const int nks = full_chunk ? min(4, (a.c_red - c * 64) >> 4) : 2;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {       // +32 bytes (2 descriptor units) per K=16 step
-                  if (ks < nks) {
-                    umma_bf16_lohi(d, a_lo + 2 * ks, hi, b_lo + 2 * ks, hi, idesc, acc);
-                    acc = 1u;
+  } else if (warp < kEpiWarps + kFwdMma) {
+    // ================= MMA issuers: warp 4 owns tile 0 of every work item, warp 5 tile 1 (T == 2) =================
+    // The single-thread issue loop is the critical path of this kernel (~90 instructions per stage), so the two
+    // tiles of a work item, which accumulate into different TMEM columns, get an issuer each. The whole warp runs
+    // the loop (warp-uniform values live in uniform registers); one elected lane issues MMAs and commits.
+    const int me = warp - kEpiWarps;
+    if (me < a.T) {
+      const bool lead = elect_one_sync();
+      const uint32_t idesc = umma_idesc_bf16(kTileM, a.ntile, 0, 0);
+      const uint32_t hi128 = umma_desc_hi(1024, 128), hi64 = umma_desc_hi(512, 64), hi32 = umma_desc_hi(256, 32);
+      const uint32_t hia = (KPACK == 2) ? hi64 : (KPACK == 4 ? hi32 : hi128);
+      Ring ra, rb;
+      ra.init(SA); rb.init(SB);
+      int wi = 0;
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
+        const int par = wi & 1;
+        mbar_wait(acc_empty + 8 * par, ((uint32_t)(wi >> 1) & 1u) ^ 1u, 2);
+        tc_fence_after();
+        const MaskBits m0 = fwd_tile_mask(a, w * a.T);
+        const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
+        const MaskBits mu = mask_or(m0, m1);
+        const uint32_t d = tmem_base + (uint32_t)((par * a.T + me) * a.colstride);
+        uint32_t acc = 0;
+        for (int kg = next_group<KPACK>(mu, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mu, kg + 1, a.nkg, a.mwords)) {
+          const uint32_t s0 = mask_bits(m0, kg * KPACK, KPACK), s1 = mask_bits(m1, kg * KPACK, KPACK);
+          const uint32_t sub = me ? s1 : s0;
+          for (int c = 0; c < nch; ++c) {
+            if (sub) {
+              // Stages of the other tile are passed WITH a wait on their full barrier: a parity wait is only sound
+              // for a waiter that has observed every earlier phase of that barrier.
+              if (a.T > 1 && me == 1 && s0) { mbar_wait(a_full + 8 * ra.slot, ra.phase, 3); if (lead) mbar_arrive(a_empty + 8 * ra.slot); ra.next(); }   // tile 0's stage comes first
+              mbar_wait(b_full + 8 * rb.slot, rb.phase, 4);
+              mbar_wait(a_full + 8 * ra.slot, ra.phase, 5);
+              tc_fence_after();
+              if (lead) {
+                const uint32_t b_lo = umma_desc_lo(smem_base + a.off_b + rb.slot * a.b_bytes, 16);
+                const uint32_t a_lo = umma_desc_lo(smem_base + ra.slot * kASlotBytes, 16);
+                if (KPACK == 1) {
+                  const bool full_chunk = c < a.nfull;
+                  const int nks = full_chunk ? min(4, (a.c_red - c * 64) >> 4) : 2;
+                  if (nks == 4) {                        // the common case, straight-line: +32 bytes per K=16 step
+                    umma_bf16_lohi(d, a_lo, hi128, b_lo, hi128, idesc, acc);
+                    umma_bf16_lohi(d, a_lo + 2, hi128, b_lo + 2, hi128, idesc, 1u);
+                    umma_bf16_lohi(d, a_lo + 4, hi128, b_lo + 4, hi128, idesc, 1u);
+                    umma_bf16_lohi(d, a_lo + 6, hi128, b_lo + 6, hi128, idesc, 1u);
+                  } else {
+                    const uint32_t hi = full_chunk ? hi128 : hi64;
+                    for (int ks = 0; ks < nks; ++ks) umma_bf16_lohi(d, a_lo + 2 * ks, hi, b_lo + 2 * ks, hi, idesc, ks ? 1u : acc);
                   }
-                }
-              } else if (KPACK == 8) {
-                // 8 offsets x 8 channels side by side in one SW128 tile: a K=16 step covers a pair of offsets
+                } else if (KPACK == 8) {
+                  // 8 offsets x 8 channels side by side in one SW128 tile: a K=16 step covers a pair of offsets
+                  uint32_t ac = acc;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if ((sub >> (2 * ks)) & 3u) {
-                    umma_bf16_lohi(d, a_lo + 2 * ks, hi128, b_lo + 2 * ks, hi128, idesc, acc);
-                    acc = 1u;
+                  for (int ks = 0; ks < 4; ++ks) {
+                    if ((sub >> (2 * ks)) & 3u) {
+                      umma_bf16_lohi(d, a_lo + 2 * ks, hi128, b_lo + 2 * ks, hi128, idesc, ac);
+                      ac = 1u;
+                    }
                   }
-                }
-              } else {
-                constexpr uint32_t wa = 128 / KPACK;               // sub-tile row bytes: 64 (SW64) or 32 (SW32)
+                } else {
+                  constexpr uint32_t wa = 128 / KPACK;               // sub-tile row bytes: 64 (SW64) or 32 (SW32)
+                  uint32_t ac = acc;
 #pragma unroll
-                for (int j = 0; j < KPACK; ++j) {
-                  if ((sub >> j) & 1u) {
+                  for (int j = 0; j < KPACK; ++j) {
+                    if ((sub >> j) & 1u) {
 #pragma unroll
-                    for (uint32_t ks = 0; ks < wa / 32; ++ks) {
-                      umma_bf16_lohi(d, a_lo + ((j * kTileM * wa) >> 4) + 2 * ks, hia, b_lo + ((j * wa) >> 4) + 2 * ks, hi128, idesc, acc);
-                      acc = 1u;
+                      for (uint32_t ks = 0; ks < wa / 32; ++ks) {
+                        umma_bf16_lohi(d, a_lo + ((j * kTileM * wa) >> 4) + 2 * ks, hia, b_lo + ((j * wa) >> 4) + 2 * ks, hi128, idesc, ac);
+                        ac = 1u;
+                      }
                     }
                   }
                 }
+                umma_commit(a_empty + 8 * ra.slot);
+                umma_commit(b_empty + 8 * rb.slot);            // arrives once this tile's MMAs on the slice are done
               }
-              umma_commit(a_empty + 8 * ra.slot);
+              acc = 1u;
+              ra.next();
+              if (a.T > 1 && me == 0 && s1) { mbar_wait(a_full + 8 * ra.slot, ra.phase, 6); if (lead) mbar_arrive(a_empty + 8 * ra.slot); ra.next(); }   // pass tile 1's stage
+            } else {
+              // The other tile uses this offset group, this one does not: pass its A stage and release the B slot.
+              // Waiting for the slice first keeps this warp from running a whole slot use ahead: b_empty counts
+              // arrivals, it cannot tell two arrivals of one warp from one arrival of each.
+              mbar_wait(a_full + 8 * ra.slot, ra.phase, 7);
+              if (lead) mbar_arrive(a_empty + 8 * ra.slot);
+              ra.next();
+              mbar_wait(b_full + 8 * rb.slot, rb.phase, 8);
+              if (lead) mbar_arrive(b_empty + 8 * rb.slot);
             }
-            started |= 1u << t;
-            ra.next();
+            rb.next();
           }
-          if (lead) umma_commit(b_empty + 8 * rb.slot);
-          rb.next();
         }
+        if (lead) umma_commit(acc_full + 8 * par);
       }
-      if (lead) umma_commit(acc_full + 8 * par);
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == kEpiWarps + kFwdMma) {
     // ================= B loader: bulk copies of pre-swizzled weight slices (warp-uniform, elected lane issues) ====
     const bool lead = elect_one_sync();
     Ring rb;
@@ -381,7 +412,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       const MaskBits mu = mask_or(m0, m1);
       for (int kg = next_group<KPACK>(mu, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mu, kg + 1, a.nkg, a.mwords)) {
         for (int c = 0; c < nch; ++c) {
-          mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u);
+          mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u, 9);
           if (lead) {
             const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
             const int wb = (c < a.nfull) ? 128 : 64;
@@ -399,8 +430,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     // ================= gather warps: A stage s is produced by warp s % kFwdProd =================
     // Stage s is produced by warp s % np with np <= SA: a warp then never runs more than one use of a slot ahead
     // of the consumer, which is what waiting on an mbarrier phase PARITY requires.
-    const int p = warp - (kEpiWarps + 2);
-    const int np = min(kFwdProd, SA);
+    constexpr int NS = (KPACK == 1) ? kFwdSplit : 1;
+    const int p = (warp - (kEpiWarps + kFwdMma + 1)) / NS;      // producer group; its NS warps split the row quads
+    const int part = (warp - (kEpiWarps + kFwdMma + 1)) % NS;
+    const int np = min(kFwdProd / NS, SA);
+    const int q_lo = part * 32 / NS, q_hi = (part + 1) * 32 / NS;   // this warp's row quads of a 128-row tile
     Ring ra;
     ra.init(SA);
     int turn = 0;  // stage counter modulo np
@@ -415,24 +449,28 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
             const uint32_t sub = t ? s1 : s0;
             if (!sub) continue;
             if (turn == p) {
-              const int64_t pos0 = (int64_t)(w * a.T + t) * kTileM + 4 * lane;  // this lane gathers rows pos0 .. pos0+3
+              const int quad = (KPACK == 1) ? q_lo + lane : lane;                 // this lane gathers rows 4*quad .. 4*quad+3
+              const int64_t pos0 = (int64_t)(w * a.T + t) * kTileM + 4 * quad;
               const uint32_t a_s = smem_base + ra.slot * kASlotBytes;
               const uint32_t full = a_full + 8 * ra.slot;
               if (KPACK == 1) {
-                int4 idx;
-                if (a.nbr) {
-                  idx = ld_nc_int4(a.nbr + (int64_t)kg * a.n_pitch + pos0);
-                } else {
-                  idx.x = pos0 < a.n_out ? (int)pos0 : -1;
-                  idx.y = pos0 + 1 < a.n_out ? (int)pos0 + 1 : -1;
-                  idx.z = pos0 + 2 < a.n_out ? (int)pos0 + 2 : -1;
-                  idx.w = pos0 + 3 < a.n_out ? (int)pos0 + 3 : -1;
+                const bool on = quad < q_hi;
+                int4 idx = make_int4(-1, -1, -1, -1);
+                if (on) {
+                  if (a.nbr) {
+                    idx = ld_nc_int4(a.nbr + (int64_t)kg * a.n_pitch + pos0);
+                  } else {
+                    idx.x = pos0 < a.n_out ? (int)pos0 : -1;
+                    idx.y = pos0 + 1 < a.n_out ? (int)pos0 + 1 : -1;
+                    idx.z = pos0 + 2 < a.n_out ? (int)pos0 + 2 : -1;
+                    idx.w = pos0 + 3 < a.n_out ? (int)pos0 + 3 : -1;
+                  }
                 }
                 const uint32_t wc = (c < a.nfull) ? 128u : 64u;
-                mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u);
-                if (lane == 0) mbar_arrive_expect_tx(full, kTileM * wc);
+                mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u, 10);
+                if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(q_hi - q_lo) * 4u * wc);
                 __syncwarp();
-                tma_gather4(a_s + lane * 4 * wc, (c < a.nfull) ? &tm_main : &tm_rem, full, c * 64, idx.x, idx.y, idx.z, idx.w);
+                if (on) tma_gather4(a_s + quad * 4 * wc, (c < a.nfull) ? &tm_main : &tm_rem, full, c * 64, idx.x, idx.y, idx.z, idx.w);
               } else if (KPACK == 8) {
                 // cp.async path: lane = (offset j of the group, row quad rq); 8 x (one 16-byte index load + 4 copies)
                 const int j = lane & 7, rq = lane >> 3;
@@ -502,7 +540,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 6) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
@@ -850,6 +888,21 @@ static int num_sms() {
   }
   return g_num_sms;
 }
+
+#ifdef B2M_DEBUG_WAIT
+// debug builds only: mapped host buffer that timed-out barrier waits report into ([0] = count, entries from [8])
+extern "C" unsigned int* b2m_debug_wait_buffer(void) {
+  static unsigned int* host = nullptr;
+  if (!host) {
+    if (cudaHostAlloc(&host, 8192 * 4, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    for (int i = 0; i < 8192; ++i) host[i] = 0;
+    unsigned int* dev = nullptr;
+    cudaHostGetDevicePointer(&dev, host, 0);
+    cudaMemcpyToSymbol(g_b2m_dbg, &dev, sizeof(dev));
+  }
+  return host;
+}
+#endif
 
 extern "C" size_t b2m_packed_weight_bytes(int32_t kvol, int32_t c_in, int32_t c_out, int32_t mode) {
   const int c_red = (mode == 0) ? c_in : c_out;
