@@ -41,6 +41,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace b2m {
 
@@ -187,6 +188,8 @@ struct Ring {
   int slot; uint32_t phase; int n;
   __device__ __forceinline__ void init(int n_) { slot = 0; phase = 0; n = n_; }
   __device__ __forceinline__ void next() { if (++slot == n) { slot = 0; phase ^= 1u; } }
+  __device__ __forceinline__ void advance(int k) { slot += k; while (slot >= n) { slot -= n; phase ^= 1u; } }
+  __device__ __forceinline__ Ring at(int k) const { Ring r = *this; r.advance(k); return r; }
 };
 
 // KPACK = offsets per A stage: 1 (c_red >= 48: 64-wide chunks), 2 / 4 (c_red 32 / 16: SW64 / SW32 sub-tiles),
@@ -438,17 +441,25 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     Ring ra;
     ra.init(SA);
     int turn = 0;  // stage counter modulo np
-    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+    for (int w = (p < np) ? blockIdx.x : a.n_work; w < a.n_work; w += gridDim.x) {   // warps beyond np have no stages
       const MaskBits m0 = fwd_tile_mask(a, w * a.T);
       const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
       const MaskBits mu = mask_or(m0, m1);
       for (int kg = next_group<KPACK>(mu, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mu, kg + 1, a.nkg, a.mwords)) {
         const uint32_t s0 = mask_bits(m0, kg * KPACK, KPACK), s1 = mask_bits(m1, kg * KPACK, KPACK);
-        for (int c = 0; c < nch; ++c) {
-          for (int t = 0; t < a.T; ++t) {
+        // The stages of this offset group come in (chunk, tile) order; jump straight to the ones whose turn is
+        // this warp's (stage index = turn + d) instead of walking all of them.
+        const int nt = (s0 != 0) + (s1 != 0);
+        const int n_kg = nch * nt;
+        int d0 = p - turn;
+        if (d0 < 0) d0 += np;
+        const Ring ra0 = ra;
+        for (int d = d0; d < n_kg; d += np) {
+            const int c = d / nt;
+            const int t = (nt == 2) ? (d - c * nt) : (s0 ? 0 : 1);
             const uint32_t sub = t ? s1 : s0;
-            if (!sub) continue;
-            if (turn == p) {
+            ra = ra0.at(d);
+            {
               const int quad = (KPACK == 1) ? q_lo + lane : lane;                 // this lane gathers rows 4*quad .. 4*quad+3
               const int64_t pos0 = (int64_t)(w * a.T + t) * kTileM + 4 * quad;
               const uint32_t a_s = smem_base + ra.slot * kASlotBytes;
@@ -530,10 +541,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                     tma_gather4(a_s + j * kTileM * wa + lane * 4 * wa, &tm_main, full, 0, idx[j].x, idx[j].y, idx[j].z, idx[j].w);
               }
             }
-            ra.next();
-            turn = (turn + 1 == np) ? 0 : turn + 1;
-          }
         }
+        ra = ra0.at(n_kg);
+        turn += n_kg;
+        while (turn >= np) turn -= np;
       }
     }
   }
@@ -867,7 +878,7 @@ static bool make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int co
                               : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                 : (box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
   return g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -878,6 +889,9 @@ static bool make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int co
 // ------------------------------------------------------------------------------------------------
 using namespace b2m;
 
+// Number of CTAs the persistent convolution kernels launch: one per SM, or B2M_MAX_CTAS from the environment
+// (read once). Data-parallel training sets it below the SM count so that the NCCL all-reduce kernels that overlap
+// the backward pass find free SMs instead of forcing a second wave of conv CTAs.
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -885,6 +899,11 @@ static int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
+    const char* e = getenv("B2M_MAX_CTAS");
+    if (e) {
+      const int v = atoi(e);
+      if (v > 0 && v < g_num_sms) g_num_sms = v;
+    }
   }
   return g_num_sms;
 }
