@@ -211,10 +211,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
   const int nch = a.nfull + a.rem;
 
   if (warp == 4 && lane == 0) {
-    // An A slot is recycled only when EVERY tile's issuer has released it (the owner by tcgen05.commit, the others
-    // by a plain arrive after seeing it full): a parity wait is sound only for a waiter that observes every phase,
-    // so no issuer may be lapped on a slot it merely passes.
-    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, KPACK == 1 ? kFwdSplit : 1); mbar_init(a_empty + 8 * s, a.T); }
+    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, KPACK == 1 ? kFwdSplit : 1); mbar_init(a_empty + 8 * s, 1); }
     // every tile's MMA issuer releases a B slot / completes an accumulator set: T arrivals each
     for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, a.T); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full + 8 * s, a.T); mbar_init(acc_empty + 8 * s, kEpiWarps); }
@@ -319,8 +316,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       const uint32_t idesc = umma_idesc_bf16(kTileM, a.ntile, 0, 0);
       const uint32_t hi128 = umma_desc_hi(1024, 128), hi64 = umma_desc_hi(512, 64), hi32 = umma_desc_hi(256, 32);
       const uint32_t hia = (KPACK == 2) ? hi64 : (KPACK == 4 ? hi32 : hi128);
+      // Each tile of the work item has a PRIVATE ring of A slots (SA / T each) fed by its own producer warps, so an
+      // issuer only ever meets its own stages (a parity wait is sound only for a waiter that sees every phase of a
+      // barrier). The weight slices (B ring) are shared: both issuers wait for and release every slice.
+      const int SAr = SA / a.T, abase = me * SAr;
       Ring ra, rb;
-      ra.init(SA); rb.init(SB);
+      ra.init(SAr); rb.init(SB);
       int wi = 0;
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
         const int par = wi & 1;
@@ -336,15 +337,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
           const uint32_t sub = me ? s1 : s0;
           for (int c = 0; c < nch; ++c) {
             if (sub) {
-              // Stages of the other tile are passed WITH a wait on their full barrier: a parity wait is only sound
-              // for a waiter that has observed every earlier phase of that barrier.
-              if (a.T > 1 && me == 1 && s0) { mbar_wait(a_full + 8 * ra.slot, ra.phase, 3); if (lead) mbar_arrive(a_empty + 8 * ra.slot); ra.next(); }   // tile 0's stage comes first
+              const int aslot = abase + ra.slot;
               mbar_wait(b_full + 8 * rb.slot, rb.phase, 4);
-              mbar_wait(a_full + 8 * ra.slot, ra.phase, 5);
+              mbar_wait(a_full + 8 * aslot, ra.phase, 5);
               tc_fence_after();
               if (lead) {
                 const uint32_t b_lo = umma_desc_lo(smem_base + a.off_b + rb.slot * a.b_bytes, 16);
-                const uint32_t a_lo = umma_desc_lo(smem_base + ra.slot * kASlotBytes, 16);
+                const uint32_t a_lo = umma_desc_lo(smem_base + aslot * kASlotBytes, 16);
                 if (KPACK == 1) {
                   const bool full_chunk = c < a.nfull;
                   const int nks = full_chunk ? min(4, (a.c_red - c * 64) >> 4) : 2;
@@ -381,19 +380,15 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                     }
                   }
                 }
-                umma_commit(a_empty + 8 * ra.slot);
+                umma_commit(a_empty + 8 * aslot);
                 umma_commit(b_empty + 8 * rb.slot);            // arrives once this tile's MMAs on the slice are done
               }
               acc = 1u;
               ra.next();
-              if (a.T > 1 && me == 0 && s1) { mbar_wait(a_full + 8 * ra.slot, ra.phase, 6); if (lead) mbar_arrive(a_empty + 8 * ra.slot); ra.next(); }   // pass tile 1's stage
             } else {
-              // The other tile uses this offset group, this one does not: pass its A stage and release the B slot.
-              // Waiting for the slice first keeps this warp from running a whole slot use ahead: b_empty counts
-              // arrivals, it cannot tell two arrivals of one warp from one arrival of each.
-              mbar_wait(a_full + 8 * ra.slot, ra.phase, 7);
-              if (lead) mbar_arrive(a_empty + 8 * ra.slot);
-              ra.next();
+              // The other tile uses this offset group, this one does not: release the B slot. Waiting for the slice
+              // first keeps this warp from running a whole slot use ahead: b_empty counts arrivals, it cannot tell
+              // two arrivals of one warp from one arrival of each.
               mbar_wait(b_full + 8 * rb.slot, rb.phase, 8);
               if (lead) mbar_arrive(b_empty + 8 * rb.slot);
             }
@@ -433,37 +428,39 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     // ================= gather warps: A stage s is produced by warp s % kFwdProd =================
     // Stage s is produced by warp s % np with np <= SA: a warp then never runs more than one use of a slot ahead
     // of the consumer, which is what waiting on an mbarrier phase PARITY requires.
+    // With T == 2 the warps are split between the two tiles' private rings (see the MMA issuers). Within a ring,
+    // stage s is produced by warp s % np with np <= ring size: a warp then never runs more than one use of a slot
+    // ahead of the consumer, which is what waiting on an mbarrier phase PARITY requires.
     constexpr int NS = (KPACK == 1) ? kFwdSplit : 1;
-    const int p = (warp - (kEpiWarps + kFwdMma + 1)) / NS;      // producer group; its NS warps split the row quads
+    const int pw = (warp - (kEpiWarps + kFwdMma + 1)) / NS;     // producer group; its NS warps split the row quads
     const int part = (warp - (kEpiWarps + kFwdMma + 1)) % NS;
-    const int np = min(kFwdProd / NS, SA);
+    const int groups = (kFwdProd / NS) / a.T;                   // producer groups per ring
+    const int t = (a.T > 1 && pw >= groups) ? 1 : 0;            // the tile (ring) this warp feeds
+    const int p = pw - t * groups;
+    const int SAr = SA / a.T, abase = t * SAr;
+    const int np = min(groups, SAr);
     const int q_lo = part * 32 / NS, q_hi = (part + 1) * 32 / NS;   // this warp's row quads of a 128-row tile
     Ring ra;
-    ra.init(SA);
+    ra.init(SAr);
     int turn = 0;  // stage counter modulo np
-    for (int w = (p < np) ? blockIdx.x : a.n_work; w < a.n_work; w += gridDim.x) {   // warps beyond np have no stages
-      const MaskBits m0 = fwd_tile_mask(a, w * a.T);
-      const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
-      const MaskBits mu = mask_or(m0, m1);
-      for (int kg = next_group<KPACK>(mu, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mu, kg + 1, a.nkg, a.mwords)) {
-        const uint32_t s0 = mask_bits(m0, kg * KPACK, KPACK), s1 = mask_bits(m1, kg * KPACK, KPACK);
-        // The stages of this offset group come in (chunk, tile) order; jump straight to the ones whose turn is
-        // this warp's (stage index = turn + d) instead of walking all of them.
-        const int nt = (s0 != 0) + (s1 != 0);
-        const int n_kg = nch * nt;
+    for (int w = (p < np && pw < groups * a.T) ? blockIdx.x : a.n_work; w < a.n_work; w += gridDim.x) {   // spare warps have no stages
+      const MaskBits mt = fwd_tile_mask(a, w * a.T + t);
+      for (int kg = next_group<KPACK>(mt, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mt, kg + 1, a.nkg, a.mwords)) {
+        const uint32_t sub = mask_bits(mt, kg * KPACK, KPACK);
+        // jump straight to the chunks of this offset group whose turn is this warp's (stage index = turn + d)
+        const int n_kg = nch;
         int d0 = p - turn;
         if (d0 < 0) d0 += np;
         const Ring ra0 = ra;
         for (int d = d0; d < n_kg; d += np) {
-            const int c = d / nt;
-            const int t = (nt == 2) ? (d - c * nt) : (s0 ? 0 : 1);
-            const uint32_t sub = t ? s1 : s0;
-            ra = ra0.at(d);
+            const int c = d;
+            const Ring rs = ra0.at(d);
+            const int aslot = abase + rs.slot;
             {
               const int quad = (KPACK == 1) ? q_lo + lane : lane;                 // this lane gathers rows 4*quad .. 4*quad+3
               const int64_t pos0 = (int64_t)(w * a.T + t) * kTileM + 4 * quad;
-              const uint32_t a_s = smem_base + ra.slot * kASlotBytes;
-              const uint32_t full = a_full + 8 * ra.slot;
+              const uint32_t a_s = smem_base + aslot * kASlotBytes;
+              const uint32_t full = a_full + 8 * aslot;
               if (KPACK == 1) {
                 const bool on = quad < q_hi;
                 int4 idx = make_int4(-1, -1, -1, -1);
@@ -478,7 +475,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                   }
                 }
                 const uint32_t wc = (c < a.nfull) ? 128u : 64u;
-                mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u, 10);
+                mbar_wait(a_empty + 8 * aslot, rs.phase ^ 1u, 10);
                 if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(q_hi - q_lo) * 4u * wc);
                 __syncwarp();
                 if (on) tma_gather4(a_s + quad * 4 * wc, (c < a.nfull) ? &tm_main : &tm_rem, full, c * 64, idx.x, idx.y, idx.z, idx.w);
@@ -488,7 +485,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                 const int k = kg * 8 + j;
                 const bool on = ((sub >> j) & 1u) != 0;
                 const int32_t* nb = a.nbr ? a.nbr + (int64_t)k * a.n_pitch + (int64_t)(w * a.T + t) * kTileM : nullptr;
-                mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u);
+                mbar_wait(a_empty + 8 * aslot, rs.phase ^ 1u);
 #pragma unroll 2
                 for (int it = 0; it < 8; ++it) {
                   const int r0 = 16 * it + 4 * rq;
@@ -532,7 +529,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                       idx[j].w = pos0 + 3 < a.n_out ? (int)pos0 + 3 : -1;
                     }
                   }
-                mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u);
+                mbar_wait(a_empty + 8 * aslot, rs.phase ^ 1u);
                 if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)__popc(sub) * kTileM * wa);
                 __syncwarp();
 #pragma unroll
