@@ -759,9 +759,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     for (int64_t g = g_begin; g < g_end; ++g) {
       const MaskBits m = m_next;
       if (g + 1 < g_end) m_next = group_mask(g + 1);   // prefetched: the load latency overlaps this group's work
-      for (uint32_t rem = acc_mask(m); rem; rem &= rem - 1) {
+      // The stages of this row group are the set bits of qm in ascending order; jump to the ones whose turn is this
+      // warp's instead of walking all of them.
+      const uint32_t qm = (p < np) ? acc_mask(m) : 0u;
+      const int n_g = __popc(qm);
+      int d0 = p - turn;
+      if (d0 < 0) d0 += np;
+      const Ring ra0 = ra;
+      for (int d = d0; d < n_g; d += np) {
+        uint32_t rem = qm;
+        for (int i = 0; i < d; ++i) rem &= rem - 1;     // drop the d lowest set bits
         const int q = __ffs(rem) - 1;
-        if (turn == p && a.cpad == 8) {
+        ra = ra0.at(d);
+        const bool mine = true;
+        if (mine && a.cpad == 8) {
           // cp.async path (8-channel input): lane = (offset slot j of 16, row half rh); one 16-byte piece per (row, offset)
           const uint32_t a_s = smem_base + ra.slot * kWgASlotBytes;
           const int j = lane & 15, rh = lane >> 4;
@@ -794,7 +805,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full + 8 * ra.slot);
-        } else if (turn == p) {
+        } else if (mine) {
           const uint32_t a_s = smem_base + ra.slot * kWgASlotBytes;
           const uint32_t full = a_full + 8 * ra.slot;
           const int k0 = kbase + q * a.pk;
@@ -833,9 +844,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
           }
         }
-        ra.next();
-        turn = (turn + 1 == np) ? 0 : turn + 1;
       }
+      ra = ra0.at(n_g);
+      turn += n_g;
+      while (turn >= np) turn -= np;
     }
   }
 
