@@ -991,7 +991,7 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   a.T = (a.ntile <= 128 && a.n_tiles >= 4 * sms) ? 2 : 1;
   a.n_work = (a.n_tiles + a.T - 1) / a.T;
   a.b_bytes = a.ntile * 128;
-  a.b_slots = (a.b_bytes >= 32768) ? 2 : (a.b_bytes >= 16384 ? 3 : 4);
+  a.b_slots = (a.b_bytes >= 32768) ? 2 : (a.b_bytes >= 12288 ? 3 : 4);
   const int stage_bytes = kEpiWarps * 32 * kStagePitch * 4;
   const int csum_bytes = 2 * a.ntile * 8;
   const int budget = 227 * 1024 - 1024 - 256 - stage_bytes - csum_bytes - a.b_slots * a.b_bytes;

@@ -159,3 +159,51 @@ def test_drop_in_module_surface(setup):
         ref = torch.zeros(s, 96, device=DEV).index_add_(0, batch["pooling_ids"].to(DEV), feats.F.float())
         ref = ref / torch.bincount(batch["pooling_ids"].to(DEV), minlength=s)[:, None]
         assert torch.allclose(pooled.F, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_train_mode_stage_forward_backward_well_conditioned(setup):
+    """Training-mode BatchNorm where it IS well conditioned: the full-resolution decoder stage (block8: BasicBlock
+    128->96 with 1x1 downsample branch + BasicBlock 96->96 = 4 k27 convolutions, one 1x1, five batch-statistics
+    BatchNorms, two residual adds) on ~40k rows. Forward, input gradient and every weight / affine gradient against
+    the oracle with bf16 emulation at the same storage points. Tolerances: outputs |err| <= 2% of range and cosine
+    >= 0.9999; gradients cosine >= 0.995 (bf16 gradient storage between layers on the GPU vs fp32 in the oracle)."""
+    import box2mask_b200
+    from box2mask_b200.synthetic import make_batch
+    from oracle import sparse_ops as so
+    ME = box2mask_b200.install_as_minkowski_engine()
+    _, _, cfg, model, sd, _ = setup
+    model.load_state_dict(sd)
+    net = model.net
+    net.train()
+    batch = make_batch(2, seed=11, scale=0.3, density=1.2e4)
+    coords = batch["vox_coords"]
+    n = coords.shape[0]
+    assert n > 20000
+    torch.manual_seed(3)
+    x0 = so.bf16_round(torch.randn(n, 128))
+    gout = so.bf16_round(torch.randn(n, 96))
+    # product path
+    for p in net.block8.parameters():
+        p.grad = None
+    xg = x0.to(DEV).to(torch.bfloat16).requires_grad_(True)
+    st = ME.SparseTensor(xg, coords, device=DEV)
+    out = net.block8(st)
+    out.F.backward(gout.to(DEV).to(torch.bfloat16))
+    # oracle
+    osd = {k[len("block8."):]: v.clone() for k, v in sd.items() if k.startswith("block8.")}
+    osd = {"block8." + k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in osd.items()}
+    xo = x0.clone().requires_grad_(True)
+    onet = OracleNet(osd, cfg, training=True, emulate_bf16=True)
+    nbr = so.kernel_map_submanifold(coords.numpy(), 1, 3)
+    ref = onet.stage("block8", xo, nbr)
+    ref.backward(gout)
+    got = out.F.float().cpu()
+    scale = float(ref.abs().max())
+    assert _cos(got, ref.detach()) >= 0.9999, _cos(got, ref.detach())
+    assert float((got - ref.detach()).abs().max()) <= 0.02 * scale
+    assert _cos(xg.grad.float().cpu(), xo.grad) >= 0.995, _cos(xg.grad.float().cpu(), xo.grad)
+    worst = {}
+    for name, p in net.block8.named_parameters():
+        c = _cos(p.grad.cpu(), osd["block8." + name].grad)
+        worst[name] = c
+    assert min(worst.values()) >= 0.995, sorted(worst.items(), key=lambda kv: kv[1])[:4]
