@@ -248,7 +248,9 @@ def main():
             ms = float(t.item())
         return ms / steps
 
-    for i in range(args.warmup):
+    # warm-up: at least W steps and every distinct batch once (their row counts differ, so each one grows the
+    # caching allocator the first time it is seen; that must not happen inside the timed region)
+    for i in range(max(args.warmup, len(dev_batches))):
         train_step(model, opt, dev_batches[i % len(dev_batches)])
     sampler = ClockSampler(local) if rank == 0 else None
     ops.Profile.reset()

@@ -26,6 +26,7 @@ SIGNATURES = {
     "b2m_cast_pad_bf16": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P]),
     "b2m_packed_weight_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "b2m_pack_weights": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "b2m_pack_weights_batched": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, _P]),
     "b2m_map_pitch": (c_int64, [c_int64]),
     "b2m_kernel_map_sort_workspace_bytes": (c_size_t, [c_int64]),
     "b2m_kernel_map_sort": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P, _P, _P, c_size_t, _P]),

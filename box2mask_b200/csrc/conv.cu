@@ -60,15 +60,14 @@ __host__ __device__ inline int conv_nfull(int c_red) {
   return c_red / 64 + (((c_red % 64) == 16 || (c_red % 64) == 48) ? 1 : 0);
 }
 
-__global__ void pack_weights_kernel(const float* __restrict__ w, int kvol, int c_in, int c_out, int mode,
-                                    uint16_t* __restrict__ packed) {
+// one 16-byte group (8 bf16) of the packed image of one kernel; c_in_src <= c_in: input channels >= c_in_src are zero
+// (the 6-channel network input padded to 8)
+__device__ __forceinline__ void pack_group(const float* __restrict__ w, int kvol, int c_in_src, int c_in, int c_out, int mode,
+                                           uint16_t* __restrict__ packed, int64_t gid) {
   const int c_red = (mode == 0) ? c_in : c_out;
   const int c_n = (mode == 0) ? c_out : c_in;
   const int kpack = conv_kpack(c_red), nfull = conv_nfull(c_red), rem = conv_rem(c_red);
-  const int nkg = (kvol + kpack - 1) / kpack;
   const int64_t groups_kg = (int64_t)c_n * (nfull * 8 + rem * 4);  // 16-byte groups per offset group
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= groups_kg * nkg) return;
   const int kg = (int)(gid / groups_kg);
   int64_t r = gid % groups_kg;
   int n, g, chunk;
@@ -92,12 +91,35 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int kvol, int c
     float f = 0.f;
     if (k < kvol && ch < c_red) {
       const int ksrc = (mode == 1) ? (kvol - 1 - k) : k;
-      f = (mode == 0) ? w[((int64_t)ksrc * c_in + ch) * c_out + n] : w[((int64_t)ksrc * c_in + n) * c_out + ch];
+      const int ci = (mode == 0) ? ch : n, co = (mode == 0) ? n : ch;
+      if (ci < c_in_src) f = w[((int64_t)ksrc * c_in_src + ci) * c_out + co];
     }
     v[e] = __float2bfloat16_rn(f);
   }
   // threads write consecutive 16-byte groups: the packed image is exactly gid * 16 bytes in
   *reinterpret_cast<uint4*>(packed + gid * 8) = *reinterpret_cast<const uint4*>(v);
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, int kvol, int c_in, int c_out, int mode,
+                                    uint16_t* __restrict__ packed, int64_t total) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid < total) pack_group(w, kvol, c_in, c_in, c_out, mode, packed, gid);
+}
+
+// All kernels of a network in one launch. Job j: src[j] fp32 [kvol, c_in_src, c_out] -> dst[j]; meta[j] = {kvol,
+// c_in_src, c_in, c_out, mode}; prefix[j] = first global 16-byte group of job j (prefix[n_jobs] = total).
+__global__ void pack_weights_batched_kernel(const float* const* __restrict__ src, uint16_t* const* __restrict__ dst,
+                                            const int32_t* __restrict__ meta, const int64_t* __restrict__ prefix,
+                                            int n_jobs) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= prefix[n_jobs]) return;
+  int lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {                      // last job whose prefix <= gid
+    const int mid = (lo + hi + 1) >> 1;
+    if (prefix[mid] <= gid) lo = mid; else hi = mid - 1;
+  }
+  const int32_t* m = meta + 5 * lo;
+  pack_group(src[lo], m[0], m[1], m[2], m[3], m[4], dst[lo], gid - prefix[lo]);
 }
 
 __device__ __forceinline__ void st_shared_zero16(uint32_t addr) {
@@ -947,7 +969,18 @@ extern "C" int b2m_pack_weights(const float* kernel, int32_t kvol, int32_t c_in,
   const int c_n = (mode == 0) ? c_out : c_in;
   if (c_n % 8 != 0 || (c_red % 16 != 0 && c_red != 8)) return B2M_ERR_UNSUPPORTED_SHAPE;
   const int64_t total = (int64_t)(b2m_packed_weight_bytes(kvol, c_in, c_out, mode) / 16);
-  pack_weights_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(kernel, kvol, c_in, c_out, mode, packed);
+  pack_weights_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(kernel, kvol, c_in, c_out, mode, packed, total);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" int b2m_pack_weights_batched(const float* const* kernels, uint16_t* const* packed, const int32_t* meta,
+                                        const int64_t* group_prefix, int32_t n_jobs, int64_t total_groups,
+                                        b2m_stream_t stream) {
+  if (n_jobs == 0) return B2M_OK;
+  if (!kernels || !packed || !meta || !group_prefix || n_jobs < 0 || total_groups < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (total_groups == 0) return B2M_OK;
+  pack_weights_batched_kernel<<<cdiv(total_groups, 256), 256, 0, (cudaStream_t)stream>>>(kernels, packed, meta, group_prefix, n_jobs);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }

@@ -19,20 +19,24 @@ class SparseConvFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, kernel, nbr_fwd, nbr_bwd, dgrad_mode, n_out, c_in_real):
+    def forward(ctx, x, kernel, nbr_fwd, nbr_bwd, dgrad_mode, n_out, c_in_real, prepacked=None):
+        """prepacked: optional (forward image, dgrad image) of `kernel` from an ops.WeightPacker run of this step."""
         kvol = 1 if kernel.dim() == 2 else kernel.shape[0]
         c_out = kernel.shape[-1]
-        w = kernel.detach()
-        if w.shape[-2] != x.shape[1]:  # first conv: input channels zero-padded to a multiple of 16
-            pad = x.shape[1] - w.shape[-2]
-            w = torch.nn.functional.pad(w, (0, 0, 0, pad))
-        w = w.contiguous()
-        packed = ops.pack_weights(w, 0)
-        colsum = torch.zeros(2 * c_out, dtype=torch.float64, device=x.device)
+        if prepacked is not None:
+            packed = prepacked[0]
+        else:
+            w = kernel.detach()
+            if w.shape[-2] != x.shape[1]:  # first conv: input channels zero-padded to the bf16 input width
+                pad = x.shape[1] - w.shape[-2]
+                w = torch.nn.functional.pad(w, (0, 0, 0, pad))
+            packed = ops.pack_weights(w.contiguous(), 0)
+        colsum = ops.ZeroArena.take(2 * c_out, x.device)
         y = ops.conv_forward(x, nbr_fwd, packed, kvol, n_out, c_out, colsum)
         ctx.save_for_backward(x, kernel)
         ctx.nbr_fwd, ctx.nbr_bwd, ctx.dgrad_mode, ctx.n_out, ctx.kvol = nbr_fwd, nbr_bwd, dgrad_mode, n_out, kvol
         ctx.c_in_real = c_in_real
+        ctx.packed_t = prepacked[1] if prepacked is not None else None
         ctx.mark_non_differentiable(colsum)
         return y, colsum
 
@@ -42,15 +46,16 @@ class SparseConvFn(torch.autograd.Function):
         dy = dy.contiguous()
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            w = kernel.detach().contiguous()
-            packed_t = ops.pack_weights(w, ctx.dgrad_mode)
+            packed_t = ctx.packed_t
+            if packed_t is None:
+                packed_t = ops.pack_weights(kernel.detach().contiguous(), ctx.dgrad_mode)
             dx = ops.conv_forward(dy, ctx.nbr_bwd, packed_t, ctx.kvol, x.shape[0], x.shape[1])
         if ctx.needs_input_grad[1]:
             dw = ops.conv_wgrad(x, dy, ctx.nbr_fwd, ctx.kvol, ctx.n_out)
             if dw.shape[1] != ctx.c_in_real:
                 dw = dw[:, :ctx.c_in_real, :]
             dw = dw.reshape(kernel.shape).contiguous()
-        return dx, dw, None, None, None, None, None
+        return dx, dw, None, None, None, None, None, None
 
 
 class BatchNormFn(torch.autograd.Function):

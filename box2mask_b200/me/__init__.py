@@ -12,7 +12,7 @@ CUDA context (utils.batched_coordinates runs inside DataLoader worker processes,
 from .sparse_tensor import CoordinateManager, SparseTensor, TensorField, cat  # noqa: F401
 from .nn import (  # noqa: F401
     MinkowskiBatchNorm, MinkowskiConvolution, MinkowskiConvolutionTranspose, MinkowskiGlobalAvgPooling,
-    MinkowskiGlobalMaxPooling, MinkowskiReLU, MinkowskiSyncBatchNorm, conv_bn_act,
+    MinkowskiGlobalMaxPooling, MinkowskiReLU, MinkowskiSyncBatchNorm, conv_bn_act, prepack_conv_weights,
 )
 from . import utils  # noqa: F401
 from . import modules  # noqa: F401

@@ -106,12 +106,18 @@ class _ConvBase(nn.Module):
             raise TypeError("features must be float32 or bfloat16")
         if feats.shape[1] % 16 != 0 and feats.shape[1] != 8:
             raise NotImplementedError("bf16 feature width must be 8 or a multiple of 16")
-        y, colsum = Fn.SparseConvFn.apply(feats.contiguous(), self.kernel, nbr_fwd, nbr_bwd, mode, n_out, self.in_channels)
+        # images packed for this step by prepack_conv_weights (one launch for the whole network), if still current
+        pre = getattr(self, "_prepacked", None)
+        if pre is not None and (pre[2] != self.kernel._version or pre[3] != feats.shape[1] or pre[4] != mode):
+            pre = None
+        y, colsum = Fn.SparseConvFn.apply(feats.contiguous(), self.kernel, nbr_fwd, nbr_bwd, mode, n_out, self.in_channels,
+                                          pre)
         out = x._like(y, out_stride)
         if self.bias is not None:
             out._F = y + self.bias.to(y.dtype)
         else:
             out._colsum = colsum
+            out._colsum_gen = ops.ZeroArena.generation(y.device)
         return out
 
 
@@ -167,7 +173,10 @@ def _bn_act(mod, x, residual=None, relu=False):
     if getattr(mod, "process_group", None) is not None and training and torch.distributed.is_initialized():
         group = mod.process_group
     res = residual.F.contiguous() if residual is not None else None
-    out = Fn.BatchNormFn.apply(feats.contiguous(), x._colsum if training else None, bn.weight, bn.bias, bn.running_mean,
+    colsum = x._colsum if training else None
+    if colsum is not None and getattr(x, "_colsum_gen", -1) != ops.ZeroArena.generation(feats.device):
+        colsum = None      # the scratch arena was recycled since the convolution ran: recompute the statistics
+    out = Fn.BatchNormFn.apply(feats.contiguous(), colsum, bn.weight, bn.bias, bn.running_mean,
                                bn.running_var, momentum, bn.eps, training, res, relu, group)
     return x._like(out)
 
@@ -229,6 +238,37 @@ class MinkowskiGlobalAvgPooling(_GlobalPool):
 
 class MinkowskiGlobalMaxPooling(_GlobalPool):
     mode = "max"
+
+
+def _dgrad_mode(conv):
+    """Weight packing of the dgrad operand: 1 = mirrored offsets on the same coordinates (stride-1 k3/k5),
+    2 = plain transpose (1x1, strided and transposed convolutions) — what _ConvBase._maps returns."""
+    return 1 if (not conv.is_transpose and conv.stride == 1 and conv.kernel_size in (3, 5)) else 2
+
+
+def prepack_conv_weights(module):
+    """Pack the forward and dgrad weight images of every bf16-path convolution under `module` in one launch and
+    attach them to the modules (used by their next forward/backward as long as the kernel is not modified).
+    Call once per step before the forward pass; convolutions called without it pack their own weights."""
+    state = module.__dict__.get("_b2m_packer")
+    convs = state[0] if state is not None else None
+    if state is None or state[1].stale():
+        convs = [m for m in module.modules() if isinstance(m, _ConvBase) and m.kernel.is_cuda and not (
+            m.kernel_volume == 1 and m.stride == 1 and (m.bias is not None or m.out_channels % 16 != 0))]
+        if not convs:
+            return
+        jobs = []
+        for m in convs:
+            c_in = _round16(m.in_channels)
+            jobs.append((m.kernel.detach(), c_in, 0))
+            jobs.append((m.kernel.detach(), c_in, _dgrad_mode(m)))
+        state = (convs, ops.WeightPacker(jobs, convs[0].kernel.device))
+        module.__dict__["_b2m_packer"] = state
+    packer = state[1]
+    packer.run()
+    for i, m in enumerate(convs):
+        m.__dict__["_prepacked"] = (packer.buffers[2 * i], packer.buffers[2 * i + 1], m.kernel._version,
+                                    _round16(m.in_channels), _dgrad_mode(m))
 
 
 def conv_bn_act(conv, norm, x, residual=None, relu=True):

@@ -45,6 +45,36 @@ def _run(kind, n_kernels, call, flops=None, nbytes=None, tag=""):
     return r
 
 
+class ZeroArena:
+    """Zeroed fp64 scratch for the per-layer statistics (conv epilogue column sums, BatchNorm backward reductions):
+    slices of one pre-zeroed buffer per device instead of one fill kernel per layer (243 per training step).
+    A slice is consumed by the kernels launched right after it is taken; when the buffer is used up it is zeroed
+    again in stream order and `generation` advances, which invalidates column sums still attached to a tensor."""
+    SIZE = 1 << 19      # doubles (4 MB)
+    _state = {}         # device -> [buffer, next offset, generation]
+
+    @classmethod
+    def take(cls, n, device):
+        device = torch.device(device)
+        st = cls._state.get(device)
+        n_al = (int(n) + 31) // 32 * 32
+        if st is None:
+            st = [torch.zeros(cls.SIZE, dtype=torch.float64, device=device), 0, 0]
+            cls._state[device] = st
+        elif st[1] + n_al > cls.SIZE:
+            st[0].zero_()
+            st[1] = 0
+            st[2] += 1
+        out = st[0][st[1]:st[1] + n]
+        st[1] += n_al
+        return out
+
+    @classmethod
+    def generation(cls, device):
+        st = cls._state.get(torch.device(device))
+        return st[2] if st is not None else 0
+
+
 def _cuda(t, dtype=None, name="tensor"):
     if not t.is_cuda:
         raise _lib.B2MError("%s must be a CUDA tensor (no CPU fallback in the product path)" % name)
@@ -218,6 +248,42 @@ def pack_weights(kernel, mode):
     return packed
 
 
+class WeightPacker:
+    """Packs the kernels of many convolutions in ONE launch (b2m_pack_weights_batched). jobs: list of
+    (kernel f32 [K, c_in_src, c_out] or [c_in_src, c_out], c_in (>= c_in_src, the padded bf16 input width), mode);
+    buffers[i] is the packed image of job i, refreshed by run()."""
+
+    def __init__(self, jobs, device):
+        lib = _lib_or_raise()
+        self.kernels = [j[0] for j in jobs]
+        self.buffers, meta, prefix = [], [], [0]
+        for kernel, c_in, mode in jobs:
+            _cuda(kernel, torch.float32, "kernel")
+            kvol = 1 if kernel.dim() == 2 else kernel.shape[0]
+            c_in_src, c_out = kernel.shape[-2], kernel.shape[-1]
+            nbytes = lib.b2m_packed_weight_bytes(kvol, c_in, c_out, mode)
+            self.buffers.append(torch.empty(nbytes, dtype=torch.uint8, device=device))
+            meta.append([kvol, c_in_src, c_in, c_out, mode])
+            prefix.append(prefix[-1] + nbytes // 16)
+        self.total = prefix[-1]
+        self.n = len(jobs)
+        self.ptrs = tuple(k.data_ptr() for k in self.kernels)
+        self.src = torch.tensor(self.ptrs, dtype=torch.int64, device=device)
+        self.dst = torch.tensor([b.data_ptr() for b in self.buffers], dtype=torch.int64, device=device)
+        self.meta = torch.tensor(meta, dtype=torch.int32, device=device)
+        self.prefix = torch.tensor(prefix, dtype=torch.int64, device=device)
+
+    def stale(self):
+        """True when a parameter was re-allocated (e.g. `.to(device)`): the job table must be rebuilt."""
+        return tuple(k.data_ptr() for k in self.kernels) != self.ptrs
+
+    def run(self):
+        lib = _lib_or_raise()
+        _run("pack_weights", 1, lambda: check(lib.b2m_pack_weights_batched(
+            ptr(self.src), ptr(self.dst), ptr(self.meta), ptr(self.prefix), self.n, self.total, stream_ptr()),
+            "pack_weights_batched"), nbytes=sum(k.numel() * 4 for k in self.kernels) + 16 * self.total)
+
+
 def conv_forward(x, kmap, packed_w, kvol, n_out, c_n, colsum=None):
     """y bf16[n_out, c_n] = sum_k x[nbr[k]] @ B[k] over a sorted KernelMap (None = identity, kvol 1);
     colsum f64[2*c_n] (zeroed by the caller) optional."""
@@ -259,7 +325,7 @@ def conv_wgrad(x, dy, kmap, kvol, n_out):
 def colstats(x):
     lib = _lib_or_raise()
     _cuda(x, torch.bfloat16, "x")
-    sums = torch.zeros(2 * x.shape[1], dtype=torch.float64, device=x.device)
+    sums = ZeroArena.take(2 * x.shape[1], x.device)
     _run("colstats", 1, lambda: check(lib.b2m_colstats(ptr(x), x.shape[0], x.shape[1], ptr(sums), stream_ptr()),
                                       "colstats"), nbytes=2 * x.numel())
     return sums
@@ -285,7 +351,7 @@ def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, wan
                 reduce_hook=None):
     lib = _lib_or_raise()
     n, c = x.shape
-    red = torch.zeros(2 * c, dtype=torch.float64, device=x.device)
+    red = ZeroArena.take(2 * c, x.device)
     _run("bn_backward_reduce", 1, lambda: check(lib.b2m_bn_backward_reduce(
         ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd), int(bool(relu)), ptr(red), stream_ptr()),
         "bn_backward_reduce"), nbytes=2 * x.numel() * (3 if relu else 2))

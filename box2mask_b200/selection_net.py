@@ -170,6 +170,7 @@ class SelectionNet(nn.Module):
     def forward(self, x, pooling_ids=None, num_segments=None):
         # all 8 coordinate levels and 16 kernel maps first (the only host syncs of the step), then a sync-free pass
         nlev = len(ENCODER)
+        ME.prepack_conv_weights(self)      # every conv's forward and dgrad weight image, one launch per step
         x.coordinate_manager.prepare(nlev, [(1, self.conv0p1s1.kernel_size)] + [(2 ** l, 3) for l in range(nlev + 1)])
         stem = conv_bn_act(self.conv0p1s1, self.bn0, x, relu=True)
         out, skips = stem, []

@@ -126,6 +126,14 @@ int b2m_cast_pad_bf16(const float* x, int64_t n, int32_t c, int32_t c_pad, uint1
 size_t b2m_packed_weight_bytes(int32_t kvol, int32_t c_in, int32_t c_out, int32_t mode);
 int b2m_pack_weights(const float* kernel, int32_t kvol, int32_t c_in, int32_t c_out, int32_t mode,
                      uint16_t* packed, b2m_stream_t stream);
+/* The same for every convolution of a network in ONE launch (one call per training step instead of one per layer).
+ * All arrays are DEVICE arrays: kernels[j] fp32 [kvol, c_in_src, c_out], packed[j] = destination of
+ * b2m_packed_weight_bytes(kvol, c_in, c_out, mode) bytes, meta int32[n_jobs, 5] = {kvol, c_in_src, c_in, c_out, mode}
+ * (input channels c_in_src..c_in-1 are zero: the 6-channel input padded to 8), group_prefix int64[n_jobs + 1] =
+ * running sum of packed bytes / 16; total_groups = group_prefix[n_jobs]. */
+int b2m_pack_weights_batched(const float* const* kernels, uint16_t* const* packed, const int32_t* meta,
+                             const int64_t* group_prefix, int32_t n_jobs, int64_t total_groups,
+                             b2m_stream_t stream);
 /* y[order[j], :] = sum_k x[nbr[k][j], :] * B[k]   (entries < 0 contribute zero). (nbr, order, group_mask) is a
  * sorted kernel map from b2m_kernel_map_sort; nbr == NULL means the identity map with kvol == 1 (order and
  * group_mask ignored). x bf16[n_in, c_red], y bf16[n_out, c_n]. c_red % 16 == 0, c_n % 16 == 0, c_n <= 512.
