@@ -110,42 +110,16 @@ colreduce_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ ou
   }
 }
 
-// One block per launch computes the per-channel affine (scale, shift), the saved statistics and the
-// running-statistics update; written to a small float workspace that the apply kernel reads.
-__global__ void bn_prepare_kernel(const double* __restrict__ sums, int64_t n, int c, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, float* running_mean, float* running_var,
-                                  float momentum, float eps, int training, float* __restrict__ save_mean,
-                                  float* __restrict__ save_invstd) {
-  for (int j = threadIdx.x; j < c; j += blockDim.x) {
-    float mean, invstd;
-    if (training) {
-      const double m = sums[j] / (double)n;
-      double var = sums[c + j] / (double)n - m * m;
-      if (var < 0.0) var = 0.0;
-      mean = (float)m;
-      invstd = (float)(1.0 / sqrt(var + (double)eps));
-      if (running_mean) running_mean[j] = (1.f - momentum) * running_mean[j] + momentum * mean;
-      if (running_var) {
-        const double unbiased = (n > 1) ? var * (double)n / (double)(n - 1) : var;
-        running_var[j] = (1.f - momentum) * running_var[j] + momentum * (float)unbiased;
-      }
-    } else {
-      mean = running_mean[j];
-      invstd = (float)(1.0 / sqrt((double)running_var[j] + (double)eps));
-    }
-    save_mean[j] = mean;
-    save_invstd[j] = invstd;
-  }
-  (void)gamma; (void)beta;
-}
-
 // Apply kernels: thread (rl, g) owns the 8 columns of group g for rows rl, rl + rows-per-pass, ... so the per-column
 // coefficients live in registers (loaded once) and a warp still reads consecutive 16-byte vectors (row-major rows
 // are contiguous: thread t of a pass reads vector r0 * G + t).
+// Statistics and apply in one launch: every thread derives mean / invstd of its 8 columns from the fp64 column sums
+// (training) or the running statistics (eval); block 0 also writes the saved statistics and updates the running ones.
 __global__ void __launch_bounds__(kNormThreads)
-bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int c, const float* __restrict__ gamma,
-                const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
-                const uint16_t* __restrict__ residual, int relu, uint16_t* __restrict__ out) {
+bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int64_t n_stat, int c, const double* __restrict__ sums,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
+                float momentum, float eps, int training, const uint16_t* __restrict__ residual, int relu,
+                uint16_t* __restrict__ out, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
   const int G = c / 8;
   const int rpp = kNormThreads / G;
   const int g = threadIdx.x % G, rl = threadIdx.x / G;
@@ -154,9 +128,32 @@ bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int c, const float* _
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int j = g * 8 + i;
-    mu[i] = mean[j];
-    sc[i] = gamma[j] * invstd[j];
+    float mean, invstd;
+    double var = 0.0;
+    if (training) {
+      const double m = sums[j] / (double)n_stat;
+      var = sums[c + j] / (double)n_stat - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      invstd = (float)(1.0 / sqrt(var + (double)eps));
+    } else {
+      mean = running_mean[j];
+      invstd = (float)(1.0 / sqrt((double)running_var[j] + (double)eps));
+    }
+    mu[i] = mean;
+    sc[i] = gamma[j] * invstd;
     be[i] = beta[j];
+    if (blockIdx.x == 0 && rl == 0) {          // one writer per column
+      save_mean[j] = mean;
+      save_invstd[j] = invstd;
+      if (training) {
+        if (running_mean) running_mean[j] = (1.f - momentum) * running_mean[j] + momentum * mean;
+        if (running_var) {
+          const double unbiased = (n_stat > 1) ? var * (double)n_stat / (double)(n_stat - 1) : var;
+          running_var[j] = (1.f - momentum) * running_var[j] + momentum * (float)unbiased;
+        }
+      }
+    }
   }
   constexpr int U = 4;  // independent rows (16-byte loads) in flight per thread
   const int64_t rstep = (int64_t)gridDim.x * rpp;
@@ -311,11 +308,11 @@ extern "C" int b2m_bn_forward(const uint16_t* x, int64_t n, int64_t n_stat, int3
   if (!norm_shape_ok(c)) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n == 0) return B2M_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  bn_prepare_kernel<<<1, 256, 0, st>>>(sums, n_stat, c, gamma, beta, running_mean, running_var, momentum, eps, training,
-                                      save_mean, save_invstd);
-  B2M_CHECK_LAUNCH();
-  bn_apply_kernel<<<apply_grid(n, c), kNormThreads, 0, st>>>(x, n, c, gamma, beta, save_mean, save_invstd,
-                                                                   residual, relu, out);
+  // Running statistics are updated by block 0 while the other blocks may still read them in eval mode only, where they
+  // are not written; in training mode the normalisation uses the batch sums, so there is no read/write hazard.
+  bn_apply_kernel<<<apply_grid(n, c), kNormThreads, 0, st>>>(x, n, n_stat, c, sums, gamma, beta, running_mean, running_var,
+                                                            momentum, eps, training, residual, relu, out, save_mean,
+                                                            save_invstd);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }

@@ -18,9 +18,13 @@ def NMS_clustering(boxes, cluster_th=0.5, get_heatmaps=True):
     assert 0 < cluster_th < 1
     boxes = boxes.contiguous().float()
     reps, cluster_of, heat = ops.aabb_nms(boxes, cluster_th, want_heatmaps=get_heatmaps)
+    # members of each cluster in descending-score order: one stable sort by cluster id of the score-ordered boxes
+    # and one split (a single host sync for the K sizes) instead of K boolean-mask selections
     order = torch.argsort(-boxes[:, 0], stable=True)
-    sorted_cluster = cluster_of[order]
-    clusters = [order[sorted_cluster == c] for c in range(len(reps))]
+    sorted_cluster = cluster_of[order].long()
+    by_cluster = order[torch.argsort(sorted_cluster, stable=True)]
+    sizes = torch.bincount(sorted_cluster, minlength=len(reps)).tolist()
+    clusters = list(torch.split(by_cluster, sizes))
     if get_heatmaps:
         return reps, clusters, heat
     return reps, clusters

@@ -339,7 +339,7 @@ def bn_forward(x, sums, gamma, beta, running_mean, running_var, momentum, eps, t
     out = torch.empty_like(x)
     save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
     save_invstd = torch.empty(c, dtype=torch.float32, device=x.device)
-    _run("bn_forward", 2, lambda: check(lib.b2m_bn_forward(
+    _run("bn_forward", 1, lambda: check(lib.b2m_bn_forward(
         ptr(x), n, n if n_stat is None else int(n_stat), c, ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean),
         ptr(running_var), float(momentum), float(eps), int(bool(training)), ptr(residual), int(bool(relu)), ptr(out),
         ptr(save_mean), ptr(save_invstd), stream_ptr()), "bn_forward"),
