@@ -162,6 +162,12 @@ constexpr int kTileM = 128;
 constexpr int kStagePitch = 33;
 constexpr int kASlotBytes = kTileM * 128;
 
+#ifdef B2M_DEBUG_BUILD
+#define B2M_ABLATE(a, bit) (((a).ablate >> (bit)) & 1)
+#else
+#define B2M_ABLATE(a, bit) 0
+#endif
+
 struct FwdArgs {
   const uint16_t* x; const int32_t* nbr; const int32_t* order; const uint32_t* gmask; const uint8_t* w;
   uint16_t* y; double* colsum;
@@ -169,6 +175,7 @@ struct FwdArgs {
   int c_red, kvol, c_n, ntile, T, kpack, nkg, nfull, rem, wa, mwords, colstride, n_tiles, n_work;
   int a_slots, b_slots, b_bytes, kg_bytes;
   int off_b, off_stage, off_csum, off_bars, tmem_cols;
+  int ablate;   // debug builds (B2M_ABLATE env): 1 = no A gathers, 2 = no MMAs, 4 = no epilogue stores, 8 = no B copies
 };
 
 __device__ __forceinline__ MaskBits fwd_tile_mask(const FwdArgs& a, int tile) {
@@ -282,7 +289,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0u;
           }
-          if (a.colsum != nullptr) {
+          if (a.colsum != nullptr && !B2M_ABLATE(a, 2)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j < cw) st_shared_f32(stage_a + (lane * kStagePitch + j) * 4, __uint_as_float(v[j]));
@@ -299,7 +306,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
               red_shared_f64(csum_a + (a.ntile + cc * 32 + lane) * 8, (double)s2);
             }
           }
-          if (orow >= 0) {
+          if (orow >= 0 && !B2M_ABLATE(a, 2)) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (q * 8 < cw) {
@@ -369,7 +376,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                 if (KPACK == 1) {
                   const bool full_chunk = c < a.nfull;
                   const int nks = full_chunk ? min(4, (a.c_red - c * 64) >> 4) : 2;
-                  if (nks == 4) {                        // the common case, straight-line: +32 bytes per K=16 step
+                  if (B2M_ABLATE(a, 1)) {
+                  } else if (nks == 4) {                        // the common case, straight-line: +32 bytes per K=16 step
                     umma_bf16_lohi(d, a_lo, hi128, b_lo, hi128, idesc, acc);
                     umma_bf16_lohi(d, a_lo + 2, hi128, b_lo + 2, hi128, idesc, 1u);
                     umma_bf16_lohi(d, a_lo + 4, hi128, b_lo + 4, hi128, idesc, 1u);
@@ -438,8 +446,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
             const int wb = (c < a.nfull) ? 128 : 64;
             const uint32_t bytes = (uint32_t)(a.ntile * wb);
             const uint8_t* src = a.w + (int64_t)kg * a.kg_bytes + (int64_t)min(c, a.nfull) * a.c_n * 128 + (int64_t)n0 * wb;
-            mbar_arrive_expect_tx(b_full + 8 * rb.slot, bytes);
-            bulk_g2s(b_s, src, bytes, b_full + 8 * rb.slot);
+            if (B2M_ABLATE(a, 3)) {
+              mbar_arrive(b_full + 8 * rb.slot);
+            } else {
+              mbar_arrive_expect_tx(b_full + 8 * rb.slot, bytes);
+              bulk_g2s(b_s, src, bytes, b_full + 8 * rb.slot);
+            }
           }
           rb.next();
         }
@@ -465,7 +477,81 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     Ring ra;
     ra.init(SAr);
     int turn = 0;  // stage counter modulo np
-    for (int w = (p < np && pw < groups * a.T) ? blockIdx.x : a.n_work; w < a.n_work; w += gridDim.x) {   // spare warps have no stages
+    const bool has_work = (p < np && pw < groups * a.T);   // spare warps have no stages
+    if (KPACK == 1) {
+      // 64-wide-chunk mode, software-pipelined: the index quad of this warp's NEXT stage is loaded before the current
+      // stage waits for its slot, so the ~1 us index-load latency is off the slot's turn-around path (with every unit
+      // of real work removed the kernel was still bound by that loop: ablation in DESIGN.md section 3).
+      struct St { int w, kg, c, slot; uint32_t phase; bool valid; };
+      int w = has_work ? (int)blockIdx.x : a.n_work;
+      MaskBits mt = mask_zero();
+      int kg = a.nkg, d = 0;
+      Ring ra0 = ra;
+      bool fresh = true;                 // work item w not entered yet
+      auto next = [&]() -> St {
+        St s; s.valid = false; s.w = 0; s.kg = 0; s.c = 0; s.slot = 0; s.phase = 0;
+        while (w < a.n_work) {
+          if (fresh) {
+            mt = fwd_tile_mask(a, w * a.T + t);
+            kg = next_group<1>(mt, 0, a.nkg, a.mwords);
+            d = p - turn; if (d < 0) d += np;
+            fresh = false;
+          }
+          if (kg < a.nkg) {
+            if (d < nch) {
+              const Ring rs = ra0.at(d);
+              s.valid = true; s.w = w; s.kg = kg; s.c = d; s.slot = abase + rs.slot; s.phase = rs.phase;
+              d += np;
+              return s;
+            }
+            ra0 = ra0.at(nch);
+            turn += nch; while (turn >= np) turn -= np;
+            kg = next_group<1>(mt, kg + 1, a.nkg, a.mwords);
+            d = p - turn; if (d < 0) d += np;
+            continue;
+          }
+          w += gridDim.x;
+          fresh = true;
+        }
+        return s;
+      };
+      const int quad = q_lo + lane;                         // this lane gathers rows 4*quad .. 4*quad+3 of the tile
+      const bool on = quad < q_hi;
+      auto load_idx = [&](const St& s) -> int4 {
+        int4 idx = make_int4(-1, -1, -1, -1);
+        if (s.valid && on) {
+          const int64_t pos0 = (int64_t)(s.w * a.T + t) * kTileM + 4 * quad;
+          if (a.nbr) {
+            idx = ld_nc_int4(a.nbr + (int64_t)s.kg * a.n_pitch + pos0);
+          } else {
+            idx.x = pos0 < a.n_out ? (int)pos0 : -1;
+            idx.y = pos0 + 1 < a.n_out ? (int)pos0 + 1 : -1;
+            idx.z = pos0 + 2 < a.n_out ? (int)pos0 + 2 : -1;
+            idx.w = pos0 + 3 < a.n_out ? (int)pos0 + 3 : -1;
+          }
+        }
+        return idx;
+      };
+      St cur = next();
+      int4 idx = load_idx(cur);
+      while (cur.valid) {
+        const St nxt = next();
+        const int4 idx_next = load_idx(nxt);               // in flight while this stage waits for its slot
+        const uint32_t a_s = smem_base + cur.slot * kASlotBytes;
+        const uint32_t full = a_full + 8 * cur.slot;
+        const uint32_t wc = (cur.c < a.nfull) ? 128u : 64u;
+        mbar_wait(a_empty + 8 * cur.slot, cur.phase ^ 1u, 10);
+        if (lane == 0) {
+          if (B2M_ABLATE(a, 0)) mbar_arrive(full); else mbar_arrive_expect_tx(full, (uint32_t)(q_hi - q_lo) * 4u * wc);
+        }
+        __syncwarp();
+        if (on && !B2M_ABLATE(a, 0))
+          tma_gather4(a_s + quad * 4 * wc, (cur.c < a.nfull) ? &tm_main : &tm_rem, full, cur.c * 64, idx.x, idx.y, idx.z, idx.w);
+        cur = nxt;
+        idx = idx_next;
+      }
+    } else
+    for (int w = has_work ? (int)blockIdx.x : a.n_work; w < a.n_work; w += gridDim.x) {
       const MaskBits mt = fwd_tile_mask(a, w * a.T + t);
       for (int kg = next_group<KPACK>(mt, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mt, kg + 1, a.nkg, a.mwords)) {
         const uint32_t sub = mask_bits(mt, kg * KPACK, KPACK);
@@ -498,9 +584,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                 }
                 const uint32_t wc = (c < a.nfull) ? 128u : 64u;
                 mbar_wait(a_empty + 8 * aslot, rs.phase ^ 1u, 10);
-                if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(q_hi - q_lo) * 4u * wc);
+                if (lane == 0) {
+                  if (B2M_ABLATE(a, 0)) mbar_arrive(full); else mbar_arrive_expect_tx(full, (uint32_t)(q_hi - q_lo) * 4u * wc);
+                }
                 __syncwarp();
-                if (on) tma_gather4(a_s + quad * 4 * wc, (c < a.nfull) ? &tm_main : &tm_rem, full, c * 64, idx.x, idx.y, idx.z, idx.w);
+                if (on && !B2M_ABLATE(a, 0)) tma_gather4(a_s + quad * 4 * wc, (c < a.nfull) ? &tm_main : &tm_rem, full, c * 64, idx.x, idx.y, idx.z, idx.w);
               } else if (KPACK == 8) {
                 // cp.async path: lane = (offset j of the group, row quad rq); 8 x (one 16-byte index load + 4 copies)
                 const int j = lane & 7, rq = lane >> 3;
@@ -1037,6 +1125,10 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   a.off_bars = (a.off_csum + csum_bytes + 15) / 16 * 16;
   a.tmem_cols = pow2_cols(2 * a.T * a.colstride);
   if (a.tmem_cols > 512) return B2M_ERR_UNSUPPORTED_SHAPE;
+  a.ablate = 0;
+#ifdef B2M_DEBUG_BUILD
+  if (const char* e = getenv("B2M_ABLATE")) a.ablate = atoi(e);
+#endif
   const int smem_bytes = a.off_bars + 16 * a.a_slots + 16 * a.b_slots + 64 + 1024;
   if (smem_bytes > 227 * 1024) return B2M_ERR_UNSUPPORTED_SHAPE;
   CUtensorMap tm_main, tm_rem;
