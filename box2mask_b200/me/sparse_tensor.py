@@ -48,17 +48,52 @@ class CoordinateManager:
         return self.stride2[fine_stride]
 
 
-    def prepare(self, n_strided, sub_kernels):
+    def prepare(self, n_strided, sub_kernels, stream=None):
         """Build every coordinate level and kernel map a network will ask for, up front. Each strided level costs
-        one host sync (its row count); doing them back to back on an otherwise empty stream keeps those waits
-        short and leaves the forward / backward passes free of host syncs, so the host runs ahead of the GPU.
-        n_strided: number of stride-2 levels below the input; sub_kernels: iterable of (tensor_stride, kernel_size)."""
+        one host sync (its row count); doing them back to back keeps those waits short and leaves the forward /
+        backward passes free of host syncs, so the host runs ahead of the GPU.
+        n_strided: number of stride-2 levels below the input; sub_kernels: iterable of (tensor_stride, kernel_size).
+
+        stream: build on this (side) CUDA stream instead of the current one — used to construct the maps of the NEXT
+        batch while the GPU is still busy with the current step. The consumer calls wait_ready() on its own stream."""
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                self.prepare(n_strided, sub_kernels)
+                self._ready = torch.cuda.Event()
+                self._ready.record(stream)
+            self._side_stream = stream
+            return
         s = 1
         for _ in range(int(n_strided)):
             self.stride2_maps(s)
             s *= 2
         for stride, ksize in sub_kernels:
             self.submanifold_map(int(stride), int(ksize))
+
+    def _tensors(self):
+        for t in self.levels.values():
+            yield t
+        for tb in self.tables.values():
+            yield tb.keys
+            yield tb.vals
+            yield tb.status
+        maps = list(self.sub_maps.values()) + [m for pair in self.stride2.values() for m in pair]
+        for m in maps:
+            for t in (m.nbr, m.order, m.gmask, m.raw):
+                if t is not None:
+                    yield t
+
+    def wait_ready(self):
+        """After a side-stream prepare(): make the current stream wait for the maps and tell the caching allocator
+        that they are used on it (they were allocated from the side stream's pool). No-op otherwise."""
+        ev = getattr(self, "_ready", None)
+        if ev is None:
+            return
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for t in self._tensors():
+            t.record_stream(cur)
+        self._ready = None
 
 
 class SparseTensor:

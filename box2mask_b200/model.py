@@ -48,9 +48,32 @@ class Model:
     def compute_loss(self, batch, epoch):
         return self.compute_loss_detection(batch, epoch)[0]
 
+    def prefetch_coordinates(self, batch):
+        """Optional: build the coordinate levels and kernel maps of `batch` on a side stream NOW (typically right after
+        the previous step was enqueued, so that the integer map construction overlaps its backward pass). The batch
+        keeps the result under "_coordinate_manager"; compute_loss_detection / get_prediction pick it up. Purely an
+        overlap of work that would otherwise run at the start of the step; results are identical."""
+        dev = torch.device(self.device)
+        if not hasattr(self, "_side_stream"):
+            self._side_stream = torch.cuda.Stream(device=dev)
+        side = self._side_stream
+        side.wait_stream(torch.cuda.current_stream(dev))     # the coordinates may have been produced on the main stream
+        with torch.cuda.stream(side):
+            coords = batch["vox_coords"].to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+        cm = ME.CoordinateManager(coords)
+        cm.prepare(*self.net.coordinate_plan(), stream=side)
+        batch["_coordinate_manager"] = cm
+        return batch
+
+    def _input_tensor(self, batch):
+        cm = batch.pop("_coordinate_manager", None) if isinstance(batch, dict) else None
+        if cm is not None:
+            return ME.SparseTensor(batch["vox_features"].to(self.device), coordinate_manager=cm)
+        return ME.SparseTensor(batch["vox_features"], batch["vox_coords"], device=self.device)
+
     def compute_loss_detection(self, batch, epoch):
         cfg, dev = self.cfg, self.device
-        sin = ME.SparseTensor(batch["vox_features"], batch["vox_coords"], device=dev)
+        sin = self._input_tensor(batch)
         pred = self.detection_model(sin, batch["pooling_ids"].to(dev), batch.get("num_segments"))
         pred = {k: v.F.float() for k, v in pred.items()}
         losses = {"optimization_loss": 0}

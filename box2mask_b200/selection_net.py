@@ -166,12 +166,17 @@ class SelectionNet(nn.Module):
                 nn.init.constant_(m.bn.weight, 1)
                 nn.init.constant_(m.bn.bias, 0)
 
+    def coordinate_plan(self):
+        """(number of stride-2 levels, [(tensor_stride, kernel_size) of every stride-1 map]) this network asks for."""
+        nlev = len(ENCODER)
+        return nlev, [(1, self.conv0p1s1.kernel_size)] + [(2 ** l, 3) for l in range(nlev + 1)]
+
     # -- forward ----------------------------------------------------------------------------------
     def forward(self, x, pooling_ids=None, num_segments=None):
         # all 8 coordinate levels and 16 kernel maps first (the only host syncs of the step), then a sync-free pass
-        nlev = len(ENCODER)
         ME.prepack_conv_weights(self)      # every conv's forward and dgrad weight image, one launch per step
-        x.coordinate_manager.prepare(nlev, [(1, self.conv0p1s1.kernel_size)] + [(2 ** l, 3) for l in range(nlev + 1)])
+        x.coordinate_manager.wait_ready()  # maps prefetched on a side stream (Model.prefetch_coordinates), if any
+        x.coordinate_manager.prepare(*self.coordinate_plan())   # no-op for levels / maps that already exist
         stem = conv_bn_act(self.conv0p1s1, self.bn0, x, relu=True)
         out, skips = stem, []
         for conv, bn, block, _ in ENCODER:
