@@ -109,11 +109,11 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model(device, multigpu):
+def build_model(device, multigpu, grad_sync="flat"):
     from box2mask_b200.model import Model
     from box2mask_b200.selection_net import default_config
     from box2mask_b200.synthetic import label_maps
-    cfg = default_config(multigpu=multigpu, mlp_bb_scores_start_epoch=0)
+    cfg = default_config(multigpu=multigpu, mlp_bb_scores_start_epoch=0, grad_sync=grad_sync)
     valid, id2idx, is_fg = label_maps(20)
     torch.manual_seed(0)
     model = Model(cfg, valid, id2idx, None, is_fg, device=device)
@@ -188,6 +188,9 @@ def main():
     ap.add_argument("--scale", type=float, default=SCENE_SCALE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-bn", action="store_true")
+    ap.add_argument("--grad-sync", default="flat", choices=["flat", "ddp"],
+                    help="flat: one all-reduce of the flat gradient buffer after backward (box2mask_b200/grad_sync.py); "
+                         "ddp: torch DistributedDataParallel buckets overlapped with backward")
     ap.add_argument("--prefetch", action="store_true",
                     help="build the coordinate maps one step ahead on a side stream (Model.prefetch_coordinates); measured "
                          "slower than building them inside the step: the persistent conv kernels leave the side stream no SMs")
@@ -198,7 +201,7 @@ def main():
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
+    if world > 1 and args.grad_sync == "ddp":
         # leave SMs for the NCCL all-reduce kernels that overlap the backward pass (persistent conv kernels otherwise
         # hold every SM and the collective forces a second wave of their CTAs)
         os.environ.setdefault("B2M_MAX_CTAS", "132")
@@ -213,7 +216,7 @@ def main():
 
     scenes = make_scenes(args.scenes, seed=10 + rank, scale=args.scale)
     rng = np.random.default_rng(rank)
-    model, opt, cfg = build_model(dev, multigpu=world > 1)
+    model, opt, cfg = build_model(dev, multigpu=world > 1, grad_sync=args.grad_sync)
     if world > 1 and not args.sync_bn:
         for m in model.net.modules():      # per-rank BatchNorm statistics unless --sync-bn
             if hasattr(m, "process_group"):
@@ -321,6 +324,7 @@ def main():
                                "hash + 16 kernel maps + fwd + box-vote losses + bwd + Adam" % (args.scenes, voxels),
                    "scenes_per_gpu": args.scenes, "voxels_per_gpu": voxels, "parallelism": "dp%d" % world,
                    "sync_bn": bool(args.sync_bn and world > 1),
+                   "grad_sync": (args.grad_sync if world > 1 else None),
                    "coordinate_maps": "built one step ahead on a side stream" if args.prefetch else "built inside the step",
                    "cache": "inputs larger than L2: every full-resolution activation is >= 235 MB (L2 is 126 MB) and "
                             "every step runs on freshly translated coordinates, so all 16 kernel maps are rebuilt"},

@@ -37,9 +37,17 @@ class Model:
         self.detection_model = SelectionNet(cfg, device, semantic_valid_class_ids, is_foreground,
                                             out_channels=[96, 96, 6]).to(device)
         self.net = self.detection_model   # the un-wrapped network (state-dict owner)
+        self.grad_sync = None
         if cfg.multigpu:
-            self.detection_model = torch.nn.parallel.DistributedDataParallel(
-                self.detection_model, device_ids=[torch.device(device).index], gradient_as_bucket_view=True)
+            # models/model.py:23-25: gradient averaging over the scene-sharded ranks + SyncBatchNorm. The default is one
+            # flat all-reduce after backward (grad_sync.py: overlapping NCCL with the persistent conv kernels costs more
+            # than the sub-millisecond collective); cfg.grad_sync = "ddp" keeps torch's bucketed, overlapped DDP.
+            if getattr(cfg, "grad_sync", "flat") == "ddp":
+                self.detection_model = torch.nn.parallel.DistributedDataParallel(
+                    self.detection_model, device_ids=[torch.device(device).index], gradient_as_bucket_view=True)
+            else:
+                from .grad_sync import FlatGradSync
+                self.grad_sync = FlatGradSync(self.net)
             ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(self.net)
         self.bce = torch.nn.BCEWithLogitsLoss()
         self.ce = torch.nn.CrossEntropyLoss(ignore_index=-100)

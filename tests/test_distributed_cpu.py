@@ -60,6 +60,25 @@ def _worker(rank, world, port, out):
             assert torch.allclose(p.grad, q.grad, atol=1e-5), (k, float((p.grad - q.grad).abs().max()))
         assert torch.allclose(net[2].bn.running_mean, ref[2].bn.running_mean, atol=1e-6)
         assert torch.allclose(net[2].bn.running_var, ref[2].bn.running_var, atol=1e-5)
+        # 2b. the same head under FlatGradSync (one flat all-reduce at the end of backward, grad_sync.py): identical
+        #     gradients, p.grad re-pointed at slices of the flat buffer, parameters broadcast from rank 0 at construction
+        from box2mask_b200.grad_sync import FlatGradSync
+        net2 = head()
+        ME.MinkowskiSyncBatchNorm.convert_sync_batchnorm(net2)
+        if rank == 1:
+            with torch.no_grad():
+                for p in net2.parameters():
+                    p.add_(1.0)               # must be overwritten by rank 0's values
+        gs2 = FlatGradSync(net2)
+        for step in range(2):                 # second pass: set_to_none=False keeps the views and accumulates in place
+            net2.zero_grad(set_to_none=(step == 0))
+            cm3 = CoordinateManager(torch.zeros((x.shape[0], 4), dtype=torch.int32))
+            y2 = net2(SparseTensor(x, coordinate_manager=cm3)).F
+            ((y2 ** 2).sum() / 50 * world).backward()
+            assert gs2.syncs == step + 1
+            for (k, p), (_, q) in zip(net2.named_parameters(), ref.named_parameters()):
+                assert torch.allclose(p.grad, q.grad, atol=1e-5), (k, float((p.grad - q.grad).abs().max()))
+            assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(gs2.params, gs2.views))
         # 3. per-rank scene sharding of the bench: different scenes per rank, deterministic per rank
         import bench
         a = bench.make_scenes(1, seed=10 + rank, scale=0.1)[0]["vox_coords"]
