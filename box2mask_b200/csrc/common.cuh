@@ -76,6 +76,13 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 // debug builds: a timed-out wait first records {block, thread, barrier address, parity, tag} in mapped host memory
 __device__ unsigned int* g_b2m_dbg = nullptr;
 #define B2M_WAIT_TAG(t) (t)
+// debug builds: SM-clock stamps of block (0,0,0) at a few points of a kernel, written to the mapped host buffer
+// ([4096 + id]; tools/small_conv_trace.py). Lane 0 of the calling warp writes; posted store, no read-back.
+__device__ __forceinline__ void b2m_trace(int id) {
+  if (g_b2m_dbg && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0)
+    *reinterpret_cast<volatile unsigned int*>(g_b2m_dbg + 4096 + id) = (unsigned int)clock64() | 1u;
+}
+#define B2M_TRACE(id) b2m_trace(id)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -94,6 +101,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
   }
 }
 #else
+#define B2M_TRACE(id) ((void)0)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
   (void)tag;
   uint32_t spins = 0;

@@ -155,7 +155,10 @@ constexpr int kFwdProd = 12;
 // Warps that share the gathers of ONE stage in the 64-wide-chunk mode (KPACK == 1). A slot is occupied from the moment
 // its producer owns it: the ~76-cycle-per-lane TMA issue loop of a single warp (2400 cycles for 32 row quads) was the
 // largest part of a slot's turnaround; split over kFwdSplit warps the 10-slot ring turns over that much faster.
-constexpr int kFwdSplit = 1;
+#ifndef B2M_FWD_SPLIT
+#define B2M_FWD_SPLIT 1
+#endif
+constexpr int kFwdSplit = B2M_FWD_SPLIT;   // tools/build_variant.py s2 -DB2M_FWD_SPLIT=2 builds the 2-warp variant
 constexpr int kFwdMma = 2;                                     // one MMA issuer warp per tile of a work item
 constexpr int kFwdThreads = (kEpiWarps + kFwdMma + 1 + kFwdProd) * 32;  // 608
 constexpr int kTileM = 128;
@@ -238,6 +241,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + a.off_bars + 16 * SA + 16 * SB + 32);
   const int n0 = blockIdx.y * a.ntile;
   const int nch = a.nfull + a.rem;
+  if (warp == 0) B2M_TRACE(0);
 
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, KPACK == 1 ? kFwdSplit : 1); mbar_init(a_empty + 8 * s, 1); }
@@ -254,6 +258,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (warp == 0) B2M_TRACE(1);
 
   if (warp < kEpiWarps) {
     // ================= epilogue warps: TMEM -> registers -> (staging for the column statistics) + row stores ====
@@ -267,6 +272,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       const int par = wi & 1;
       mbar_wait(acc_full + 8 * par, (uint32_t)(wi >> 1) & 1u, 1);
       tc_fence_after();
+      if (warp == 0 && wi == 0) B2M_TRACE(30);
       for (int t = 0; t < a.T; ++t) {
         const int tile = w * a.T + t;
         if (tile >= a.n_tiles) break;
@@ -325,7 +331,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * par);
+      if (warp == 0 && wi == 0) B2M_TRACE(31);
     }
+    if (warp == 0) B2M_TRACE(32);
     if (a.colsum != nullptr) {
       named_bar_sync(1, kEpiWarps * 32);   // all four epilogue warps have added their last tile
       const double* cs = reinterpret_cast<const double*>(smem + a.off_csum);
@@ -334,6 +342,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
         atomicAdd(a.colsum + col, cs[i]);
       }
     }
+    if (warp == 0) B2M_TRACE(33);
   } else if (warp < kEpiWarps + kFwdMma) {
     // ================= MMA issuers: warp 4 owns tile 0 of every work item, warp 5 tile 1 (T == 2) =================
     // The single-thread issue loop is the critical path of this kernel (~90 instructions per stage), so the two
@@ -352,6 +361,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       Ring ra, rb;
       ra.init(SAr); rb.init(SB);
       int wi = 0;
+      int nstage = 0;      // debug trace only
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
         const int par = wi & 1;
         mbar_wait(acc_empty + 8 * par, ((uint32_t)(wi >> 1) & 1u) ^ 1u, 2);
@@ -367,9 +377,16 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
           for (int c = 0; c < nch; ++c) {
             if (sub) {
               const int aslot = abase + ra.slot;
+              if (me == 0 && nstage >= 32 && nstage < 44) B2M_TRACE(100 + (nstage - 32) * 4);
               mbar_wait(b_full + 8 * rb.slot, rb.phase, 4);
+              if (me == 0 && nstage == 0) B2M_TRACE(19);
+              if (me == 0 && nstage >= 32 && nstage < 44) B2M_TRACE(101 + (nstage - 32) * 4);
               mbar_wait(a_full + 8 * aslot, ra.phase, 5);
               tc_fence_after();
+              if (me == 0 && nstage >= 32 && nstage < 44) B2M_TRACE(102 + (nstage - 32) * 4);
+              if (me == 0 && nstage < 16) B2M_TRACE(40 + nstage);
+              if (me == 0 && (nstage & 15) == 0 && nstage < 256) B2M_TRACE(60 + (nstage >> 4));
+              ++nstage;
               if (lead) {
                 const uint32_t b_lo = umma_desc_lo(smem_base + a.off_b + rb.slot * a.b_bytes, 16);
                 const uint32_t a_lo = umma_desc_lo(smem_base + aslot * kASlotBytes, 16);
@@ -413,6 +430,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                 umma_commit(a_empty + 8 * aslot);
                 umma_commit(b_empty + 8 * rb.slot);            // arrives once this tile's MMAs on the slice are done
               }
+              if (me == 0 && nstage > 32 && nstage <= 44) B2M_TRACE(103 + (nstage - 33) * 4);
               acc = 1u;
               ra.next();
             } else {
@@ -426,6 +444,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
           }
         }
         if (lead) umma_commit(acc_full + 8 * par);
+        if (me == 0 && wi == 0) B2M_TRACE(21);
       }
     }
     __syncwarp();
@@ -534,6 +553,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       };
       St cur = next();
       int4 idx = load_idx(cur);
+      int ntr = 0;       // debug trace only
       while (cur.valid) {
         const St nxt = next();
         const int4 idx_next = load_idx(nxt);               // in flight while this stage waits for its slot
@@ -541,12 +561,16 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
         const uint32_t full = a_full + 8 * cur.slot;
         const uint32_t wc = (cur.c < a.nfull) ? 128u : 64u;
         mbar_wait(a_empty + 8 * cur.slot, cur.phase ^ 1u, 10);
+        if (pw == 0 && ntr < 4) B2M_TRACE(10 + 2 * ntr);
         if (lane == 0) {
           if (B2M_ABLATE(a, 0)) mbar_arrive(full); else mbar_arrive_expect_tx(full, (uint32_t)(q_hi - q_lo) * 4u * wc);
         }
         __syncwarp();
         if (on && !B2M_ABLATE(a, 0))
           tma_gather4(a_s + quad * 4 * wc, (cur.c < a.nfull) ? &tm_main : &tm_rem, full, cur.c * 64, idx.x, idx.y, idx.z, idx.w);
+        __syncwarp();
+        if (pw == 0 && ntr < 4) B2M_TRACE(11 + 2 * ntr);
+        ++ntr;
         cur = nxt;
         idx = idx_next;
       }
@@ -658,6 +682,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) B2M_TRACE(2);
   if (warp == 6) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
@@ -700,10 +725,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const int col = blockIdx.x;             // which G offset groups
   const int mt = blockIdx.z;              // M tile (input-channel block of 128) when c_in > 128
   const int64_t total_groups = (a.n_out + kWgRows - 1) / kWgRows;
-  const int64_t g_begin = (int64_t)blockIdx.y * a.groups_per_cta;
-  const int64_t g_end = min(total_groups, g_begin + a.groups_per_cta);
+  // Row groups are dealt round-robin to the gridDim.y CTAs of a column: all CTAs then sweep the arrays together, so
+  // the rows one CTA gathers (and the dY stage its column neighbours re-read) are still in L2 when the others need them.
+  // With a contiguous range per CTA the 24 x 6 CTAs of a full-resolution launch streamed 24 distant regions and
+  // drifted apart (L2 hit rate 57 %, 2 GB of DRAM reads per launch against 0.5 GB of operands).
+  const int64_t g_begin = (int64_t)blockIdx.y;
+  const int64_t g_end = total_groups;
+  const int64_t g_step = (int64_t)gridDim.y;
   const int kbase = col * a.G * a.pk;     // first kernel offset of accumulator 0
   const int nq = min(a.G, (a.kvol - kbase + a.pk - 1) / a.pk);   // accumulators of this CTA that hold real offsets
+  if (warp == 0) B2M_TRACE(0);
 
   if (warp == kWgEpi && lane == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
@@ -718,6 +749,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (warp == 0) B2M_TRACE(1);
 
   auto group_mask = [&](int64_t g) -> MaskBits {
     if (a.gmask == nullptr) { MaskBits m = mask_zero(); m.w0 = 1u; return m; }
@@ -744,34 +776,49 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     // ================= epilogue: TMEM -> fp32 vector atomics into dw =================
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (warp == 0) B2M_TRACE(30);
     const uint32_t used = *reinterpret_cast<volatile uint32_t*>(used_s);
-    const int mrow = warp * 32 + lane;              // TMEM lane == M row
-    const int slot = mrow / a.cpad;                 // which packed offset
-    const int ci = mrow % a.cpad + mt * 128;
+    // A lane holds 32 consecutive output columns of ONE M row (TMEM lane == M row == input channel), and rows of dw
+    // are c_out floats apart: atomics issued straight from that layout touch 32 different 128-byte lines per warp
+    // instruction (measured: 40 us for the 2 x 128 x 256 accumulators of a 256->256 layer, the whole cost of a
+    // deep-level launch). Each 32x32 tile is therefore transposed through shared memory (the A ring is idle: every
+    // stage has been consumed once accum_bar completes) so that 8 lanes cover the 128 contiguous bytes of a row and
+    // a warp instruction touches 4 full lines.
+    const uint32_t tr = smem_base + warp * (32 * kStagePitch * 4);
+    const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
     const int nchunk32 = (a.c_out + 31) / 32;
     for (int q = 0; q < nq; ++q) {
       if (!((used >> q) & 1u)) continue;
-      const int k = kbase + q * a.pk + slot;
-      const bool ok = slot < a.pk && k < a.kvol && ci < a.c_in;
       for (int cc = 0; cc < nchunk32; ++cc) {
         const int cw = min(32, a.c_out - cc * 32);
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * a.colstride + cc * 32);
         if (cw == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         tmem_ld_wait();
-        if (ok) {
-          float* dst = a.dw + ((int64_t)k * a.c_in + ci) * a.c_out + cc * 32;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < cw) {
-              atomicAdd(reinterpret_cast<float4*>(dst + j),
-                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                    __uint_as_float(v[j + 3])));
+        for (int j = 0; j < 32; ++j)
+          if (j < cw) st_shared_f32(tr + (lane * kStagePitch + j) * 4, __uint_as_float(v[j]));
+        __syncwarp();
+        if (c4 < cw) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = 4 * j + r_sub;                  // row of the 32x32 tile
+            const int mrow = warp * 32 + r;               // M row
+            const int slot = mrow / a.cpad;               // which packed offset
+            const int ci = mrow % a.cpad + mt * 128;
+            const int k = kbase + q * a.pk + slot;
+            if (slot < a.pk && k < a.kvol && ci < a.c_in) {
+              const uint32_t src = tr + (r * kStagePitch + c4) * 4;
+              const float4 val = make_float4(ld_shared_f32(src), ld_shared_f32(src + 4), ld_shared_f32(src + 8),
+                                             ld_shared_f32(src + 12));
+              atomicAdd(reinterpret_cast<float4*>(a.dw + ((int64_t)k * a.c_in + ci) * a.c_out + cc * 32 + c4), val);
             }
           }
         }
+        __syncwarp();
       }
     }
+    if (warp == 0) B2M_TRACE(31);
   } else if (warp == kWgEpi) {
     // ================= MMA issuer (warp-uniform loop, one elected lane issues; see conv_fwd_kernel) =================
     const bool lead = elect_one_sync();
@@ -785,18 +832,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     Ring ra, rb;
     ra.init(SA); rb.init(SB);
     MaskBits m_next = group_mask(g_begin < g_end ? g_begin : 0);
-    for (int64_t g = g_begin; g < g_end; ++g) {
+    for (int64_t g = g_begin; g < g_end; g += g_step) {
       const MaskBits m = m_next;
-      if (g + 1 < g_end) m_next = group_mask(g + 1);   // prefetched: the load latency overlaps this group's work
+      if (g + g_step < g_end) m_next = group_mask(g + g_step);   // prefetched: the load latency overlaps this group's work
       const uint32_t qm = acc_mask(m);
       if (!qm) continue;
       mbar_wait(b_full + 8 * rb.slot, rb.phase);
+      if (g == g_begin) B2M_TRACE(19);
       const uint32_t b_lo = (((smem_base + a.off_b + rb.slot * a.b_bytes) >> 4) & 0x3FFFu) | lbo_b;
 #pragma unroll 1
       for (uint32_t rem = qm; rem; rem &= rem - 1) {
         const int q = __ffs(rem) - 1;
         mbar_wait(a_full + 8 * ra.slot, ra.phase);
         tc_fence_after();
+        if (g == g_begin) B2M_TRACE(20);
         if (lead) {
           const uint32_t a_lo = (((smem_base + ra.slot * kWgASlotBytes) >> 4) & 0x3FFFu) | lbo_a;
           const uint32_t d = tmem_base + (uint32_t)(q * a.colstride);
@@ -819,6 +868,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       __threadfence_block();
       umma_commit(accum_bar);
     }
+    B2M_TRACE(21);
     __syncwarp();
   } else if (warp <= kWgEpi + kWgBProd) {
     // ================= dY producers (B operand, MN-major): gather rows order[g*64 ..]; stage s by warp s % kWgBProd ====
@@ -829,9 +879,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     int turn = 0;
     const int items = a.nbb * 16;   // (column block, 4-row quad)
     MaskBits m_next = group_mask(g_begin < g_end ? g_begin : 0);
-    for (int64_t g = g_begin; g < g_end; ++g) {
+    for (int64_t g = g_begin; g < g_end; g += g_step) {
       const MaskBits m = m_next;
-      if (g + 1 < g_end) m_next = group_mask(g + 1);   // prefetched: the load latency overlaps this group's work
+      if (g + g_step < g_end) m_next = group_mask(g + g_step);   // prefetched: the load latency overlaps this group's work
       if (!acc_mask(m)) continue;
       const bool mine = (turn == pb);
       turn = (turn + 1 == npb) ? 0 : turn + 1;
@@ -849,12 +899,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         idx.w = pos0 + 3 < a.n_out ? (int)pos0 + 3 : -1;
       }
       mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u);
+      if (g == g_begin) B2M_TRACE(10);
       if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(a.nbb * kWgRows * a.wb));
       __syncwarp();
       for (int it = lane; it < items; it += 32) {
         const int blk = it >> 4;
         tma_gather4(b_s + blk * (kWgRows * a.wb) + (it & 15) * 4 * a.wb, &tm_dy, full, blk * 64, idx.x, idx.y, idx.z, idx.w);
       }
+      __syncwarp();
+      if (g == g_begin) B2M_TRACE(11);
       rb.next();
     }
   } else {
@@ -866,9 +919,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     int turn = 0;
     const int items = a.nab * 16;   // (block, 4-row quad); pk > 1: block == packed offset slot, else channel block
     MaskBits m_next = group_mask(g_begin < g_end ? g_begin : 0);
-    for (int64_t g = g_begin; g < g_end; ++g) {
+    for (int64_t g = g_begin; g < g_end; g += g_step) {
       const MaskBits m = m_next;
-      if (g + 1 < g_end) m_next = group_mask(g + 1);   // prefetched: the load latency overlaps this group's work
+      if (g + g_step < g_end) m_next = group_mask(g + g_step);   // prefetched: the load latency overlaps this group's work
       // The stages of this row group are the set bits of qm in ascending order; jump to the ones whose turn is this
       // warp's instead of walking all of them.
       const uint32_t qm = (p < np) ? acc_mask(m) : 0u;
@@ -941,6 +994,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             }
           }
           mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u);
+          if (g == g_begin && p == 0) B2M_TRACE(12);
           const int nblk = (a.pk > 1) ? nslots : a.nab;
           if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(nblk * kWgRows * a.wa));
           __syncwarp();
@@ -953,6 +1007,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               tma_gather4(a_s + blk * (kWgRows * a.wa) + (it & 15) * 4 * a.wa, &tm_x, full, colx, idx[u].x, idx[u].y, idx[u].z, idx[u].w);
             }
           }
+          __syncwarp();
+          if (g == g_begin && p == 0) B2M_TRACE(13);
         }
       }
       ra = ra0.at(n_g);
@@ -963,6 +1019,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) B2M_TRACE(2);
   if (warp == kWgEpi + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
@@ -1112,13 +1169,32 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   a.T = (a.ntile <= 128 && a.n_tiles >= 4 * sms) ? 2 : 1;
   a.n_work = (a.n_tiles + a.T - 1) / a.T;
   a.b_bytes = a.ntile * 128;
-  a.b_slots = (a.b_bytes >= 32768) ? 2 : (a.b_bytes >= 12288 ? 3 : 4);
   const int stage_bytes = kEpiWarps * 32 * kStagePitch * 4;
   const int csum_bytes = 2 * a.ntile * 8;
-  const int budget = 227 * 1024 - 1024 - 256 - stage_bytes - csum_bytes - a.b_slots * a.b_bytes;
-  a.a_slots = budget / kASlotBytes;
-  if (a.a_slots > 10) a.a_slots = 10;
-  if (a.a_slots < 2) return B2M_ERR_UNSUPPORTED_SHAPE;
+  // Ring depths. One unit of work (offset group, chunk) consumes T A stages (one per tile ring) and one weight
+  // slice; a slot of either ring is reused only after a full turnaround (MMA completion + commit -> producer ->
+  // copy lands -> consumer), measured with tools/small_conv_trace.py at ~2.9 us for a gathered A stage (1.2 us of it
+  // is the producer warp issuing its 32 gather4s) and ~2.0 us for a weight slice. Throughput = slots in flight /
+  // turnaround, so shared memory is split to minimise max(2.9 / A slots per ring, 2.0 / B slots): narrow column tiles
+  // get up to 12 weight slots (4 made every deep-level launch run at 2.2 us / 4 per stage whatever the A depth),
+  // 256-wide tiles trade A slots for a third or fourth weight slot, 96-wide full-resolution tiles keep 10 + 3.
+  {
+    const int budget = 227 * 1024 - 1024 - 256 - stage_bytes - csum_bytes - 16 * 32;
+    int best_sa = 0, best_sb = 0;
+    float best = 1e30f;
+    for (int sb = 2; sb <= 12; ++sb) {
+      int sa = (budget - sb * a.b_bytes) / kASlotBytes;
+      if (sa > 12) sa = 12;
+      sa -= sa % a.T;
+      if (sa < 2 * a.T) break;
+      const float ta = 2.9f / (float)(sa / a.T), tb = 2.0f / (float)sb;
+      const float t = ta > tb ? ta : tb;
+      if (t < best - 1e-6f) { best = t; best_sa = sa; best_sb = sb; }
+    }
+    if (best_sa == 0) return B2M_ERR_UNSUPPORTED_SHAPE;
+    a.a_slots = best_sa;
+    a.b_slots = best_sb;
+  }
   a.off_b = a.a_slots * kASlotBytes;
   a.off_stage = a.off_b + a.b_slots * a.b_bytes;
   a.off_csum = (a.off_stage + stage_bytes + 15) / 16 * 16;

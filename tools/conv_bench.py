@@ -10,6 +10,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if os.environ.get("B2M_BENCH_LIB"):      # a variant built by tools/build_variant.py
+    from box2mask_b200 import _lib
+    _lib.LIB_PATH = os.path.abspath(os.environ["B2M_BENCH_LIB"])
 from box2mask_b200 import ops  # noqa: E402
 from box2mask_b200.synthetic import batched_coordinates, make_scene  # noqa: E402
 
