@@ -7,7 +7,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb2m.so")
+# B2M_LIB selects a variant built by tools/build_variant.py (debug / experiment builds); the product library otherwise
+LIB_PATH = os.path.abspath(os.environ["B2M_LIB"]) if os.environ.get("B2M_LIB") else os.path.join(_HERE, "lib", "libb2m.so")
 
 _P = c_void_p  # every device pointer travels as void*
 

@@ -774,7 +774,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 
   if (warp < kWgEpi) {
     // ================= epilogue: TMEM -> fp32 vector atomics into dw =================
-    mbar_wait(accum_bar, 0);
+    mbar_wait(accum_bar, 0, 20);
     tc_fence_after();
     if (warp == 0) B2M_TRACE(30);
     const uint32_t used = *reinterpret_cast<volatile uint32_t*>(used_s);
@@ -837,13 +837,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (g + g_step < g_end) m_next = group_mask(g + g_step);   // prefetched: the load latency overlaps this group's work
       const uint32_t qm = acc_mask(m);
       if (!qm) continue;
-      mbar_wait(b_full + 8 * rb.slot, rb.phase);
+      mbar_wait(b_full + 8 * rb.slot, rb.phase, 21);
       if (g == g_begin) B2M_TRACE(19);
       const uint32_t b_lo = (((smem_base + a.off_b + rb.slot * a.b_bytes) >> 4) & 0x3FFFu) | lbo_b;
 #pragma unroll 1
       for (uint32_t rem = qm; rem; rem &= rem - 1) {
         const int q = __ffs(rem) - 1;
-        mbar_wait(a_full + 8 * ra.slot, ra.phase);
+        mbar_wait(a_full + 8 * ra.slot, ra.phase, 22);
         tc_fence_after();
         if (g == g_begin) B2M_TRACE(20);
         if (lead) {
@@ -898,7 +898,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         idx.z = pos0 + 2 < a.n_out ? (int)pos0 + 2 : -1;
         idx.w = pos0 + 3 < a.n_out ? (int)pos0 + 3 : -1;
       }
-      mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u);
+      mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u, 23);
       if (g == g_begin) B2M_TRACE(10);
       if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(a.nbb * kWgRows * a.wb));
       __syncwarp();
@@ -941,7 +941,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           const int j = lane & 15, rh = lane >> 4;
           const int k = kbase + q * a.pk + j;
           const int32_t* nb = (a.nbr && k < a.kvol) ? a.nbr + (int64_t)k * a.n_pitch + g * kWgRows : nullptr;
-          mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u);
+          mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u, 24);
 #pragma unroll 2
           for (int it = 0; it < 8; ++it) {
             const int r0 = 8 * it + 4 * rh;
@@ -993,7 +993,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               }
             }
           }
-          mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u);
+          mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u, 24);
           if (g == g_begin && p == 0) B2M_TRACE(12);
           const int nblk = (a.pk > 1) ? nslots : a.nab;
           if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(nblk * kWgRows * a.wa));

@@ -21,6 +21,7 @@ ap.add_argument("--scenes", type=int, default=8)
 ap.add_argument("--mhz", type=float, default=1965.0)
 ap.add_argument("--levels", default="3,4,5,6,7")
 ap.add_argument("--channels", type=int, default=256)
+ap.add_argument("--which", default="fwd,wgrad")
 args = ap.parse_args()
 _lib.LIB_PATH = args.lib
 from box2mask_b200 import ops  # noqa: E402
@@ -102,6 +103,8 @@ for lvl in [int(v) for v in args.levels.split(",")]:
     colsum = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
     for name, fn in (("fwd", lambda: ops.conv_forward(x, km, packed, 27, n, C, colsum)),
                      ("wgrad", lambda: ops.conv_wgrad(x, dy, km, 27, n))):
+        if name not in args.which.split(","):
+            continue
         single, b2b, gms, st = timed(fn)
         print("L%d n=%d %s %d->%d: single launch %.1f us, back-to-back %.1f us/launch, in a CUDA graph %.1f us/launch" % (
             lvl, n, name, C, C, single, b2b, gms))
