@@ -152,13 +152,6 @@ constexpr int kEpiWarps = 4;
 // ~76 cycles per lane (ELECT + R2UR loop around UTMALDG; tools/tma_gather_bench.cu) whatever the box size, and
 // scales linearly with the number of warps, so the TMA engine is fed by many warps.
 constexpr int kFwdProd = 12;
-// Warps that share the gathers of ONE stage in the 64-wide-chunk mode (KPACK == 1). A slot is occupied from the moment
-// its producer owns it: the ~76-cycle-per-lane TMA issue loop of a single warp (2400 cycles for 32 row quads) was the
-// largest part of a slot's turnaround; split over kFwdSplit warps the 10-slot ring turns over that much faster.
-#ifndef B2M_FWD_SPLIT
-#define B2M_FWD_SPLIT 1
-#endif
-constexpr int kFwdSplit = B2M_FWD_SPLIT;   // tools/build_variant.py s2 -DB2M_FWD_SPLIT=2 builds the 2-warp variant
 constexpr int kFwdMma = 2;                                     // one MMA issuer warp per tile of a work item
 constexpr int kFwdThreads = (kEpiWarps + kFwdMma + 1 + kFwdProd) * 32;  // 608
 constexpr int kTileM = 128;
@@ -177,6 +170,7 @@ struct FwdArgs {
   int64_t n_out, n_pitch;
   int c_red, kvol, c_n, ntile, T, kpack, nkg, nfull, rem, wa, mwords, colstride, n_tiles, n_work;
   int a_slots, b_slots, b_bytes, kg_bytes;
+  int cps, ncg, a_slot_bytes;   // KPACK == 1: 64-wide chunks per A stage (1 or 2), stages per offset, bytes of an A slot
   int off_b, off_stage, off_csum, off_bars, tmem_cols;
   int ablate;   // debug builds (B2M_ABLATE env): 1 = no A gathers, 2 = no MMAs, 4 = no epilogue stores, 8 = no B copies
 };
@@ -224,6 +218,18 @@ struct Ring {
   __device__ __forceinline__ Ring at(int k) const { Ring r = *this; r.advance(k); return r; }
 };
 
+// the 4 (2) K = 16 steps of one 64-wide SW128 (32-wide SW64) chunk: +32 bytes per step in both descriptors
+__device__ __forceinline__ void umma_chunk4(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  umma_bf16_lohi(d, a_lo, hi, b_lo, hi, idesc, acc);
+  umma_bf16_lohi(d, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
+  umma_bf16_lohi(d, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
+  umma_bf16_lohi(d, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
+}
+__device__ __forceinline__ void umma_chunk2(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  umma_bf16_lohi(d, a_lo, hi, b_lo, hi, idesc, acc);
+  umma_bf16_lohi(d, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
+}
+
 // KPACK = offsets per A stage: 1 (c_red >= 48: 64-wide chunks), 2 / 4 (c_red 32 / 16: SW64 / SW32 sub-tiles),
 // 8 (c_red 8: cp.async path). A template parameter so that the single-thread MMA issue loop has no mode branches.
 template <int KPACK>
@@ -241,10 +247,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + a.off_bars + 16 * SA + 16 * SB + 32);
   const int n0 = blockIdx.y * a.ntile;
   const int nch = a.nfull + a.rem;
+  const int nst = (KPACK == 1) ? a.ncg : nch;     // pipeline stages (and weight slots) per offset group
   if (warp == 0) B2M_TRACE(0);
 
   if (warp == 4 && lane == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, KPACK == 1 ? kFwdSplit : 1); mbar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, KPACK == 1 ? a.cps : 1); mbar_init(a_empty + 8 * s, 1); }
     // every tile's MMA issuer releases a B slot / completes an accumulator set: T arrivals each
     for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, a.T); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full + 8 * s, a.T); mbar_init(acc_empty + 8 * s, kEpiWarps); }
@@ -360,6 +367,23 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       const int SAr = SA / a.T, abase = me * SAr;
       Ring ra, rb;
       ra.init(SAr); rb.init(SB);
+      // KPACK == 1: the low descriptor words of the current A / B slots travel with the rings (no per-stage address
+      // arithmetic on the issue path: every instruction of this loop is ~10 cycles of a lone warp's critical path).
+      // Stage forms: every chunk is a full 64-wide SW128 tile (4 K-steps; a 16- or 48-wide tail is zero in both
+      // operands) except the very last chunk of an offset when c_red % 64 == 32 (2 K-steps, SW64).
+      const uint32_t a_ring_lo = umma_desc_lo(smem_base + abase * a.a_slot_bytes, 16);
+      const uint32_t b_ring_lo = umma_desc_lo(smem_base + a.off_b, 16);
+      const uint32_t a_step = (uint32_t)(a.a_slot_bytes >> 4), b_step = (uint32_t)(a.b_bytes >> 4);
+      const uint32_t b_chunk = (uint32_t)((a.ntile * 128) >> 4);
+      uint32_t a_cur = a_ring_lo, b_cur = b_ring_lo;
+      const bool two = (KPACK == 1) && a.cps == 2;
+      const int last_n = nch - (nst - 1) * ((KPACK == 1) ? a.cps : 1);   // chunks of an offset's last stage
+      const bool has_rem = a.rem != 0;
+      // which of the four stage forms the LAST stage of an offset has; every other stage is two (one) full chunks
+      uint32_t last_c0_rem = (has_rem && last_n == 1) ? 1u : 0u, last_c1 = (two && last_n == 2) ? (has_rem ? 2u : 1u) : 0u;
+      uint32_t st_a = a_step, st_b = b_step, st_c = b_chunk, st_last = (uint32_t)(nst - 1);
+      // keep them in registers: re-deriving them from the kernel parameters costs constant-bank loads on the issue path
+      asm volatile("" : "+r"(last_c0_rem), "+r"(last_c1), "+r"(st_a), "+r"(st_b), "+r"(st_c), "+r"(st_last));
       int wi = 0;
       int nstage = 0;      // debug trace only
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
@@ -374,7 +398,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
         for (int kg = next_group<KPACK>(mu, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mu, kg + 1, a.nkg, a.mwords)) {
           const uint32_t s0 = mask_bits(m0, kg * KPACK, KPACK), s1 = mask_bits(m1, kg * KPACK, KPACK);
           const uint32_t sub = me ? s1 : s0;
-          for (int c = 0; c < nch; ++c) {
+          for (int c = 0; c < nst; ++c) {
             if (sub) {
               const int aslot = abase + ra.slot;
               if (me == 0 && nstage >= 32 && nstage < 44) B2M_TRACE(100 + (nstage - 32) * 4);
@@ -388,20 +412,19 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
               if (me == 0 && (nstage & 15) == 0 && nstage < 256) B2M_TRACE(60 + (nstage >> 4));
               ++nstage;
               if (lead) {
-                const uint32_t b_lo = umma_desc_lo(smem_base + a.off_b + rb.slot * a.b_bytes, 16);
-                const uint32_t a_lo = umma_desc_lo(smem_base + aslot * kASlotBytes, 16);
+                const uint32_t b_lo = (KPACK == 1) ? 0u : umma_desc_lo(smem_base + a.off_b + rb.slot * a.b_bytes, 16);
+                const uint32_t a_lo = (KPACK == 1) ? 0u : umma_desc_lo(smem_base + aslot * a.a_slot_bytes, 16);
                 if (KPACK == 1) {
-                  const bool full_chunk = c < a.nfull;
-                  const int nks = full_chunk ? min(4, (a.c_red - c * 64) >> 4) : 2;
+                  // a stage holds one or two chunks of this offset: sub-tile j of the A slot (16 KB apart) against
+                  // weight slice j of the B slot (ntile * 128 bytes apart)
+                  const bool last = ((uint32_t)c == st_last);
                   if (B2M_ABLATE(a, 1)) {
-                  } else if (nks == 4) {                        // the common case, straight-line: +32 bytes per K=16 step
-                    umma_bf16_lohi(d, a_lo, hi128, b_lo, hi128, idesc, acc);
-                    umma_bf16_lohi(d, a_lo + 2, hi128, b_lo + 2, hi128, idesc, 1u);
-                    umma_bf16_lohi(d, a_lo + 4, hi128, b_lo + 4, hi128, idesc, 1u);
-                    umma_bf16_lohi(d, a_lo + 6, hi128, b_lo + 6, hi128, idesc, 1u);
                   } else {
-                    const uint32_t hi = full_chunk ? hi128 : hi64;
-                    for (int ks = 0; ks < nks; ++ks) umma_bf16_lohi(d, a_lo + 2 * ks, hi, b_lo + 2 * ks, hi, idesc, ks ? 1u : acc);
+                    if (last && last_c0_rem) umma_chunk2(d, a_cur, b_cur, hi64, idesc, acc);
+                    else umma_chunk4(d, a_cur, b_cur, hi128, idesc, acc);
+                    const uint32_t f1 = last ? last_c1 : (two ? 1u : 0u);      // 0 = no second chunk, 1 = full, 2 = 32-wide
+                    if (f1 == 1u) umma_chunk4(d, a_cur + (kASlotBytes >> 4), b_cur + st_c, hi128, idesc, 1u);
+                    else if (f1 == 2u) umma_chunk2(d, a_cur + (kASlotBytes >> 4), b_cur + st_c, hi64, idesc, 1u);
                   }
                 } else if (KPACK == 8) {
                   // 8 offsets x 8 channels side by side in one SW128 tile: a K=16 step covers a pair of offsets
@@ -433,6 +456,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
               if (me == 0 && nstage > 32 && nstage <= 44) B2M_TRACE(103 + (nstage - 33) * 4);
               acc = 1u;
               ra.next();
+              a_cur = (ra.slot == 0) ? a_ring_lo : a_cur + st_a;
             } else {
               // The other tile uses this offset group, this one does not: release the B slot. Waiting for the slice
               // first keeps this warp from running a whole slot use ahead: b_empty counts arrivals, it cannot tell
@@ -441,6 +465,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
               if (lead) mbar_arrive(b_empty + 8 * rb.slot);
             }
             rb.next();
+            b_cur = (rb.slot == 0) ? b_ring_lo : b_cur + st_b;
           }
         }
         if (lead) umma_commit(acc_full + 8 * par);
@@ -458,18 +483,23 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
       const MaskBits mu = mask_or(m0, m1);
       for (int kg = next_group<KPACK>(mu, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mu, kg + 1, a.nkg, a.mwords)) {
-        for (int c = 0; c < nch; ++c) {
+        for (int c = 0; c < nst; ++c) {
           mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u, 9);
           if (lead) {
             const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
-            const int wb = (c < a.nfull) ? 128 : 64;
-            const uint32_t bytes = (uint32_t)(a.ntile * wb);
-            const uint8_t* src = a.w + (int64_t)kg * a.kg_bytes + (int64_t)min(c, a.nfull) * a.c_n * 128 + (int64_t)n0 * wb;
+            const int per = (KPACK == 1) ? a.cps : 1;            // weight slices of this stage
+            const int ch0 = c * per, ch1 = min(nch, ch0 + per);
+            uint32_t total = 0;
+            for (int ch = ch0; ch < ch1; ++ch) total += (uint32_t)(a.ntile * ((ch < a.nfull) ? 128 : 64));
             if (B2M_ABLATE(a, 3)) {
               mbar_arrive(b_full + 8 * rb.slot);
             } else {
-              mbar_arrive_expect_tx(b_full + 8 * rb.slot, bytes);
-              bulk_g2s(b_s, src, bytes, b_full + 8 * rb.slot);
+              mbar_arrive_expect_tx(b_full + 8 * rb.slot, total);
+              for (int ch = ch0; ch < ch1; ++ch) {
+                const int wb = (ch < a.nfull) ? 128 : 64;
+                const uint8_t* src = a.w + (int64_t)kg * a.kg_bytes + (int64_t)min(ch, a.nfull) * a.c_n * 128 + (int64_t)n0 * wb;
+                bulk_g2s(b_s + (uint32_t)((ch - ch0) * a.ntile * 128), src, (uint32_t)(a.ntile * wb), b_full + 8 * rb.slot);
+              }
             }
           }
           rb.next();
@@ -484,15 +514,17 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     // With T == 2 the warps are split between the two tiles' private rings (see the MMA issuers). Within a ring,
     // stage s is produced by warp s % np with np <= ring size: a warp then never runs more than one use of a slot
     // ahead of the consumer, which is what waiting on an mbarrier phase PARITY requires.
-    constexpr int NS = (KPACK == 1) ? kFwdSplit : 1;
-    const int pw = (warp - (kEpiWarps + kFwdMma + 1)) / NS;     // producer group; its NS warps split the row quads
-    const int part = (warp - (kEpiWarps + kFwdMma + 1)) % NS;
+    // KPACK == 1: the a.cps chunks of a stage are gathered by a.cps warps (a producer group), one chunk each, so that
+    // the ~1.2 us a warp needs to issue its 32 gather4s does not grow with the stage.
+    const int NS = (KPACK == 1) ? a.cps : 1;
+    const int pw = (warp - (kEpiWarps + kFwdMma + 1)) / NS;     // producer group
+    const int part = (warp - (kEpiWarps + kFwdMma + 1)) % NS;   // the chunk of the stage this warp gathers
     const int groups = (kFwdProd / NS) / a.T;                   // producer groups per ring
     const int t = (a.T > 1 && pw >= groups) ? 1 : 0;            // the tile (ring) this warp feeds
     const int p = pw - t * groups;
     const int SAr = SA / a.T, abase = t * SAr;
     const int np = min(groups, SAr);
-    const int q_lo = part * 32 / NS, q_hi = (part + 1) * 32 / NS;   // this warp's row quads of a 128-row tile
+    const int q_lo = 0, q_hi = 32;                               // every warp gathers all 32 row quads of the tile
     Ring ra;
     ra.init(SAr);
     int turn = 0;  // stage counter modulo np
@@ -517,14 +549,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
             fresh = false;
           }
           if (kg < a.nkg) {
-            if (d < nch) {
+            if (d < nst) {
               const Ring rs = ra0.at(d);
               s.valid = true; s.w = w; s.kg = kg; s.c = d; s.slot = abase + rs.slot; s.phase = rs.phase;
               d += np;
               return s;
             }
-            ra0 = ra0.at(nch);
-            turn += nch; while (turn >= np) turn -= np;
+            ra0 = ra0.at(nst);
+            turn += nst; while (turn >= np) turn -= np;
             kg = next_group<1>(mt, kg + 1, a.nkg, a.mwords);
             d = p - turn; if (d < 0) d += np;
             continue;
@@ -557,17 +589,19 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       while (cur.valid) {
         const St nxt = next();
         const int4 idx_next = load_idx(nxt);               // in flight while this stage waits for its slot
-        const uint32_t a_s = smem_base + cur.slot * kASlotBytes;
+        const int ch = cur.c * NS + part;                      // this warp's chunk of the stage (may not exist)
+        const bool has = ch < nch;
+        const uint32_t a_s = smem_base + cur.slot * a.a_slot_bytes + part * kASlotBytes;
         const uint32_t full = a_full + 8 * cur.slot;
-        const uint32_t wc = (cur.c < a.nfull) ? 128u : 64u;
+        const uint32_t wc = (ch < a.nfull) ? 128u : 64u;
         mbar_wait(a_empty + 8 * cur.slot, cur.phase ^ 1u, 10);
         if (pw == 0 && ntr < 4) B2M_TRACE(10 + 2 * ntr);
         if (lane == 0) {
-          if (B2M_ABLATE(a, 0)) mbar_arrive(full); else mbar_arrive_expect_tx(full, (uint32_t)(q_hi - q_lo) * 4u * wc);
+          if (B2M_ABLATE(a, 0) || !has) mbar_arrive(full); else mbar_arrive_expect_tx(full, (uint32_t)(q_hi - q_lo) * 4u * wc);
         }
         __syncwarp();
-        if (on && !B2M_ABLATE(a, 0))
-          tma_gather4(a_s + quad * 4 * wc, (cur.c < a.nfull) ? &tm_main : &tm_rem, full, cur.c * 64, idx.x, idx.y, idx.z, idx.w);
+        if (on && has && !B2M_ABLATE(a, 0))
+          tma_gather4(a_s + quad * 4 * wc, (ch < a.nfull) ? &tm_main : &tm_rem, full, ch * 64, idx.x, idx.y, idx.z, idx.w);
         __syncwarp();
         if (pw == 0 && ntr < 4) B2M_TRACE(11 + 2 * ntr);
         ++ntr;
@@ -591,7 +625,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
             {
               const int quad = (KPACK == 1) ? q_lo + lane : lane;                 // this lane gathers rows 4*quad .. 4*quad+3
               const int64_t pos0 = (int64_t)(w * a.T + t) * kTileM + 4 * quad;
-              const uint32_t a_s = smem_base + aslot * kASlotBytes;
+              const uint32_t a_s = smem_base + aslot * a.a_slot_bytes;
               const uint32_t full = a_full + 8 * aslot;
               if (KPACK == 1) {
                 const bool on = quad < q_hi;
@@ -1168,34 +1202,57 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   const int sms = num_sms();
   a.T = (a.ntile <= 128 && a.n_tiles >= 4 * sms) ? 2 : 1;
   a.n_work = (a.n_tiles + a.T - 1) / a.T;
-  a.b_bytes = a.ntile * 128;
+  // KPACK == 1: an A stage holds one or two 64-wide chunks of one offset (each gathered by its own warp) and a weight
+  // slot the matching slices. The MMA issuer pays ~1000 cycles (0.5 us) of dependent barrier / fence / commit latency
+  // per stage whatever the stage holds (tools/small_conv_trace.py), so a 96- or 128-wide reduction is better off with
+  // one stage per offset than two, a 256-wide one with two than four - unless the coarser slots leave too few in
+  // flight. The 32-wide remainder chunk takes 8 KB, not a whole 16 KB slot.
+  //
+  // Ring depths. A slot of either ring is reused only after a full turnaround (MMA completion + commit -> producer ->
+  // copy lands -> consumer), measured at ~2.9 us for a gathered A stage (1.2 us of it is the producer warp issuing its
+  // 32 gather4s) and ~2.0 us for a weight slot. Throughput = slots in flight / turnaround, so for each candidate
+  // stage size shared memory is split to minimise max(2.9 / A slots per ring, 2.0 / B slots), and the stage size with
+  // the lower time per offset = stages * max(that, 0.5 us issuer floor) wins (ties: the larger stage).
   const int stage_bytes = kEpiWarps * 32 * kStagePitch * 4;
   const int csum_bytes = 2 * a.ntile * 8;
-  // Ring depths. One unit of work (offset group, chunk) consumes T A stages (one per tile ring) and one weight
-  // slice; a slot of either ring is reused only after a full turnaround (MMA completion + commit -> producer ->
-  // copy lands -> consumer), measured with tools/small_conv_trace.py at ~2.9 us for a gathered A stage (1.2 us of it
-  // is the producer warp issuing its 32 gather4s) and ~2.0 us for a weight slice. Throughput = slots in flight /
-  // turnaround, so shared memory is split to minimise max(2.9 / A slots per ring, 2.0 / B slots): narrow column tiles
-  // get up to 12 weight slots (4 made every deep-level launch run at 2.2 us / 4 per stage whatever the A depth),
-  // 256-wide tiles trade A slots for a third or fourth weight slot, 96-wide full-resolution tiles keep 10 + 3.
   {
+    const int nch = a.nfull + a.rem;
     const int budget = 227 * 1024 - 1024 - 256 - stage_bytes - csum_bytes - 16 * 32;
-    int best_sa = 0, best_sb = 0;
-    float best = 1e30f;
-    for (int sb = 2; sb <= 12; ++sb) {
-      int sa = (budget - sb * a.b_bytes) / kASlotBytes;
-      if (sa > 12) sa = 12;
-      sa -= sa % a.T;
-      if (sa < 2 * a.T) break;
-      const float ta = 2.9f / (float)(sa / a.T), tb = 2.0f / (float)sb;
-      const float t = ta > tb ? ta : tb;
-      if (t < best - 1e-6f) { best = t; best_sa = sa; best_sb = sb; }
+    int force = 0;
+    if (const char* e = getenv("B2M_CPS")) force = atoi(e);
+    float best_cost = 1e30f;
+    a.a_slots = 0;
+    for (int cps = 1; cps <= 2; ++cps) {
+      if (cps > 1 && (a.kpack != 1 || nch < 2)) break;
+      if ((force == 1 || force == 2) && a.kpack == 1 && nch >= 2 && cps != force) continue;
+      int a_slot = 0, b_slot = 0;
+      for (int ch = 0; ch < cps; ++ch) {            // the first stage of an offset is the largest
+        const bool full = (a.kpack > 1) || ch < a.nfull;
+        a_slot += full ? kASlotBytes : kASlotBytes / 2;
+        b_slot += a.ntile * (full ? 128 : 64);
+      }
+      int best_sa = 0, best_sb = 0;
+      float best = 1e30f;
+      for (int sb = 2; sb <= 12; ++sb) {
+        int sa = (budget - sb * b_slot) / a_slot;
+        if (sa > 12) sa = 12;
+        sa -= sa % a.T;
+        if (sa < 2 * a.T) break;
+        const float ta = 2.9f / (float)(sa / a.T), tb = 2.0f / (float)sb;
+        const float t = ta > tb ? ta : tb;
+        if (t < best - 1e-6f) { best = t; best_sa = sa; best_sb = sb; }
+      }
+      if (best_sa == 0) continue;
+      const int ncg = (nch + cps - 1) / cps;
+      const float cost = (float)ncg * (best > 0.5f ? best : 0.5f);
+      if (cost <= best_cost + 1e-6f) {
+        best_cost = cost;
+        a.cps = cps; a.ncg = ncg; a.a_slot_bytes = a_slot; a.b_bytes = b_slot; a.a_slots = best_sa; a.b_slots = best_sb;
+      }
     }
-    if (best_sa == 0) return B2M_ERR_UNSUPPORTED_SHAPE;
-    a.a_slots = best_sa;
-    a.b_slots = best_sb;
+    if (a.a_slots == 0) return B2M_ERR_UNSUPPORTED_SHAPE;
   }
-  a.off_b = a.a_slots * kASlotBytes;
+  a.off_b = a.a_slots * a.a_slot_bytes;
   a.off_stage = a.off_b + a.b_slots * a.b_bytes;
   a.off_csum = (a.off_stage + stage_bytes + 15) / 16 * 16;
   a.off_bars = (a.off_csum + csum_bytes + 15) / 16 * 16;

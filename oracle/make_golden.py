@@ -122,9 +122,61 @@ def golden_net():
     np.savez_compressed(os.path.join(OUT, "selection_net_small.npz"), **out)
     print({k: float(v) for k, v in out.items() if k.startswith("loss_")})
 
+def decode_inputs(seed=11):
+    """A small seeded batch + head outputs whose boxes form clusters (shared by the golden and the tests)."""
+    from box2mask_b200.synthetic import make_batch
+    batch = make_batch(2, seed=seed, scale=0.3, density=6.0e3)
+    rng = np.random.default_rng(seed)
+    loc = batch["input_location"].numpy()
+    s = len(loc)
+    centres = rng.uniform(0.2, 1.2, (2, 7, 3)).astype(np.float32)          # 7 object centres per scene
+    sizes = rng.uniform(0.15, 0.5, (2, 7, 3)).astype(np.float32)
+    which = rng.integers(0, 7, s)
+    b = batch["batch_ids"].numpy()
+    c = centres[b, which] + rng.normal(0, 0.03, (s, 3)).astype(np.float32)
+    pred = {
+        "mlp_offsets": torch.from_numpy((c - loc).astype(np.float32)),
+        "mlp_bounds": torch.from_numpy((sizes[b, which] * rng.uniform(0.85, 1.15, (s, 3))).astype(np.float32)),
+        "mlp_bb_scores": torch.from_numpy(rng.normal(0, 2, (s, 1)).astype(np.float32)),
+        "mlp_semantics": torch.from_numpy(rng.normal(0, 1, (s, 20)).astype(np.float32)),
+    }
+    batch["vox2point"] = [torch.from_numpy(rng.integers(0, len(sv), int(1.5 * len(sv)))).long() for sv in batch["seg2vox"]]
+    return batch, pred
+
+
+def golden_decode():
+    """The reference's own detection2mask (models/detection_net.py:369-488, CPU torch loops) on decode_inputs()."""
+    from types import SimpleNamespace
+    from box2mask_b200.selection_net import default_config
+    from box2mask_b200.synthetic import label_maps
+    from oracle import me_shim
+    me_shim.install()
+    sys.path.insert(0, REF)
+    import models.detection_net as ref_det
+    cfg = default_config()
+    valid, _, is_fg = label_maps(20)
+    batch, pred = decode_inputs()
+    stub = SimpleNamespace(semantic_valid_class_ids=valid, is_foreground=is_fg, requires_voxel_outputs=False)
+    out = {}
+    for mode in ("eval", "train"):
+        res = ref_det.SelectionNet.detection2mask(stub, batch, {k: v.clone() for k, v in pred.items()}, cfg, mode, True,
+                                                  *cfg.eval_ths)
+        for name, r in res.items():
+            out["%s_%s_conf" % (mode, name)] = np.asarray(r["conf"], dtype=np.float32)
+            out["%s_%s_label_id" % (mode, name)] = np.asarray(r["label_id"], dtype=np.int32)
+            out["%s_%s_mask" % (mode, name)] = np.packbits(np.asarray(r["mask"], dtype=bool), axis=1)
+            out["%s_%s_mask_shape" % (mode, name)] = np.array(r["mask"].shape)
+            if mode == "train":
+                out["train_%s_reps" % name] = np.asarray(r["cluster_representatives"], dtype=np.int64)
+                out["train_%s_bbs" % name] = np.asarray(r["bbs"], dtype=np.float32)
+            print(mode, name, "instances", len(r["conf"]), "mask", tuple(r["mask"].shape))
+    np.savez_compressed(os.path.join(OUT, "decode_small.npz"), **out)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference not mounted at %s" % REF)
     os.makedirs(OUT, exist_ok=True)
     golden_nms()
     golden_net()
+    golden_decode()

@@ -396,3 +396,31 @@ def test_heatmap_project_and_mask_nms(golden_dir):
     # the fixture's own mask-NMS result (masks = heat > 0.3 in fg space)
     keep2 = ops.mask_nms(ops.pack_masks_torch((heat > 0.3).to(DEV)), 0.6)
     assert np.array_equal(torch.nonzero(keep2).flatten().cpu().numpy(), g["mask_keep"])
+
+
+def test_detection2mask_matches_reference_golden(golden_dir):
+    """The GPU decode (box2mask_b200.decode.detection2mask: NMS clustering, heat-map projection, mask-NMS, label vote,
+    point projection) against the reference's own detection2mask run on the CPU (tests/golden/decode_small.npz)."""
+    from types import SimpleNamespace
+    from box2mask_b200 import decode
+    from box2mask_b200.selection_net import default_config
+    from box2mask_b200.synthetic import label_maps
+    from oracle.make_golden import decode_inputs
+    g = np.load(os.path.join(golden_dir, "decode_small.npz"))
+    cfg = default_config()
+    valid, _, is_fg = label_maps(20)
+    batch, pred = decode_inputs()
+    net = SimpleNamespace(device=DEV, semantic_valid_class_ids=valid, is_foreground=is_fg)
+    for mode in ("eval", "train"):
+        res = decode.detection2mask(net, batch, pred, cfg, mode, True, *cfg.eval_ths)
+        for scene in batch["scene"]:
+            name, r = scene["name"], res[scene["name"]]
+            # scores go through sigmoid on the device: allow the last ulp, everything discrete must be identical
+            assert np.allclose(r["conf"].numpy(), g["%s_%s_conf" % (mode, name)], rtol=0, atol=2e-7)
+            assert np.array_equal(np.asarray(r["label_id"]), g["%s_%s_label_id" % (mode, name)])
+            shape = tuple(g["%s_%s_mask_shape" % (mode, name)])
+            ref = np.unpackbits(g["%s_%s_mask" % (mode, name)], axis=1)[:, :shape[1]].astype(bool)
+            assert tuple(r["mask"].shape) == shape
+            assert np.array_equal(r["mask"].numpy(), ref)
+            if mode == "train":
+                assert np.array_equal(r["cluster_representatives"].numpy(), g["train_%s_reps" % name])

@@ -11,6 +11,37 @@ from oracle import sparse_ops as so
 
 
 # ------------------------------------------------------------------------------------------------
+# whole-scene decode: the oracle against the fixture produced by the reference's own detection2mask
+# (models/detection_net.py:369-488, run unmodified in the build container by oracle/make_golden.py)
+# ------------------------------------------------------------------------------------------------
+def test_decode_scene_matches_reference_detection2mask(golden_dir):
+    from box2mask_b200.selection_net import default_config
+    from box2mask_b200.synthetic import label_maps
+    from oracle.make_golden import decode_inputs
+    g = np.load(os.path.join(golden_dir, "decode_small.npz"))
+    cfg = default_config()
+    valid, _, is_fg = label_maps(20)
+    batch, pred = decode_inputs()
+    boxes = onms.to_boxes(batch["input_location"], pred["mlp_offsets"], pred["mlp_bounds"],
+                          torch.sigmoid(pred["mlp_bb_scores"]))
+    sem = valid[torch.argmax(pred["mlp_semantics"], 1)].long()
+    for b, scene in enumerate(batch["scene"]):
+        m = batch["batch_ids"] == b
+        fg = is_fg(sem[m])
+        r = onms.decode_scene(boxes[m][fg], fg, batch["seg2vox"][b], sem[m], *cfg.eval_ths)
+        name = scene["name"]
+        assert np.array_equal(r["conf"].numpy(), g["train_%s_conf" % name])
+        assert np.array_equal(r["label_id"], g["train_%s_label_id" % name])
+        assert np.array_equal(r["representatives"].numpy(), g["train_%s_reps" % name])
+        shape = tuple(g["train_%s_mask_shape" % name])
+        ref_mask = np.unpackbits(g["train_%s_mask" % name], axis=1)[:, :shape[1]].astype(bool)
+        assert np.array_equal(r["mask"].numpy(), ref_mask)
+        shape = tuple(g["eval_%s_mask_shape" % name])
+        ref_pts = np.unpackbits(g["eval_%s_mask" % name], axis=1)[:, :shape[1]].astype(bool)
+        assert np.array_equal(r["mask"][:, batch["vox2point"][b]].numpy(), ref_pts)
+
+
+# ------------------------------------------------------------------------------------------------
 # NMS: bit-exact against fixtures produced by the reference's own models/iou_nms.py
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["nms_small", "nms_medium", "nms_lowth"])
