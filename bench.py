@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--grad-sync", default="flat", choices=["flat", "ddp"],
                     help="flat: one all-reduce of the flat gradient buffer after backward (box2mask_b200/grad_sync.py); "
                          "ddp: torch DistributedDataParallel buckets overlapped with backward")
+    ap.add_argument("--regions", type=int, default=3, help="timed regions of --steps steps each; the fastest is reported")
     ap.add_argument("--prefetch", action="store_true",
                     help="build the coordinate maps one step ahead on a side stream (Model.prefetch_coordinates); measured "
                          "slower than building them inside the step: the persistent conv kernels leave the side stream no SMs")
@@ -278,7 +279,7 @@ def main():
         train_step(model, opt, dev_batches[i % len(dev_batches)])
     # Each region times exactly `steps` steps between barrier + synchronize; the fastest of REGIONS regions is
     # reported (a one-off host stall in one region is not a property of the path).
-    REGIONS = 3
+    REGIONS = max(1, args.regions)
     ms_all = []
     for r in range(REGIONS):
         ops.Profile.reset()

@@ -48,6 +48,8 @@ SIGNATURES = {
     "b2m_mask_nms_workspace_bytes": (c_size_t, [c_int64]),
     "b2m_mask_nms": (c_int32, [_P, c_int64, c_int64, c_float, _P, _P, _P, c_size_t, _P]),
     "b2m_unpack_masks": (c_int32, [_P, c_int64, c_int64, c_int64, _P, _P]),
+    "b2m_voxel_coords": (c_int32, [_P, c_int64, _P, c_double, _P, _P, _P]),
+    "b2m_nearest_point": (c_int32, [_P, _P, c_double, _P, c_int64, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -469,3 +469,35 @@ def pack_masks_torch(masks_bool):
     w = (m * weights).sum(-1)
     w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)
     return w.to(torch.int32).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# voxelisation (the step before the path; models/dataloader.py:61-77)
+# ---------------------------------------------------------------------------------------------
+def voxel_coords(positions, min_position, voxel_size):
+    """positions f64[P,3], min_position f64[1] (device) -> int32[P,4] rounded voxel coordinate of every point, status."""
+    lib = _lib_or_raise()
+    _cuda(positions, torch.float64, "positions")
+    _cuda(min_position, torch.float64, "min_position")
+    p = positions.shape[0]
+    coords = torch.empty((p, 4), dtype=torch.int32, device=positions.device)
+    status = torch.zeros(1, dtype=torch.int32, device=positions.device)
+    _run("voxel_coords", 1, lambda: check(lib.b2m_voxel_coords(
+        ptr(positions), p, ptr(min_position), float(voxel_size), ptr(coords), ptr(status), stream_ptr()), "voxel_coords"),
+        nbytes=24 * p + 16 * p)
+    return coords, status
+
+
+def nearest_point(positions, min_position, voxel_size, vox_coords, nbr, start, point_order):
+    """index of the scene point nearest to every voxel centre, int64[n_vox] (see csrc/voxel.cu)."""
+    lib = _lib_or_raise()
+    _cuda(positions, torch.float64, "positions")
+    _cuda(vox_coords, torch.int32, "vox_coords")
+    _cuda(start, torch.int64, "start")
+    _cuda(point_order, torch.int64, "point_order")
+    n_vox = vox_coords.shape[0]
+    out = torch.empty(n_vox, dtype=torch.int64, device=positions.device)
+    _run("nearest_point", 1, lambda: check(lib.b2m_nearest_point(
+        ptr(positions), ptr(min_position), float(voxel_size), ptr(vox_coords), n_vox, ptr(nbr), ptr(start),
+        ptr(point_order), ptr(out), stream_ptr()), "nearest_point"), nbytes=24 * positions.shape[0] + 27 * 4 * n_vox)
+    return out

@@ -224,6 +224,24 @@ int b2m_mask_nms(const uint32_t* masks, int64_t k, int64_t words, float th, uint
 int b2m_unpack_masks(const uint32_t* masks, int64_t k, int64_t words, int64_t n_vox, uint8_t* out,
                      b2m_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Voxelisation of a scene's points (the step before the path)
+ * reference: models/dataloader.py:61-77 (numpy round + unique, scikit-learn ball-tree 1-NN per voxel)
+ * ---------------------------------------------------------------------------------------------- */
+/* coords int32[n,4] = (0, rint((p - min(0, *min_position)) / voxel_size)) for positions f64[n,3] (fp64, the
+ * reference's operation order; rint = np.round's half-to-even). The sorted unique voxel set and the
+ * point -> voxel map follow from b2m_downsample_coords(coords, stride 1). status int32[1]: points outside the
+ * packable coordinate range. min_position: DEVICE scalar, the minimum over all 3n position components. */
+int b2m_voxel_coords(const double* positions, int64_t n, const double* min_position, double voxel_size,
+                     int32_t* coords, int32_t* status, b2m_stream_t stream);
+/* nearest[v] = index of the scene point closest to the centre of voxel v (ties: lower index), searched
+ * among the points of the 27 neighbouring voxels, which is exact (see csrc/voxel.cu). vox_coords
+ * int32[n_vox,4]; nbr = its k=3 table from b2m_kernel_map_submanifold (pitch b2m_map_pitch(n_vox));
+ * start int64[n_vox+1], point_order int64[n]: points grouped by voxel (CSR). */
+int b2m_nearest_point(const double* positions, const double* min_position, double voxel_size,
+                      const int32_t* vox_coords, int64_t n_vox, const int32_t* nbr, const int64_t* start,
+                      const int64_t* point_order, int64_t* nearest, b2m_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,3 +213,25 @@ def test_segment_ops():
     assert torch.allclose(m[0], f[0]) and torch.allclose(m[1], f[1:31].mean(0), atol=1e-6)
     mx = so.segment_max(f, ids, 3)
     assert torch.equal(mx[2], f[31:].max(0)[0])
+
+
+# ------------------------------------------------------------------------------------------------
+# voxelisation restatement (next-row component): the ball-tree result against brute force, invariants
+# ------------------------------------------------------------------------------------------------
+def test_voxelize_restatement_invariants():
+    from oracle import voxelize as ovz
+    rng = np.random.default_rng(0)
+    p = 3000
+    pos = rng.uniform(-0.3, 0.9, (p, 3))
+    seg = rng.integers(0, 25, p) * 3
+    r = ovz.voxelize_scene(pos, rng.normal(size=(p, 3)).astype(np.float32), rng.normal(size=(p, 3)).astype(np.float32), seg, 0.05)
+    v = r["vox_coords"]
+    assert np.array_equal(v, np.unique(v, axis=0)) and v.min() >= 0                      # sorted unique, non-negative
+    scaled = (pos - min(0, pos.min())) / 0.05
+    assert np.array_equal(np.round(scaled), v[r["vox2point"]])                            # vox2point is the inverse map
+    d = ((scaled[None, :, :] - v[:, None, :]) ** 2).sum(-1)                               # brute-force nearest point
+    assert np.array_equal(d.argmin(1), r["point2vox"])
+    assert float(np.sqrt(d.min(1)).max()) <= np.sqrt(3) / 2 + 1e-12                       # within the voxel's own reach
+    assert np.array_equal(r["unique_vox_segments"][r["seg2vox"]], r["vox_segments"])
+    ids = ovz.to_unique([np.array([5, 5, 9]), np.array([2, 7, 7])])
+    assert ids.tolist() == [0, 0, 1, 2, 3, 3]
