@@ -20,13 +20,15 @@
 //  conv_fwd_kernel   persistent, warp-specialised, output-stationary implicit GEMM.
 //      work item  = T (1 or 2) tiles of 128 output rows x <=256 output columns, accumulators in TMEM,
 //                   double-buffered across work items so the epilogue overlaps the next main loop.
-//      A stage    = 128 gathered rows x 64 (or the 32-wide remainder) reduction elements of one kernel offset;
-//                   for c_red in {16, 32} a stage holds 4 / 2 offsets as separate SW32 / SW64 sub-tiles.
-//      producers  = 12 warps, stage s belongs to warp s % 12: one 16-byte index load + one gather4 per lane.
-//      B loader   = one thread: 1-D bulk copies (TMA engine) of pre-swizzled weight slices; a slice is
-//                   shared by the T tiles of the work item.
+//      A stage    = 128 gathered rows x one or two 64-wide chunks (the 32-wide remainder counts as a chunk) of the
+//                   reduction of one kernel offset; for c_red in {16, 32} a stage holds 4 / 2 offsets as separate
+//                   SW32 / SW64 sub-tiles. The host picks chunks per stage and ring depths (b2m_conv_forward).
+//      producers  = 12 warps in groups of one warp per chunk of a stage; stage s belongs to group s % groups: one
+//                   16-byte index load + one gather4 per lane.
+//      B loader   = one thread: 1-D bulk copies (TMA engine) of the pre-swizzled weight slices of a stage; a weight
+//                   slot is shared by the T tiles of the work item.
 //      MMA issuers = one elected thread per tile of the work item: tcgen05.mma.cta_group::1.kind::f16, M=128,
-//                   N=ntile, K=16.
+//                   N=ntile, K=16. Its per-stage latency chain (~0.4 us) is what bounds the kernel.
 //      epilogue   = 4 warps: tcgen05.ld -> per-warp fp32 staging -> BatchNorm column statistics (fp64 atomics)
 //                   -> bf16 row stores (scattered through `order`).
 //      The same kernel computes dgrad (weights packed transposed / mirrored).
@@ -34,7 +36,7 @@
 //      rows when c_in <= 64), N = c_out, reduction over output rows in 64-row stages, both operands
 //      MN-major (a gathered row IS a run of M / N elements). One CTA owns up to G accumulators (G*N <= 512 TMEM
 //      columns) = G offset groups and a range of row groups; a dY stage is shared by the G gathers. fp32 vector
-//      atomics into dW at the end.
+//      atomics into dW at the end, transposed through shared memory so that a warp instruction touches 4 lines.
 #ifdef B2M_DEBUG_BUILD
 #define B2M_DEBUG_WAIT
 #endif
