@@ -113,6 +113,76 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
   }
 }
 #endif
+// The issuer's waits almost always find the barrier complete: test once on the fall-through path (a taken branch
+// costs a lone warp ~30 cycles, tools/umma_issue_bench.cu) and only then enter the bounded polling loop.
+__device__ __forceinline__ void mbar_wait_likely(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
+  if (__builtin_expect(mbar_try_wait(bar, parity) != 0u, 1)) return;
+  mbar_wait(bar, parity, tag);
+}
+// One pipeline stage of the forward / dgrad kernel in ONE straight-line block (no branches on the issue path):
+// chunk 0 at (a_lo, b_lo) and an optional chunk 1 at (a_lo + 16 KB, b_lo + b_chunk), each either a full 64-wide SW128
+// chunk (4 K = 16 steps, +32 bytes per step) or the 32-wide SW64 remainder (2 steps), then the two commits that
+// release the A slot and the weight slot. c0_rem != 0: chunk 0 is the 32-wide one; f1: 0 = no chunk 1, 1 = full,
+// 2 = 32-wide. Executed by the one elected thread.
+__device__ __forceinline__ void umma_stage_bf16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t b_chunk,
+                                                uint32_t idesc, uint32_t accumulate, uint32_t c0_rem, uint32_t f1,
+                                                uint32_t hi128, uint32_t hi64, uint32_t bar_a, uint32_t bar_b) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pacc, pt, p0f, p1, p1f;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 hi0, hi1, a1, b1, ta, tb;\n\t"
+      "setp.ne.b32 pacc, %5, 0;\n\t"
+      "setp.eq.b32 pt, %0, %0;\n\t"
+      "setp.eq.b32 p0f, %6, 0;\n\t"
+      "setp.ne.b32 p1, %7, 0;\n\t"
+      "setp.eq.b32 p1f, %7, 1;\n\t"
+      "selp.b32 hi0, %8, %9, p0f;\n\t"
+      "selp.b32 hi1, %8, %9, p1f;\n\t"
+      "mov.b64 da, {%1, hi0};\n\t"
+      "mov.b64 db, {%2, hi0};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pacc;\n\t"
+      "add.u32 ta, %1, 2;\n\t"
+      "add.u32 tb, %2, 2;\n\t"
+      "mov.b64 da, {ta, hi0};\n\t"
+      "mov.b64 db, {tb, hi0};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "add.u32 ta, %1, 4;\n\t"
+      "add.u32 tb, %2, 4;\n\t"
+      "mov.b64 da, {ta, hi0};\n\t"
+      "mov.b64 db, {tb, hi0};\n\t"
+      "@p0f tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "add.u32 ta, %1, 6;\n\t"
+      "add.u32 tb, %2, 6;\n\t"
+      "mov.b64 da, {ta, hi0};\n\t"
+      "mov.b64 db, {tb, hi0};\n\t"
+      "@p0f tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "add.u32 a1, %1, 1024;\n\t"
+      "add.u32 b1, %2, %3;\n\t"
+      "mov.b64 da, {a1, hi1};\n\t"
+      "mov.b64 db, {b1, hi1};\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "add.u32 ta, a1, 2;\n\t"
+      "add.u32 tb, b1, 2;\n\t"
+      "mov.b64 da, {ta, hi1};\n\t"
+      "mov.b64 db, {tb, hi1};\n\t"
+      "@p1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "add.u32 ta, a1, 4;\n\t"
+      "add.u32 tb, b1, 4;\n\t"
+      "mov.b64 da, {ta, hi1};\n\t"
+      "mov.b64 db, {tb, hi1};\n\t"
+      "@p1f tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "add.u32 ta, a1, 6;\n\t"
+      "add.u32 tb, b1, 6;\n\t"
+      "mov.b64 da, {ta, hi1};\n\t"
+      "mov.b64 db, {tb, hi1};\n\t"
+      "@p1f tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(b_chunk), "r"(idesc), "r"(accumulate), "r"(c0_rem), "r"(f1), "r"(hi128),
+        "r"(hi64), "r"(bar_a), "r"(bar_b) : "memory");
+}
 // cp.async 16 B global->shared, zero-filled when src_bytes == 0
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");

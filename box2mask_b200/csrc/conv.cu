@@ -45,6 +45,12 @@
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 
+#ifdef B2M_LEAN_ISSUER
+#define B2M_ISSUER_WAIT(bar, parity, tag) mbar_wait_likely(bar, parity, tag)
+#else
+#define B2M_ISSUER_WAIT(bar, parity, tag) mbar_wait(bar, parity, tag)
+#endif
+
 namespace b2m {
 
 // ------------------------------------------------------------------------------------------------
@@ -404,10 +410,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
             if (sub) {
               const int aslot = abase + ra.slot;
               if (me == 0 && nstage >= 32 && nstage < 44) B2M_TRACE(100 + (nstage - 32) * 4);
-              mbar_wait(b_full + 8 * rb.slot, rb.phase, 4);
+              B2M_ISSUER_WAIT(b_full + 8 * rb.slot, rb.phase, 4);
               if (me == 0 && nstage == 0) B2M_TRACE(19);
               if (me == 0 && nstage >= 32 && nstage < 44) B2M_TRACE(101 + (nstage - 32) * 4);
-              mbar_wait(a_full + 8 * aslot, ra.phase, 5);
+              B2M_ISSUER_WAIT(a_full + 8 * aslot, ra.phase, 5);
               tc_fence_after();
               if (me == 0 && nstage >= 32 && nstage < 44) B2M_TRACE(102 + (nstage - 32) * 4);
               if (me == 0 && nstage < 16) B2M_TRACE(40 + nstage);
@@ -420,6 +426,16 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                   // a stage holds one or two chunks of this offset: sub-tile j of the A slot (16 KB apart) against
                   // weight slice j of the B slot (ntile * 128 bytes apart)
                   const bool last = ((uint32_t)c == st_last);
+#ifdef B2M_LEAN_ISSUER
+                  if (!B2M_ABLATE(a, 1)) {
+                    // the whole stage, MMAs and both commits, as one straight-line block (common.cuh)
+                    umma_stage_bf16(d, a_cur, b_cur, st_c, idesc, acc, last ? last_c0_rem : 0u,
+                                    last ? last_c1 : (two ? 1u : 0u), hi128, hi64, a_empty + 8 * aslot, b_empty + 8 * rb.slot);
+                  } else {
+                    umma_commit(a_empty + 8 * aslot);
+                    umma_commit(b_empty + 8 * rb.slot);
+                  }
+#else
                   if (B2M_ABLATE(a, 1)) {
                   } else {
                     if (last && last_c0_rem) umma_chunk2(d, a_cur, b_cur, hi64, idesc, acc);
@@ -428,6 +444,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                     if (f1 == 1u) umma_chunk4(d, a_cur + (kASlotBytes >> 4), b_cur + st_c, hi128, idesc, 1u);
                     else if (f1 == 2u) umma_chunk2(d, a_cur + (kASlotBytes >> 4), b_cur + st_c, hi64, idesc, 1u);
                   }
+#endif
                 } else if (KPACK == 8) {
                   // 8 offsets x 8 channels side by side in one SW128 tile: a K=16 step covers a pair of offsets
                   uint32_t ac = acc;
@@ -452,8 +469,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
                     }
                   }
                 }
-                umma_commit(a_empty + 8 * aslot);
-                umma_commit(b_empty + 8 * rb.slot);            // arrives once this tile's MMAs on the slice are done
+#ifdef B2M_LEAN_ISSUER
+                if (KPACK != 1)
+#endif
+                {
+                  umma_commit(a_empty + 8 * aslot);
+                  umma_commit(b_empty + 8 * rb.slot);          // arrives once this tile's MMAs on the slice are done
+                }
               }
               if (me == 0 && nstage > 32 && nstage <= 44) B2M_TRACE(103 + (nstage - 33) * 4);
               acc = 1u;
