@@ -205,7 +205,8 @@ def main():
     if world > 1 and args.grad_sync == "ddp":
         # leave SMs for the NCCL all-reduce kernels that overlap the backward pass (persistent conv kernels otherwise
         # hold every SM and the collective forces a second wave of their CTAs)
-        os.environ.setdefault("B2M_MAX_CTAS", "132")
+        from box2mask_b200 import _lib as _b2m_lib
+        _b2m_lib.set_option(_b2m_lib.OPT_MAX_CTAS, 132)
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)

@@ -16,6 +16,7 @@ _P = c_void_p  # every device pointer travels as void*
 SIGNATURES = {
     "b2m_version": (c_int32, []),
     "b2m_error_string": (c_char_p, [c_int32]),
+    "b2m_set_option": (c_int32, [c_int32, c_int64]),
     "b2m_hash_capacity": (c_int64, [c_int64]),
     "b2m_hash_build": (c_int32, [_P, c_int64, _P, _P, c_int64, _P, _P]),
     "b2m_hash_query": (c_int32, [_P, c_int64, _P, _P, c_int64, _P, _P]),
@@ -37,10 +38,11 @@ SIGNATURES = {
     "b2m_bn_forward": (c_int32, [_P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, c_float, c_float, c_int32, _P, c_int32,
                                  _P, _P, _P, _P]),
     "b2m_bn_backward_reduce": (c_int32, [_P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P, _P]),
-    "b2m_bn_backward_apply": (c_int32, [_P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P, _P, c_int32, c_int32, _P, _P, _P,
-                                        _P, _P]),
+    "b2m_bn_backward_apply": (c_int32, [_P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_int32, c_int32, _P,
+                                        _P, _P, _P, _P]),
     "b2m_segment_mean_forward": (c_int32, [_P, _P, c_int64, c_int32, c_int64, _P, _P, _P]),
-    "b2m_segment_mean_backward": (c_int32, [_P, _P, _P, c_int64, c_int32, _P, _P]),
+    "b2m_segment_mean_backward": (c_int32, [_P, _P, _P, c_int64, c_int32, c_int64, _P, _P]),
+    "b2m_segment_max_backward": (c_int32, [_P, _P, c_int64, c_int32, c_int64, _P, _P]),
     "b2m_segment_max_forward": (c_int32, [_P, _P, c_int64, c_int32, c_int64, _P, _P, _P]),
     "b2m_nms_workspace_bytes": (c_size_t, [c_int64]),
     "b2m_aabb_nms": (c_int32, [_P, c_int64, c_float, _P, _P, _P, _P, c_int64, _P, c_size_t, _P]),
@@ -90,6 +92,14 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+OPT_MAX_CTAS, OPT_CHUNKS_PER_STAGE, OPT_SPLIT_OFFSETS = 1, 2, 3
+
+
+def set_option(option, value):
+    check(load().b2m_set_option(int(option), int(value)), "set_option")
+
+
+def stream_ptr(device=None):
+    """Current CUDA stream of `device` (default: the current device) as a void*."""
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1123,23 +1123,42 @@ static bool make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int co
 // ------------------------------------------------------------------------------------------------
 using namespace b2m;
 
-// Number of CTAs the persistent convolution kernels launch: one per SM, or B2M_MAX_CTAS from the environment
-// (read once). Data-parallel training sets it below the SM count so that the NCCL all-reduce kernels that overlap
-// the backward pass find free SMs instead of forcing a second wave of conv CTAs.
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-    const char* e = getenv("B2M_MAX_CTAS");
-    if (e) {
-      const int v = atoi(e);
-      if (v > 0 && v < g_num_sms) g_num_sms = v;
-    }
+// Per-device cache (indexed by the CUDA device ordinal): SM count and whether the kernels' dynamic shared memory
+// opt-in has been made on that device (cudaFuncSetAttribute is per device). Filled on first use by whichever thread
+// gets there first; the values are idempotent, so a race only repeats the same calls.
+constexpr int kMaxDevices = 64;
+struct DeviceCache { int sms; bool fwd_attr, wg_attr; };
+static DeviceCache g_dev[kMaxDevices];
+static DeviceCache* device_cache() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  DeviceCache* d = &g_dev[dev];
+  if (d->sms == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    d->sms = n > 0 ? n : 148;
   }
-  return g_num_sms;
+  return d;
+}
+// Explicit process-wide tuning options (b2m_set_option), replacing round 1's getenv calls inside the C-ABI.
+//   B2M_OPT_MAX_CTAS: upper bound on the CTAs the persistent convolution kernels launch (0 = one per SM). Data-parallel
+//   training lowers it while a gradient all-reduce runs on a side stream, so that the NCCL kernels find free SMs
+//   instead of forcing a second wave of conv CTAs.
+//   B2M_OPT_CHUNKS_PER_STAGE: force 1 or 2 64-wide chunks per pipeline stage of the forward kernel (0 = automatic).
+//   B2M_OPT_SPLIT_OFFSETS: 0 = automatic offset splitting on levels with few row tiles, 1 = never split (tests).
+static int g_opt_max_ctas = 0, g_opt_cps = 0, g_opt_nosplit = 0;
+static int num_sms() {
+  const int sms = device_cache()->sms;
+  const int cap = g_opt_max_ctas;
+  return (cap > 0 && cap < sms) ? cap : sms;
+}
+extern "C" int b2m_set_option(int32_t option, int64_t value) {
+  switch (option) {
+    case B2M_OPT_MAX_CTAS: g_opt_max_ctas = value > 0 ? (int)value : 0; return B2M_OK;
+    case B2M_OPT_CHUNKS_PER_STAGE: g_opt_cps = (value == 1 || value == 2) ? (int)value : 0; return B2M_OK;
+    case B2M_OPT_SPLIT_OFFSETS: g_opt_nosplit = value ? 1 : 0; return B2M_OK;
+    default: return B2M_ERR_INVALID_ARGUMENT;
+  }
 }
 
 #ifdef B2M_DEBUG_WAIT
@@ -1242,8 +1261,7 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   {
     const int nch = a.nfull + a.rem;
     const int budget = 227 * 1024 - 1024 - 256 - stage_bytes - csum_bytes - 16 * 32;
-    int force = 0;
-    if (const char* e = getenv("B2M_CPS")) force = atoi(e);
+    const int force = g_opt_cps;
     float best_cost = 1e30f;
     a.a_slots = 0;
     for (int cps = 1; cps <= 2; ++cps) {
@@ -1292,14 +1310,14 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   if (!make_row_map(&tm_main, x, n_in, c_red, a.kpack > 1 ? c_red : 64)) return B2M_ERR_CUDA_LAUNCH;
   if (a.rem) { if (!make_row_map(&tm_rem, x, n_in, c_red, 32)) return B2M_ERR_CUDA_LAUNCH; }
   else tm_rem = tm_main;
-  static bool attr_set = false;
-  if (!attr_set) {
+  DeviceCache* dc = device_cache();
+  if (!dc->fwd_attr) {
     if (cudaFuncSetAttribute(conv_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(conv_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(conv_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(conv_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return B2M_ERR_CUDA_LAUNCH;
-    attr_set = true;
+    dc->fwd_attr = true;
   }
   int gx = sms / ntiles_n;                                  // keep the total CTA count near one per SM
   if (gx < 1) gx = 1;
@@ -1364,11 +1382,11 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
   CUtensorMap tm_x, tm_dy;
   if (!make_row_map(&tm_x, x, n_in, c_in, a.cpad == 8 ? 8 : a.wa / 2)) return B2M_ERR_CUDA_LAUNCH;   // unused when cpad == 8
   if (!make_row_map(&tm_dy, dy, n_out, c_out, a.wb / 2)) return B2M_ERR_CUDA_LAUNCH;
-  static bool attr_set = false;
-  if (!attr_set) {
+  DeviceCache* dc = device_cache();
+  if (!dc->wg_attr) {
     if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return B2M_ERR_CUDA_LAUNCH;
-    attr_set = true;
+    dc->wg_attr = true;
   }
   dim3 grid((unsigned)columns, (unsigned)splits, (unsigned)mtiles);
   conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>(tm_x, tm_dy, a);

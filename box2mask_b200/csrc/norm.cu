@@ -124,6 +124,8 @@ bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int64_t n_stat, int c
   const int rpp = kNormThreads / G;
   const int g = threadIdx.x % G, rl = threadIdx.x / G;
   if (rl >= rpp) return;
+  // SyncBatchNorm: the global row count travels with the all-reduced sums (element 2c), no host round trip
+  if (training && n_stat <= 0) n_stat = (int64_t)llrint(sums[2 * c]);
   float mu[8], sc[8], be[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -193,16 +195,22 @@ bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int64_t n_stat, int c
 __global__ void __launch_bounds__(kNormThreads)
 bn_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ out, const uint16_t* __restrict__ dout,
                     int64_t n, int64_t n_stat, int c, const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ gamma, const double* __restrict__ red, int relu, int training,
+                    const float* __restrict__ gamma, const double* __restrict__ red,
+                    const double* __restrict__ red_local, const double* __restrict__ n_stat_dev, int relu, int training,
                     uint16_t* __restrict__ dx, uint16_t* __restrict__ dres, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
   const int G = c / 8;
+  // The affine gradients come from THIS rank's reduction (red_local): torch's SyncBatchNorm keeps grad_weight /
+  // grad_bias local and lets the gradient all-reduce average them like every other parameter; only dx needs the
+  // global (sum g, sum g*xhat) in `red`.
   if (blockIdx.x == 0) {
+    const double* rl_ = red_local ? red_local : red;
     for (int j = threadIdx.x; j < c; j += blockDim.x) {
-      if (dbeta) dbeta[j] = (float)red[j];
-      if (dgamma) dgamma[j] = (float)red[c + j];
+      if (dbeta) dbeta[j] = (float)rl_[j];
+      if (dgamma) dgamma[j] = (float)rl_[c + j];
     }
   }
+  if (n_stat_dev) n_stat = (int64_t)llrint(*n_stat_dev);
   const int rpp = kNormThreads / G;
   const int g = threadIdx.x % G, rl = threadIdx.x / G;
   if (rl >= rpp) return;
@@ -335,14 +343,16 @@ extern "C" int b2m_bn_backward_reduce(const uint16_t* x, const uint16_t* out, co
 extern "C" int b2m_bn_backward_apply(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n,
                                      int64_t n_stat, int32_t c,
                                      const float* save_mean, const float* save_invstd, const float* gamma,
-                                     const double* red, int32_t relu, int32_t training, uint16_t* dx,
+                                     const double* red, const double* red_local, const double* n_stat_dev,
+                                     int32_t relu, int32_t training, uint16_t* dx,
                                      uint16_t* dresidual, float* dgamma, float* dbeta, b2m_stream_t stream) {
   if (!x || !dout || !save_mean || !save_invstd || !gamma || !red || !dx || n < 0) return B2M_ERR_INVALID_ARGUMENT;
   if (relu && !out) return B2M_ERR_INVALID_ARGUMENT;
   if (!norm_shape_ok(c)) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n == 0) return B2M_OK;
   bn_bwd_apply_kernel<<<apply_grid(n, c), kNormThreads, 0, (cudaStream_t)stream>>>(
-      x, out, dout, n, n_stat, c, save_mean, save_invstd, gamma, red, relu, training, dx, dresidual, dgamma, dbeta);
+      x, out, dout, n, n_stat, c, save_mean, save_invstd, gamma, red, red_local, n_stat_dev, relu, training, dx, dresidual,
+      dgamma, dbeta);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }

@@ -8,23 +8,53 @@
 
 namespace b2m {
 
-__global__ void segsum_kernel(const uint16_t* __restrict__ f, const int64_t* __restrict__ ids, int64_t n, int c,
-                              int64_t s, float* __restrict__ out, float* __restrict__ counts) {
+// Segmented reduction of one 64-row tile per block iteration: the tile is staged in shared memory with coalesced
+// 16-byte loads, then thread (column, row quarter) walks its 16 rows in order and keeps a running sum while the
+// superpoint id stays the same; only a change of id (or the end of the quarter) costs a global fp32 reduction.
+// Superpoints are spatial patches and rows arrive in coordinate order, so consecutive rows mostly share an id:
+// the atomics drop from one per element to one per (run, column), and a warp's reductions still cover 128
+// contiguous bytes of one accumulator row.
+constexpr int kSegRows = 64;
+constexpr int kSegQuarter = 16;
+__global__ void __launch_bounds__(512)
+segsum_kernel(const uint16_t* __restrict__ f, const int64_t* __restrict__ ids, int64_t n, int c,
+              int64_t s, float* __restrict__ out, float* __restrict__ counts) {
+  extern __shared__ uint8_t seg_smem[];
+  uint16_t* tile = reinterpret_cast<uint16_t*>(seg_smem);                                   // [64][c] bf16
+  int64_t* tid_s = reinterpret_cast<int64_t*>(seg_smem + (size_t)kSegRows * c * 2);         // [64]
   const int G = c / 8;
-  const int64_t total = n * G;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = v / G;
-    const int g = (int)(v % G);
-    const int64_t id = __ldg(ids + r);
-    if (id < 0 || id >= s) continue;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(f) + v);
-    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
-    const float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
-    const float2 cc = __bfloat1622float2(p[2]), d = __bfloat1622float2(p[3]);
-    float* dst = out + id * c + g * 8;
-    atomicAdd(reinterpret_cast<float4*>(dst), make_float4(a.x, a.y, b.x, b.y));
-    atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(cc.x, cc.y, d.x, d.y));
-    if (g == 0) atomicAdd(counts + id, 1.f);
+  const int64_t n_tiles = (n + kSegRows - 1) / kSegRows;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t r0 = t * kSegRows;
+    const int rows = (int)min((int64_t)kSegRows, n - r0);
+    for (int v = threadIdx.x; v < rows * G; v += blockDim.x)
+      reinterpret_cast<uint4*>(tile)[v] = __ldg(reinterpret_cast<const uint4*>(f + r0 * c) + v);
+    for (int r = threadIdx.x; r < kSegRows; r += blockDim.x) tid_s[r] = (r < rows) ? __ldg(ids + r0 + r) : -1;
+    __syncthreads();
+    for (int w = threadIdx.x; w < 4 * c; w += blockDim.x) {
+      const int col = w % c, q = w / c;
+      const int rb = q * kSegQuarter, re = min(rows, rb + kSegQuarter);
+      float acc = 0.f;
+      int run = 0;
+      int64_t cur = -1;
+      for (int r = rb; r < re; ++r) {
+        const int64_t id = tid_s[r];
+        if (id != cur) {
+          if (run > 0 && cur >= 0 && cur < s) {
+            atomicAdd(out + cur * c + col, acc);
+            if (col == 0) atomicAdd(counts + cur, (float)run);
+          }
+          cur = id; acc = 0.f; run = 0;
+        }
+        acc += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(tile)[r * c + col]);
+        ++run;
+      }
+      if (run > 0 && cur >= 0 && cur < s) {
+        atomicAdd(out + cur * c + col, acc);
+        if (col == 0) atomicAdd(counts + cur, (float)run);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -36,13 +66,18 @@ __global__ void segdiv_kernel(float* __restrict__ out, const float* __restrict__
 }
 
 __global__ void segmean_bwd_kernel(const float* __restrict__ dout, const int64_t* __restrict__ ids,
-                                   const float* __restrict__ counts, int64_t n, int c, uint16_t* __restrict__ df) {
+                                   const float* __restrict__ counts, int64_t n, int c, int64_t s,
+                                   uint16_t* __restrict__ df) {
   const int G = c / 8;
   const int64_t total = n * G;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = v / G;
     const int g = (int)(v % G);
     const int64_t id = __ldg(ids + r);
+    if (id < 0 || id >= s) {      // rows the forward pass skipped (ignore ids) receive no gradient
+      reinterpret_cast<uint4*>(df)[v] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
     const float inv = 1.f / __ldg(counts + id);
     const float4 a = __ldg(reinterpret_cast<const float4*>(dout + id * c + g * 8));
     const float4 b = __ldg(reinterpret_cast<const float4*>(dout + id * c + g * 8 + 4));
@@ -89,6 +124,16 @@ __global__ void segmax_finish_kernel(float* __restrict__ out, int64_t total) {
   out[gid] = key_float(reinterpret_cast<const int*>(out)[gid]);
 }
 
+// backward of the segment max: df[argmax[s, j], j] = dout[s, j], everything else zero (df zeroed by the caller side)
+__global__ void segmax_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ argmax, int64_t total, int c,
+                                  int64_t n, uint16_t* __restrict__ df) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int32_t r = argmax[gid];
+  if (r < 0 || r >= n) return;                       // empty segment
+  reinterpret_cast<__nv_bfloat16*>(df)[(int64_t)r * c + (gid % c)] = __float2bfloat16_rn(dout[gid]);
+}
+
 }  // namespace b2m
 
 using namespace b2m;
@@ -109,7 +154,13 @@ extern "C" int b2m_segment_mean_forward(const uint16_t* f, const int64_t* ids, i
   if (cudaMemsetAsync(out, 0, (size_t)s * c * 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
   if (cudaMemsetAsync(counts, 0, (size_t)s * 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
   if (n == 0) return B2M_OK;
-  segsum_kernel<<<pool_grid(n * (c / 8)), 256, 0, st>>>(f, ids, n, c, s, out, counts);
+  {
+    const int64_t n_tiles = (n + kSegRows - 1) / kSegRows;
+    const int grid = (int)(n_tiles < 148 * 4 ? n_tiles : 148 * 4);
+    const size_t sh = (size_t)kSegRows * c * 2 + kSegRows * 8;
+    if (sh > 48 * 1024) return B2M_ERR_UNSUPPORTED_SHAPE;
+    segsum_kernel<<<grid, 512, sh, st>>>(f, ids, n, c, s, out, counts);
+  }
   B2M_CHECK_LAUNCH();
   segdiv_kernel<<<cdiv(s * c, 256), 256, 0, st>>>(out, counts, s, c);
   B2M_CHECK_LAUNCH();
@@ -117,11 +168,11 @@ extern "C" int b2m_segment_mean_forward(const uint16_t* f, const int64_t* ids, i
 }
 
 extern "C" int b2m_segment_mean_backward(const float* dout, const int64_t* ids, const float* counts, int64_t n, int32_t c,
-                                         uint16_t* df, b2m_stream_t stream) {
-  if (!dout || !ids || !counts || !df || n < 0) return B2M_ERR_INVALID_ARGUMENT;
+                                         int64_t s, uint16_t* df, b2m_stream_t stream) {
+  if (!dout || !ids || !counts || !df || n < 0 || s < 0) return B2M_ERR_INVALID_ARGUMENT;
   if (c <= 0 || c % 8 != 0) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n == 0) return B2M_OK;
-  segmean_bwd_kernel<<<pool_grid(n * (c / 8)), 256, 0, (cudaStream_t)stream>>>(dout, ids, counts, n, c, df);
+  segmean_bwd_kernel<<<pool_grid(n * (c / 8)), 256, 0, (cudaStream_t)stream>>>(dout, ids, counts, n, c, s, df);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }
@@ -141,6 +192,20 @@ extern "C" int b2m_segment_max_forward(const uint16_t* f, const int64_t* ids, in
   segargmax_kernel<<<cdiv(n * c, 256), 256, 0, st>>>(f, ids, n, c, s, reinterpret_cast<const int*>(out), argmax);
   B2M_CHECK_LAUNCH();
   segmax_finish_kernel<<<cdiv(s * c, 256), 256, 0, st>>>(out, s * c);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+/* df bf16[n, c]: gradient of b2m_segment_max_forward (a row receives dout[s, j] iff it attained the maximum of (s, j)) */
+extern "C" int b2m_segment_max_backward(const float* dout, const int32_t* argmax, int64_t s, int32_t c, int64_t n,
+                                        uint16_t* df, b2m_stream_t stream) {
+  if (!dout || !argmax || !df || n < 0 || s < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (c <= 0) return B2M_ERR_UNSUPPORTED_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) return B2M_OK;
+  if (cudaMemsetAsync(df, 0, (size_t)n * c * 2, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  if (s == 0) return B2M_OK;
+  segmax_bwd_kernel<<<cdiv(s * c, 256), 256, 0, st>>>(dout, argmax, s * c, c, n, df);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }

@@ -67,36 +67,53 @@ class BatchNormFn(torch.autograd.Function):
                 sync_group):
         n = x.shape[0]
         n_stat = n
+        count = None
         if training:
             if sums is None:
                 sums = ops.colstats(x)
             if sync_group is not None:
-                sums, n_stat = sync_bn_stats(sums, n, sync_group)
-            if n_stat <= 1:
+                # global (sum, sum of squares, row count) in ONE all-reduce; the count stays on the device
+                # (n_stat = 0 tells the kernels to read it from sums[2c]): no host sync per layer
+                sums = sync_bn_stats(sums, n, sync_group)
+                count = sums[-1:]
+                n_stat = 0
+            elif n_stat <= 1:
                 raise ValueError("Expected more than 1 value per channel when training")
         out, save_mean, save_invstd = ops.bn_forward(x, sums, gamma.detach(), beta.detach(), running_mean, running_var,
                                                      momentum, eps, training, residual, relu, n_stat)
-        ctx.save_for_backward(x, out, save_mean, save_invstd, gamma)
+        if count is not None:
+            ctx.save_for_backward(x, out, save_mean, save_invstd, gamma, count)
+        else:
+            ctx.save_for_backward(x, out, save_mean, save_invstd, gamma)
         ctx.relu, ctx.training, ctx.has_res, ctx.n_stat, ctx.sync_group = relu, training, residual is not None, n_stat, sync_group
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, out, save_mean, save_invstd, gamma = ctx.saved_tensors
+        x, out, save_mean, save_invstd, gamma = ctx.saved_tensors[:5]
+        count = ctx.saved_tensors[5] if len(ctx.saved_tensors) > 5 else None
         hook = None
         if ctx.sync_group is not None and ctx.training:
-            hook = lambda red: torch.distributed.all_reduce(red, group=ctx.sync_group)  # noqa: E731
+            def hook(red):
+                # only dx needs the global reduction; bn.weight / bn.bias gradients stay local like torch's
+                # SyncBatchNorm (the gradient all-reduce then averages them with every other parameter)
+                tot = red.clone()
+                torch.distributed.all_reduce(tot, group=ctx.sync_group)
+                return tot
         dx, dres, dgamma, dbeta = ops.bn_backward(x, out, dout.contiguous(), save_mean, save_invstd, gamma.detach(),
-                                                  ctx.relu, ctx.training, ctx.has_res, ctx.n_stat, hook)
+                                                  ctx.relu, ctx.training, ctx.has_res, ctx.n_stat, hook, count)
         return dx, None, dgamma, dbeta, None, None, None, None, None, dres, None, None
 
 
 def sync_bn_stats(sums, n, group):
-    """All-reduce the per-column (sum, sum of squares) and the row count over the ranks of `group`.
-    Returns (global sums, global n). One collective of 2C+1 doubles (SyncBN forward, models/model.py:25)."""
-    packed = torch.cat([sums, torch.tensor([float(n)], dtype=sums.dtype, device=sums.device)])
+    """All-reduce the per-column (sum, sum of squares) and the row count over the ranks of `group`: ONE collective
+    of 2C+1 doubles (SyncBN forward, models/model.py:25). Returns the packed f64[2C+1] tensor (the count is its last
+    element and stays on the device)."""
+    packed = torch.empty(sums.numel() + 1, dtype=sums.dtype, device=sums.device)
+    packed[:-1] = sums
+    packed[-1] = float(n)
     torch.distributed.all_reduce(packed, group=group)
-    return packed[:-1].contiguous(), int(round(float(packed[-1].item())))
+    return packed
 
 
 class SyncBatchNormFp32Fn(torch.autograd.Function):
@@ -106,15 +123,15 @@ class SyncBatchNormFp32Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, group):
         xd = x.double()
-        sums = torch.cat([xd.sum(0), (xd * xd).sum(0)])
-        sums, n = sync_bn_stats(sums, x.shape[0], group)
+        sums = sync_bn_stats(torch.cat([xd.sum(0), (xd * xd).sum(0)]), x.shape[0], group)
+        n = sums[-1]          # global row count, a 0-d tensor on the device (no host sync)
         c = x.shape[1]
         mean = sums[:c] / n
-        var = (sums[c:] / n - mean * mean).clamp_(min=0)
+        var = (sums[c:2 * c] / n - mean * mean).clamp_(min=0)
         invstd = torch.rsqrt(var + eps)
         with torch.no_grad():
             running_mean.mul_(1 - momentum).add_(momentum * mean.to(running_mean.dtype))
-            running_var.mul_(1 - momentum).add_(momentum * (var * n / max(n - 1, 1)).to(running_var.dtype))
+            running_var.mul_(1 - momentum).add_(momentum * (var * n / (n - 1).clamp(min=1)).to(running_var.dtype))
         xhat = ((xd - mean) * invstd).to(x.dtype)
         ctx.save_for_backward(xhat, gamma, invstd.to(x.dtype))
         ctx.n, ctx.group = n, group
@@ -159,8 +176,4 @@ class SegmentMaxFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         (argmax,) = ctx.saved_tensors
-        df = torch.zeros(ctx.shape, dtype=torch.float32, device=dout.device)
-        valid = argmax < ctx.shape[0]
-        cols = torch.arange(ctx.shape[1], device=dout.device)[None].expand_as(argmax)
-        df.index_put_((argmax[valid].long(), cols[valid]), dout[valid].float(), accumulate=True)
-        return df.to(torch.bfloat16), None, None
+        return ops.segment_max_backward(dout.contiguous().float(), argmax, ctx.shape[0]), None, None

@@ -260,8 +260,8 @@ def prepack_conv_weights(module):
         jobs = []
         for m in convs:
             c_in = _round16(m.in_channels)
-            jobs.append((m.kernel.detach(), c_in, 0))
-            jobs.append((m.kernel.detach(), c_in, _dgrad_mode(m)))
+            jobs.append((m.kernel, c_in, 0))         # the live Parameter: WeightPacker.stale() sees re-allocations
+            jobs.append((m.kernel, c_in, _dgrad_mode(m)))
         state = (convs, ops.WeightPacker(jobs, convs[0].kernel.device))
         module.__dict__["_b2m_packer"] = state
     packer = state[1]

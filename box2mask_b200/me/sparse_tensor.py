@@ -23,6 +23,26 @@ class CoordinateManager:
     def coords(self, stride):
         return self.levels[stride]
 
+    def validate(self):
+        """Insert the input coordinates into the hash (kept for the kernel maps) and read its status words: one host
+        sync. Returns (number of duplicate rows, number of rows outside the packable range)."""
+        dups, out_of_range = self.table(1).status.tolist()
+        return int(dups), int(out_of_range)
+
+    def deduplicate(self):
+        """ME's default quantisation (first occurrence wins): -> (unique_index i64[M] ascending,
+        inverse i64[N]) and this manager re-keyed on the M unique coordinates. Rare path (the reference's loaders
+        deliver unique coordinates, models/dataloader.py:63-68), plain torch indexing."""
+        coords = self.levels[1]
+        n = coords.shape[0]
+        first = ops.hash_query(self.table(1), coords).long()            # row of the first occurrence of each coordinate
+        keep = first == torch.arange(n, device=coords.device)
+        unique_index = torch.nonzero(keep).flatten()
+        inverse = (torch.cumsum(keep, 0) - 1)[first]
+        self.levels = {1: coords[unique_index].contiguous()}
+        self.tables, self.sub_maps, self.stride2 = {}, {}, {}
+        return unique_index, inverse
+
     def table(self, stride):
         if stride not in self.tables:
             t = ops.hash_build(self.levels[stride])
@@ -115,6 +135,17 @@ class SparseTensor:
                 raise ValueError("features and coordinates disagree on the number of rows")
             coordinate_manager = CoordinateManager(coords)
             tensor_stride = 1
+            # ME.SparseTensor inserts the coordinates and quantises: rows outside the representable range are an error,
+            # duplicates collapse onto their first occurrence with the features re-indexed (unique_index / inverse).
+            self.unique_index = self.inverse_mapping = None
+            if coords.shape[0] > 0:
+                dups, out_of_range = coordinate_manager.validate()
+                if out_of_range:
+                    raise RuntimeError("SparseTensor: %d coordinate rows are outside the representable range "
+                                       "[-32768, 32767] (batch index < 65535)" % out_of_range)
+                if dups:
+                    self.unique_index, self.inverse_mapping = coordinate_manager.deduplicate()
+                    features = features[self.unique_index]
         self._F = features
         self._manager = coordinate_manager
         self._stride = int(tensor_stride)

@@ -78,6 +78,10 @@ class ZeroArena:
 def _cuda(t, dtype=None, name="tensor"):
     if not t.is_cuda:
         raise _lib.B2MError("%s must be a CUDA tensor (no CPU fallback in the product path)" % name)
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the current device's stream; a tensor of another device would be dereferenced there
+        raise _lib.B2MError("%s lives on cuda:%d but the current device is cuda:%d - call torch.cuda.set_device "
+                            "(or use `with torch.cuda.device(...)`) first" % (name, t.device.index, torch.cuda.current_device()))
     if dtype is not None and t.dtype != dtype:
         raise _lib.B2MError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
     if not t.is_contiguous():
@@ -255,7 +259,10 @@ class WeightPacker:
 
     def __init__(self, jobs, device):
         lib = _lib_or_raise()
+        # jobs may carry Parameters (preferred) or plain tensors: the live objects are kept, not detached aliases, so
+        # that a re-allocation by module.to() / load_state_dict(assign=True) is seen by stale()
         self.kernels = [j[0] for j in jobs]
+        self.device = torch.device(device)
         self.buffers, meta, prefix = [], [], [0]
         for kernel, c_in, mode in jobs:
             _cuda(kernel, torch.float32, "kernel")
@@ -274,8 +281,9 @@ class WeightPacker:
         self.prefix = torch.tensor(prefix, dtype=torch.int64, device=device)
 
     def stale(self):
-        """True when a parameter was re-allocated (e.g. `.to(device)`): the job table must be rebuilt."""
-        return tuple(k.data_ptr() for k in self.kernels) != self.ptrs
+        """True when a parameter was re-allocated or moved (e.g. `.to(device)`): the job table must be rebuilt."""
+        return any(k.device != self.device for k in self.kernels) or \
+            tuple(k.data_ptr() for k in self.kernels) != self.ptrs
 
     def run(self):
         lib = _lib_or_raise()
@@ -348,23 +356,27 @@ def bn_forward(x, sums, gamma, beta, running_mean, running_var, momentum, eps, t
 
 
 def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, want_dresidual, n_stat=None,
-                reduce_hook=None):
+                reduce_hook=None, n_stat_dev=None):
+    """n_stat_dev: optional f64[1] device tensor with the global row count (SyncBN, no host round trip).
+    reduce_hook(red) -> all-reduced copy of red: only dx uses it; dgamma / dbeta stay this rank's own sums."""
     lib = _lib_or_raise()
     n, c = x.shape
     red = ZeroArena.take(2 * c, x.device)
     _run("bn_backward_reduce", 1, lambda: check(lib.b2m_bn_backward_reduce(
         ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd), int(bool(relu)), ptr(red), stream_ptr()),
         "bn_backward_reduce"), nbytes=2 * x.numel() * (3 if relu else 2))
+    red_local = None
     if reduce_hook is not None:
-        reduce_hook(red)  # SyncBN: all-reduce (sum_g, sum_g*xhat) over ranks
+        red_local = red
+        red = reduce_hook(red)  # SyncBN: (sum_g, sum_g*xhat) summed over ranks, in a NEW buffer
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dresidual else None
     dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
     dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
     _run("bn_backward_apply", 1, lambda: check(lib.b2m_bn_backward_apply(
         ptr(x), ptr(out), ptr(dout), n, n if n_stat is None else int(n_stat), c, ptr(save_mean), ptr(save_invstd),
-        ptr(gamma), ptr(red), int(bool(relu)), int(bool(training)), ptr(dx), ptr(dres), ptr(dgamma), ptr(dbeta),
-        stream_ptr()), "bn_backward_apply"), nbytes=2 * x.numel() * ((3 if relu else 2) + (2 if want_dresidual else 1)))
+        ptr(gamma), ptr(red), ptr(red_local), ptr(n_stat_dev), int(bool(relu)), int(bool(training)), ptr(dx), ptr(dres),
+        ptr(dgamma), ptr(dbeta), stream_ptr()), "bn_backward_apply"), nbytes=2 * x.numel() * ((3 if relu else 2) + (2 if want_dresidual else 1)))
     return dx, dres, dgamma, dbeta
 
 
@@ -388,7 +400,7 @@ def segment_mean_backward(dout, ids, counts, n):
     _cuda(dout, torch.float32, "dout")
     df = torch.empty((n, dout.shape[1]), dtype=torch.bfloat16, device=dout.device)
     _run("segment_mean_backward", 1, lambda: check(lib.b2m_segment_mean_backward(
-        ptr(dout), ptr(ids), ptr(counts), n, dout.shape[1], ptr(df), stream_ptr()), "segment_mean_backward"),
+        ptr(dout), ptr(ids), ptr(counts), n, dout.shape[1], dout.shape[0], ptr(df), stream_ptr()), "segment_mean_backward"),
         nbytes=2 * n * dout.shape[1] + 8 * n + 4 * dout.numel())
     return df
 
@@ -401,6 +413,17 @@ def segment_max_forward(f, ids, s):
     check(lib.b2m_segment_max_forward(ptr(f), ptr(ids), f.shape[0], f.shape[1], s, ptr(out), ptr(argmax),
                                       stream_ptr()), "segment_max_forward")
     return out, argmax
+
+
+def segment_max_backward(dout, argmax, n):
+    lib = _lib_or_raise()
+    _cuda(dout, torch.float32, "dout")
+    _cuda(argmax, torch.int32, "argmax")
+    s, c = dout.shape
+    df = torch.empty((n, c), dtype=torch.bfloat16, device=dout.device)
+    _run("segment_max_backward", 2, lambda: check(lib.b2m_segment_max_backward(
+        ptr(dout), ptr(argmax), s, c, n, ptr(df), stream_ptr()), "segment_max_backward"), nbytes=2 * n * c + 8 * s * c)
+    return df
 
 
 # ---------------------------------------------------------------------------------------------

@@ -11,7 +11,8 @@
  *  - plain pointers + sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`.
  *  - no allocation inside: outputs and workspaces are caller-allocated; `*_workspace_bytes` queries.
  *  - stream-ordered on `stream` (a cudaStream_t passed as void*); no host synchronisation inside
- *    unless stated; re-entrant; no global mutable state.
+ *    unless stated; re-entrant. The only process state: a per-device cache (SM count, shared-memory
+ *    opt-in of the kernels) and the explicit tuning options of b2m_set_option.
  *  - return 0 (B2M_OK) or a negative error code; never throws. `b2m_error_string` names a code.
  *  - "bf16" = __nv_bfloat16 bit patterns carried as uint16_t.
  *  - Kernel maps are dense neighbour tables `nbr[K][pitch]` (int32, -1 = no neighbour), pitch =
@@ -42,6 +43,16 @@ typedef void* b2m_stream_t; /* cudaStream_t */
 
 int b2m_version(void);
 const char* b2m_error_string(int code);
+
+/* Process-wide tuning options (no environment variables are read inside the library).
+ *  B2M_OPT_MAX_CTAS          cap on the CTAs of the persistent convolution kernels (0 = one per SM); lowered by
+ *                            the data-parallel host while a gradient all-reduce overlaps the backward pass
+ *  B2M_OPT_CHUNKS_PER_STAGE  force 1 or 2 reduction chunks per pipeline stage of the forward kernel (0 = auto)
+ *  B2M_OPT_SPLIT_OFFSETS     1 = never split the kernel offsets of a convolution over CTAs (0 = automatic) */
+#define B2M_OPT_MAX_CTAS 1
+#define B2M_OPT_CHUNKS_PER_STAGE 2
+#define B2M_OPT_SPLIT_OFFSETS 3
+int b2m_set_option(int32_t option, int64_t value);
 
 /* ------------------------------------------------------------------------------------------------
  * Coordinate hash (open addressing, 64-bit packed keys)           reference: ME.SparseTensor(...)
@@ -156,7 +167,8 @@ int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t
  * ---------------------------------------------------------------------------------------------- */
 /* sums double[2c] += (sum_x, sum_x^2) per column of x bf16[n,c] */
 int b2m_colstats(const uint16_t* x, int64_t n, int32_t c, double* sums, b2m_stream_t stream);
-/* n_stat = number of rows the sums were taken over (== n on one GPU; the all-rank total under SyncBN).
+/* n_stat = number of rows the sums were taken over (== n on one GPU; the all-rank total under SyncBN;
+ * n_stat <= 0: read it from sums[2c], where the SyncBN all-reduce carries the global row count).
  * training: mean/var from sums (biased var for normalisation), running stats updated with momentum
  * (unbiased var), save_mean/save_invstd float[c] written. eval (training==0): uses running stats.
  * out = act( (x-mean)*invstd*gamma + beta (+ residual) ), act = ReLU if relu else identity. */
@@ -170,9 +182,14 @@ int b2m_bn_forward(const uint16_t* x, int64_t n, int64_t n_stat, int32_t c, cons
 int b2m_bn_backward_reduce(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n,
                            int32_t c, const float* save_mean, const float* save_invstd, int32_t relu,
                            double* red, b2m_stream_t stream);
+/* SyncBatchNorm (models/model.py:25): `red` is the all-reduced (global) reduction that enters dx; `red_local`
+ * (NULL = red) is this rank's own reduction, which becomes dgamma / dbeta (torch's SyncBatchNorm keeps the affine
+ * gradients local; the gradient all-reduce averages them like any other parameter); `n_stat_dev` (NULL = use
+ * n_stat) points at the global row count as a double on the device (no host round trip). */
 int b2m_bn_backward_apply(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n,
                           int64_t n_stat, int32_t c, const float* save_mean, const float* save_invstd,
-                          const float* gamma, const double* red, int32_t relu, int32_t training,
+                          const float* gamma, const double* red, const double* red_local,
+                          const double* n_stat_dev, int32_t relu, int32_t training,
                           uint16_t* dx, uint16_t* dresidual, float* dgamma, float* dbeta,
                           b2m_stream_t stream);
 
@@ -186,10 +203,13 @@ int b2m_segment_mean_forward(const uint16_t* f, const int64_t* ids, int64_t n, i
                              float* out, float* counts, b2m_stream_t stream);
 /* df bf16[n, c] = dout[ids[v], :] / counts[ids[v]] */
 int b2m_segment_mean_backward(const float* dout, const int64_t* ids, const float* counts, int64_t n,
-                              int32_t c, uint16_t* df, b2m_stream_t stream);
+                              int32_t c, int64_t s, uint16_t* df, b2m_stream_t stream);
 /* out float[s, c] = max over the segment, argmax int32[s, c] = row that attained it */
 int b2m_segment_max_forward(const uint16_t* f, const int64_t* ids, int64_t n, int32_t c, int64_t s,
                             float* out, int32_t* argmax, b2m_stream_t stream);
+/* df bf16[n, c] = gradient of the segment max: row argmax[s, j] receives dout[s, j], all else zero */
+int b2m_segment_max_backward(const float* dout, const int32_t* argmax, int64_t s, int32_t c, int64_t n,
+                             uint16_t* df, b2m_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Box-vote decoding                 reference: models/iou_nms.py and models/detection_net.py:369-488

@@ -30,9 +30,9 @@ def _worker(rank, world, port, out):
         full = torch.randn(50, 8, dtype=torch.float64)
         mine = full[:20] if rank == 0 else full[20:]
         sums = torch.cat([mine.sum(0), (mine * mine).sum(0)])
-        gs, n = Fn.sync_bn_stats(sums, mine.shape[0], dist.group.WORLD)
-        assert n == 50
-        assert torch.allclose(gs, torch.cat([full.sum(0), (full * full).sum(0)]))
+        packed = Fn.sync_bn_stats(sums, mine.shape[0], dist.group.WORLD)    # [2C sums | global row count], on the device
+        assert packed.shape == (17,) and float(packed[-1]) == 50
+        assert torch.allclose(packed[:-1], torch.cat([full.sum(0), (full * full).sum(0)]))
         # 2. an MLP head (reference naming) under DDP + SyncBN == the same head on the concatenated batch
         def head():
             torch.manual_seed(1)
