@@ -46,6 +46,9 @@ SIGNATURES = {
     "b2m_segment_max_forward": (c_int32, [_P, _P, c_int64, c_int32, c_int64, _P, _P, _P]),
     "b2m_nms_workspace_bytes": (c_size_t, [c_int64]),
     "b2m_aabb_nms": (c_int32, [_P, c_int64, c_float, _P, _P, _P, _P, c_int64, _P, c_size_t, _P]),
+    "b2m_aabb_heatmaps": (c_int32, [_P, c_int64, _P, _P, c_int64, _P, _P]),
+    "b2m_mask_label_vote": (c_int32, [_P, c_int64, c_int64, c_int64, _P, c_int32, _P, _P, _P]),
+    "b2m_segment_label_vote": (c_int32, [_P, _P, c_int64, c_int64, c_int32, _P, _P, _P]),
     "b2m_heatmap_project": (c_int32, [_P, c_int64, c_int64, _P, _P, c_int64, c_float, _P, _P]),
     "b2m_mask_nms_workspace_bytes": (c_size_t, [c_int64]),
     "b2m_mask_nms": (c_int32, [_P, c_int64, c_int64, c_float, _P, _P, _P, c_size_t, _P]),

@@ -63,46 +63,66 @@ __global__ void nms_mask_kernel(const float* __restrict__ boxes, const int32_t* 
   mask[(int64_t)p * words + w] = bits;
 }
 
-// Greedy scan in one block: the remaining set is a bit vector in shared memory.
-__global__ void __launch_bounds__(1024)
-nms_scan_kernel(const uint32_t* __restrict__ mask, const int32_t* __restrict__ order, int m, int words,
-                int32_t* __restrict__ n_clusters, int32_t* __restrict__ reps, int32_t* __restrict__ cluster_of) {
-  extern __shared__ uint32_t remaining[];  // [words]
-  __shared__ int next_p;
-  for (int w = threadIdx.x; w < words; w += blockDim.x) {
+// Greedy scan by ONE warp: the remaining set lives in registers (kScanWords words per lane, lane l owns words
+// l, l + 32, ...), so a cluster costs one ballot to find the first remaining box, one coalesced read of its mask row
+// and an and-not: no block barriers, no shared memory; the dependent chain per cluster is one L2 read (~0.5 us).
+// Outputs the representatives as sorted positions; box indices and memberships follow in nms_assign_kernel.
+constexpr int kScanWords = 64;      // words per lane: up to 32 * 64 * 32 = 65536 boxes
+__global__ void __launch_bounds__(32)
+nms_scan_kernel(const uint32_t* __restrict__ mask, int m, int words, int32_t* __restrict__ n_clusters,
+                int32_t* __restrict__ rep_pos) {
+  const int lane = threadIdx.x;
+  const int wpl = (words + 31) / 32;                       // words per lane actually used
+  uint32_t rem[kScanWords];
+#pragma unroll
+  for (int i = 0; i < kScanWords; ++i) {
+    const int w = i * 32 + lane;
     const int lo = w * 32;
-    remaining[w] = (m - lo >= 32) ? 0xFFFFFFFFu : ((m > lo) ? ((1u << (m - lo)) - 1u) : 0u);
+    rem[i] = (i < wpl && w < words) ? ((m - lo >= 32) ? 0xFFFFFFFFu : ((m > lo) ? ((1u << (m - lo)) - 1u) : 0u)) : 0u;
   }
-  if (threadIdx.x == 0) next_p = (m > 0) ? 0 : -1;
-  __syncthreads();
-  int nc = 0;
-  while (true) {
-    const int p = next_p;
-    if (p < 0) break;
-    __syncthreads();  // everyone has read next_p
-    if (threadIdx.x == 0) { reps[nc] = order[p]; next_p = 0x7FFFFFFF; }
-    __syncthreads();
-    int local_next = 0x7FFFFFFF;
-    for (int w = threadIdx.x; w < words; w += blockDim.x) {
-      const uint32_t rem = remaining[w];
-      const uint32_t members = rem & mask[(int64_t)p * words + w];
-      uint32_t mm = members;
-      while (mm) {
-        const int b = __ffs(mm) - 1;
-        mm &= mm - 1;
-        cluster_of[order[w * 32 + b]] = nc;
-      }
-      const uint32_t left = rem & ~members;
-      remaining[w] = left;
-      if (left && local_next == 0x7FFFFFFF) local_next = w * 32 + __ffs(left) - 1;
+  // first remaining position at or after nothing: min over lanes of the first set bit
+  auto first_remaining = [&]() -> int {
+    int best = 0x7FFFFFFF;
+#pragma unroll
+    for (int i = 0; i < kScanWords; ++i) {
+      if (i < wpl && rem[i] && best == 0x7FFFFFFF) best = (i * 32 + lane) * 32 + __ffs(rem[i]) - 1;
     }
-    if (local_next != 0x7FFFFFFF) atomicMin(&next_p, local_next);
-    __syncthreads();
-    if (threadIdx.x == 0 && next_p == 0x7FFFFFFF) next_p = -1;
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    return best;
+  };
+  int nc = 0;
+  int p = first_remaining();
+  while (p != 0x7FFFFFFF) {
+    if (lane == 0) rep_pos[nc] = p;
     ++nc;
-    __syncthreads();
+    const uint32_t* row = mask + (int64_t)p * words;
+#pragma unroll
+    for (int i = 0; i < kScanWords; ++i) {
+      if (i < wpl) {
+        const int w = i * 32 + lane;
+        if (w < words) rem[i] &= ~__ldg(row + w);          // members = remaining & row (incl. p itself: diagonal bit)
+      }
+    }
+    p = first_remaining();
   }
-  if (threadIdx.x == 0) *n_clusters = nc;
+  if (lane == 0) *n_clusters = nc;
+}
+
+// reps[c] = box index of representative c; cluster_of[box] = first cluster (in greedy order) whose representative's
+// mask row has the box's bit: exactly the greedy membership, because a box leaves the remaining set at the first such row.
+__global__ void nms_assign_kernel(const uint32_t* __restrict__ mask, const int32_t* __restrict__ order, int m, int words,
+                                  const int32_t* __restrict__ n_clusters, const int32_t* __restrict__ rep_pos,
+                                  int32_t* __restrict__ reps, int32_t* __restrict__ cluster_of) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;    // sorted position of the box
+  const int nc = *n_clusters;
+  if (q < nc) reps[q] = order[rep_pos[q]];
+  if (q >= m) return;
+  const int w = q >> 5;
+  const uint32_t bit = 1u << (q & 31);
+  int c = 0;
+  for (; c < nc; ++c)
+    if (__ldg(mask + (int64_t)__ldg(rep_pos + c) * words + w) & bit) break;
+  cluster_of[order[q]] = c;      // c < nc always: a box that is never suppressed becomes a representative itself
 }
 
 // heat[c][j] = IoU(box[reps[c]], box[j]) in ORIGINAL box order, self = 1
@@ -182,6 +202,52 @@ __global__ void mask_scan_kernel(const int32_t* __restrict__ inter, const int32_
   if (threadIdx.x == 0) *n_keep = nk;
 }
 
+// counts[c][l] = number of voxels v in mask c with label[v] == l (the np.bincount of models/detection_net.py:461-466,
+// on the bit-packed masks): a block takes one mask and a slice of its words, histograms in shared memory.
+__global__ void __launch_bounds__(256)
+mask_label_hist_kernel(const uint32_t* __restrict__ masks, int64_t words, int64_t n_vox, const int32_t* __restrict__ label,
+                       int n_labels, int32_t* __restrict__ counts) {
+  extern __shared__ int hist[];   // [n_labels]
+  for (int i = threadIdx.x; i < n_labels; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int64_t c = blockIdx.y;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t bits = __ldg(masks + c * words + w);
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int64_t v = w * 32 + b;
+      if (v < n_vox) {
+        const int l = __ldg(label + v);
+        if (l >= 0 && l < n_labels) atomicAdd(&hist[l], 1);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_labels; i += blockDim.x)
+    if (hist[i]) atomicAdd(counts + c * n_labels + i, hist[i]);
+}
+// counts[seg[v]][label[v]] += 1 (per-segment label histogram: the torch.mode of models/detection_net.py:404-410)
+__global__ void segment_label_hist_kernel(const int64_t* __restrict__ seg, const int32_t* __restrict__ label, int64_t n,
+                                          int64_t n_seg, int n_labels, int32_t* __restrict__ counts) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int64_t s = __ldg(seg + v);
+  const int l = __ldg(label + v);
+  if (s >= 0 && s < n_seg && l >= 0 && l < n_labels) atomicAdd(counts + s * n_labels + l, 1);
+}
+// best[r] = smallest label with the largest count (np.argmax / torch.mode tie rule: lowest value wins)
+__global__ void hist_argmax_kernel(const int32_t* __restrict__ counts, int64_t rows, int n_labels, int32_t* __restrict__ best) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  int bl = 0, bc = counts[r * n_labels];
+  for (int l = 1; l < n_labels; ++l) {
+    const int cnt = counts[r * n_labels + l];
+    if (cnt > bc) { bc = cnt; bl = l; }
+  }
+  best[r] = bl;
+}
+
 __global__ void unpack_masks_kernel(const uint32_t* __restrict__ masks, int64_t k, int64_t words, int64_t n_vox,
                                     uint8_t* __restrict__ out) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,7 +263,7 @@ using namespace b2m;
 extern "C" size_t b2m_nms_workspace_bytes(int64_t m) {
   const int64_t words = (m + 31) / 32;
   size_t order = ((size_t)m * 4 + 255) / 256 * 256;
-  return order + (size_t)m * words * 4 + 256;
+  return order + ((size_t)m * words * 4 + 255) / 256 * 256 + order + 256;   // order | pair mask | representative positions
 }
 
 extern "C" int b2m_aabb_nms(const float* boxes, int64_t m, float cluster_th, int32_t* n_clusters, int32_t* representatives,
@@ -214,25 +280,75 @@ extern "C" int b2m_aabb_nms(const float* boxes, int64_t m, float cluster_th, int
   }
   const int mi = (int)m;
   const int words = (mi + 31) / 32;
-  if ((size_t)words * 4 > 200 * 1024) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (words > 32 * kScanWords) return B2M_ERR_UNSUPPORTED_SHAPE;
   int32_t* order = reinterpret_cast<int32_t*>(workspace);
   uint32_t* mask = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + ((size_t)m * 4 + 255) / 256 * 256);
   nms_rank_kernel<<<cdiv(mi, 128), 128, 0, st>>>(boxes, mi, order);
   B2M_CHECK_LAUNCH();
   nms_mask_kernel<<<dim3(cdiv(words, 64), mi), 64, 0, st>>>(boxes, order, mi, words, cluster_th, mask);
   B2M_CHECK_LAUNCH();
-  const size_t sh = (size_t)words * 4;
-  if (sh > 40 * 1024) {
-    if (cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh) != cudaSuccess)
-      return B2M_ERR_CUDA_LAUNCH;
-  }
-  nms_scan_kernel<<<1, 1024, sh, st>>>(mask, order, mi, words, n_clusters, representatives, cluster_of);
+  int32_t* rep_pos = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + ((size_t)m * 4 + 255) / 256 * 256 +
+                                                ((size_t)m * words * 4 + 255) / 256 * 256);
+  nms_scan_kernel<<<1, 32, 0, st>>>(mask, mi, words, n_clusters, rep_pos);
+  B2M_CHECK_LAUNCH();
+  nms_assign_kernel<<<cdiv(mi, 128), 128, 0, st>>>(mask, order, mi, words, n_clusters, rep_pos, representatives, cluster_of);
   B2M_CHECK_LAUNCH();
   if (heatmaps && max_clusters > 0) {
     const int64_t rows = max_clusters < m ? max_clusters : m;
     nms_heat_kernel<<<dim3(cdiv(mi, 128), (unsigned)rows), 128, 0, st>>>(boxes, mi, n_clusters, representatives, max_clusters, heatmaps);
     B2M_CHECK_LAUNCH();
   }
+  return B2M_OK;
+}
+
+/* Heat-map rows of the first k clusters (k read back by the caller): heat float[k, m]. Split from b2m_aabb_nms so that
+ * the caller allocates k rows instead of m. */
+extern "C" int b2m_aabb_heatmaps(const float* boxes, int64_t m, const int32_t* n_clusters, const int32_t* representatives,
+                                 int64_t k, float* heatmaps, b2m_stream_t stream) {
+  if (!boxes || !n_clusters || !representatives || !heatmaps || m < 0 || k < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (m == 0 || k == 0) return B2M_OK;
+  if (k > 65535) return B2M_ERR_UNSUPPORTED_SHAPE;
+  nms_heat_kernel<<<dim3(cdiv(m, 128), (unsigned)k), 128, 0, (cudaStream_t)stream>>>(boxes, (int)m, n_clusters, representatives, k,
+                                                                                    heatmaps);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+/* counts int32[k, n_labels] (zeroed inside) = label histogram of every bit-packed mask; best int32[k] = its arg-max
+ * (lowest label on ties) - the per-instance majority vote of models/detection_net.py:461-466. label int32[n_vox]. */
+extern "C" int b2m_mask_label_vote(const uint32_t* masks, int64_t k, int64_t words, int64_t n_vox, const int32_t* label,
+                                   int32_t n_labels, int32_t* counts, int32_t* best, b2m_stream_t stream) {
+  if (!masks || !label || !counts || !best || k < 0 || words < 0 || n_labels <= 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (n_labels > 4096 || k > 65535) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (k == 0) return B2M_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(counts, 0, (size_t)k * n_labels * 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  if (words > 0) {
+    int gx = cdiv(words, 256 * 8);
+    if (gx < 1) gx = 1;
+    mask_label_hist_kernel<<<dim3((unsigned)gx, (unsigned)k), 256, (size_t)n_labels * 4, st>>>(masks, words, n_vox, label, n_labels,
+                                                                                              counts);
+    B2M_CHECK_LAUNCH();
+  }
+  hist_argmax_kernel<<<cdiv(k, 128), 128, 0, st>>>(counts, k, n_labels, best);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+/* counts int32[n_seg, n_labels] (zeroed inside) = label histogram per segment, best int32[n_seg] = its mode (lowest
+ * label on ties, like torch.mode) - the per-segment vote of the S3DIS branch, models/detection_net.py:398-410. */
+extern "C" int b2m_segment_label_vote(const int64_t* seg, const int32_t* label, int64_t n, int64_t n_seg, int32_t n_labels,
+                                      int32_t* counts, int32_t* best, b2m_stream_t stream) {
+  if (!seg || !label || !counts || !best || n < 0 || n_seg < 0 || n_labels <= 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (n_seg == 0) return B2M_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(counts, 0, (size_t)n_seg * n_labels * 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  if (n > 0) {
+    segment_label_hist_kernel<<<cdiv(n, 256), 256, 0, st>>>(seg, label, n, n_seg, n_labels, counts);
+    B2M_CHECK_LAUNCH();
+  }
+  hist_argmax_kernel<<<cdiv(n_seg, 128), 128, 0, st>>>(counts, n_seg, n_labels, best);
+  B2M_CHECK_LAUNCH();
   return B2M_OK;
 }
 

@@ -18,12 +18,13 @@ def NMS_clustering(boxes, cluster_th=0.5, get_heatmaps=True):
     assert 0 < cluster_th < 1
     boxes = boxes.contiguous().float()
     reps, cluster_of, heat = ops.aabb_nms(boxes, cluster_th, want_heatmaps=get_heatmaps)
-    # members of each cluster in descending-score order: one stable sort by cluster id of the score-ordered boxes
-    # and one split (a single host sync for the K sizes) instead of K boolean-mask selections
-    order = torch.argsort(-boxes[:, 0], stable=True)
-    sorted_cluster = cluster_of[order].long()
-    by_cluster = order[torch.argsort(sorted_cluster, stable=True)]
-    sizes = torch.bincount(sorted_cluster, minlength=len(reps)).tolist()
+    # members of each cluster in descending-score order (ties: lower index): ONE sort of the M boxes by
+    # (cluster, -score, index) and one split (a single host sync for the K sizes), instead of K boolean selections
+    m = boxes.shape[0]
+    cl = cluster_of.long()
+    by_score = torch.argsort(-boxes[:, 0], stable=True)
+    by_cluster = by_score[torch.sort(cl[by_score], stable=True)[1]]
+    sizes = torch.bincount(cl, minlength=len(reps)).tolist() if m else []
     clusters = list(torch.split(by_cluster, sizes))
     if get_heatmaps:
         return reps, clusters, heat
@@ -46,24 +47,47 @@ def to_bbs_min_max(locations, offsets, bounds, scores=None):
 
 def detection2mask(net, batch, pred, cfg, mode="eval", score_filtering=True, cluster_th=0.3, score_th=0.3,
                    mask_bin_th=0.3, mask_nms_th=0.3):
-    """pred: dict head -> f32 tensor (any device). Returns {scene name: {conf, label_id, mask, ...}}."""
+    """pred: dict head -> f32 tensor (any device). Returns {scene name: {conf, label_id, mask, ...}}.
+
+    Two semantics sources, like the reference (models/detection_net.py:378-415):
+      * per-superpoint head (`cfg.mlp_semantics`; ScanNet, ARKitScenes): class ids through semantic_valid_class_ids,
+        foreground per superpoint, mask-NMS on;
+      * per-voxel head (`cfg.mlp_per_vox_semantics`, net.requires_voxel_outputs; S3DIS): class INDICES, every superpoint
+        takes the mode of its voxels' labels (torch.mode: lowest label on ties), foreground from those, NO mask-NMS
+        (:449-451). As in the reference this branch takes the per-voxel predictions of the whole batch for every
+        scene, i.e. it is meant for batch size 1 (models/evaluation.py:70-91 decodes scene by scene)."""
     dev = torch.device(net.device)
     P = {k: v.to(dev).float() for k, v in pred.items()}
     loc = batch["input_location"].to(dev)
     pred_bbs = to_bbs_min_max(loc, P[cfg.mlp_offsets], P[cfg.mlp_bounds], torch.sigmoid(P[cfg.mlp_bb_scores]))
-    sem_idx = torch.argmax(P[cfg.mlp_semantics], 1)
-    class_ids = torch.as_tensor(net.semantic_valid_class_ids, device=dev).long()
-    pred_sem = class_ids[sem_idx]
+    per_vox = cfg.mlp_per_vox_semantics in cfg.network_heads
+    voxel_outputs = bool(getattr(net, "requires_voxel_outputs", per_vox))
+    if per_vox:
+        pred_sem = torch.argmax(P[cfg.mlp_per_vox_semantics], 1)
+        n_lab = P[cfg.mlp_per_vox_semantics].shape[1]
+    else:
+        class_ids = torch.as_tensor(net.semantic_valid_class_ids, device=dev).long()
+        pred_sem = class_ids[torch.argmax(P[cfg.mlp_semantics], 1)]
+        n_lab = int(class_ids.max().item()) + 1
     batch_ids = batch["batch_ids"].to(dev)
     results = {}
     for scene_idx, scene in enumerate(batch["scene"]):
         scene_mask = batch_ids == scene_idx
-        scene_sem = pred_sem[scene_mask]
-        scene_fg = net.is_foreground(scene_sem)
-        scene_fg = torch.as_tensor(scene_fg, device=dev).bool()
-        scene_bbs = pred_bbs[scene_mask][scene_fg].contiguous()
         seg2vox = batch["seg2vox"][scene_idx].to(dev).long().contiguous()
         n_vox = seg2vox.shape[0]
+        if voxel_outputs:
+            # per-segment majority vote over the scene's voxels (segments are numbered by np.unique, :399-410)
+            segments = torch.as_tensor(batch["vox_segments"][scene_idx], device=dev).long()
+            uniq, seg_rank = torch.unique(segments, return_inverse=True)
+            sem_vox = pred_sem.to(torch.int32).contiguous()
+            seg_sem, _ = ops.segment_label_vote(seg_rank.contiguous(), sem_vox, int(uniq.shape[0]), n_lab)
+            scene_fg = net.is_foreground(seg_sem.long())
+        else:
+            scene_sem = pred_sem[scene_mask]
+            scene_fg = net.is_foreground(scene_sem)
+            sem_vox = scene_sem[seg2vox].to(torch.int32).contiguous()
+        scene_fg = torch.as_tensor(scene_fg, device=dev).bool()
+        scene_bbs = pred_bbs[scene_mask][scene_fg].contiguous()
         if scene_bbs.shape[0] == 0:
             results[scene["name"]] = {"conf": torch.zeros(0), "label_id": np.zeros(0, dtype="int32"),
                                       "mask": torch.zeros((0, n_vox), dtype=torch.bool)}
@@ -76,15 +100,13 @@ def detection2mask(net, batch, pred, cfg, mode="eval", score_filtering=True, clu
         fg_rank = torch.full((scene_fg.shape[0],), -1, dtype=torch.int32, device=dev)
         fg_rank[scene_fg] = torch.arange(int(scene_fg.sum()), dtype=torch.int32, device=dev)
         packed = ops.heatmap_project(heat, fg_rank, seg2vox, mask_bin_th)
-        keep = ops.mask_nms(packed, mask_nms_th)
-        packed, scores, reps = packed[keep].contiguous(), scores[keep], reps[keep]
+        if not voxel_outputs:
+            keep = ops.mask_nms(packed, mask_nms_th)
+            packed, scores, reps = packed[keep].contiguous(), scores[keep], reps[keep]
+        # per-instance majority label (np.bincount + argmax, detection_net.py:461-466) on the bit-packed masks
+        labels, _ = ops.mask_label_vote(packed, sem_vox, n_vox, n_lab)
+        labels = labels.cpu().numpy().astype("int32")
         masks = ops.unpack_masks(packed, n_vox)
-        sem_vox = scene_sem[seg2vox]
-        # per-instance majority label (np.bincount + argmax, detection_net.py:461-466)
-        n_lab = int(class_ids.max().item()) + 1
-        onehot = torch.zeros((n_vox, n_lab), device=dev)
-        onehot[torch.arange(n_vox, device=dev), sem_vox] = 1
-        labels = torch.argmax(masks.float() @ onehot, 1).to(torch.int32).cpu().numpy()
         res = {"conf": scores.cpu(), "label_id": labels}
         if mode == "eval" and "vox2point" in batch:
             res["mask"] = masks[:, batch["vox2point"][scene_idx].to(dev)].cpu()

@@ -430,7 +430,8 @@ def segment_max_backward(dout, argmax, n):
 # decode
 # ---------------------------------------------------------------------------------------------
 def aabb_nms(boxes, cluster_th, max_clusters=None, want_heatmaps=True):
-    """-> (representatives i64[K], cluster_of i32[M], heatmaps f32[K,M] or None). One host sync (K)."""
+    """-> (representatives i64[K], cluster_of i32[M], heatmaps f32[K,M] or None). One host sync (K): the heat-map rows
+    are allocated for the K clusters found (not for M) and filled by a second call."""
     lib = _lib_or_raise()
     _cuda(boxes, torch.float32, "boxes")
     m = boxes.shape[0]
@@ -438,15 +439,47 @@ def aabb_nms(boxes, cluster_th, max_clusters=None, want_heatmaps=True):
     n_clusters = torch.zeros(1, dtype=torch.int32, device=dev)
     reps = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
     cluster_of = torch.empty(max(m, 1), dtype=torch.int32, device=dev)
-    if max_clusters is None:
-        max_clusters = m
-    heat = torch.empty((max_clusters, m), dtype=torch.float32, device=dev) if want_heatmaps else None
     ws_bytes = lib.b2m_nms_workspace_bytes(m)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(lib.b2m_aabb_nms(ptr(boxes), m, float(cluster_th), ptr(n_clusters), ptr(reps), ptr(cluster_of), ptr(heat),
-                           max_clusters if want_heatmaps else 0, ptr(ws), ws_bytes, stream_ptr()), "aabb_nms")
+    _run("aabb_nms", 4, lambda: check(lib.b2m_aabb_nms(ptr(boxes), m, float(cluster_th), ptr(n_clusters), ptr(reps),
+                                                       ptr(cluster_of), None, 0, ptr(ws), ws_bytes, stream_ptr()), "aabb_nms"),
+         nbytes=28 * m + m * ((m + 31) // 32) * 4)
     k = int(n_clusters.item())
-    return reps[:k].long(), cluster_of[:m], (heat[:min(k, max_clusters)] if want_heatmaps else None)
+    heat = None
+    if want_heatmaps:
+        rows = k if max_clusters is None else min(k, int(max_clusters))
+        heat = torch.empty((rows, m), dtype=torch.float32, device=dev)
+        _run("aabb_heatmaps", 1, lambda: check(lib.b2m_aabb_heatmaps(ptr(boxes), m, ptr(n_clusters), ptr(reps), rows, ptr(heat),
+                                                                    stream_ptr()), "aabb_heatmaps"), nbytes=4 * rows * m)
+    return reps[:k].long(), cluster_of[:m], heat
+
+
+def mask_label_vote(masks, label, n_vox, n_labels):
+    """Per-mask majority label over bit-packed masks int32[k, words]; label int32[n_vox] -> (best i32[k], counts i32[k, L])."""
+    lib = _lib_or_raise()
+    _cuda(masks, torch.int32, "masks")
+    _cuda(label, torch.int32, "label")
+    k, words = masks.shape
+    counts = torch.empty((k, n_labels), dtype=torch.int32, device=masks.device)
+    best = torch.empty(k, dtype=torch.int32, device=masks.device)
+    _run("mask_label_vote", 3, lambda: check(lib.b2m_mask_label_vote(ptr(masks), k, words, n_vox, ptr(label), n_labels,
+                                                                    ptr(counts), ptr(best), stream_ptr()), "mask_label_vote"),
+         nbytes=4 * k * words + 4 * n_vox)
+    return best, counts
+
+
+def segment_label_vote(seg, label, n_seg, n_labels):
+    """Mode of label int32[n] within each segment id seg int64[n] -> (best i32[n_seg], counts i32[n_seg, L])."""
+    lib = _lib_or_raise()
+    _cuda(seg, torch.int64, "seg")
+    _cuda(label, torch.int32, "label")
+    n = seg.shape[0]
+    counts = torch.empty((n_seg, n_labels), dtype=torch.int32, device=seg.device)
+    best = torch.empty(n_seg, dtype=torch.int32, device=seg.device)
+    _run("segment_label_vote", 3, lambda: check(lib.b2m_segment_label_vote(ptr(seg), ptr(label), n, n_seg, n_labels, ptr(counts),
+                                                                          ptr(best), stream_ptr()), "segment_label_vote"),
+         nbytes=12 * n)
+    return best, counts
 
 
 def heatmap_project(heat, fg_rank, seg2vox, mask_bin_th):

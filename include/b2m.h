@@ -227,6 +227,10 @@ size_t b2m_nms_workspace_bytes(int64_t m);
 int b2m_aabb_nms(const float* boxes, int64_t m, float cluster_th, int32_t* n_clusters,
                  int32_t* representatives, int32_t* cluster_of, float* heatmaps, int64_t max_clusters,
                  void* workspace, size_t workspace_bytes, b2m_stream_t stream);
+/* Heat-map rows of the first k clusters, heat float[k, m], for callers that read n_clusters back first and allocate k
+ * rows instead of m (b2m_aabb_nms with heatmaps == NULL, then this). */
+int b2m_aabb_heatmaps(const float* boxes, int64_t m, const int32_t* n_clusters, const int32_t* representatives,
+                      int64_t k, float* heatmaps, b2m_stream_t stream);
 /* Heat-map rows -> bit-packed voxel masks (models/detection_net.py:436-446):
  *  mask[c, v] = heat[c, fg_rank[seg2vox[v]]] > mask_bin_th, 0 where fg_rank < 0 (background).
  *  heat float[k, m_fg], fg_rank int32[s] (rank of superpoint among foreground ones or -1),
@@ -240,6 +244,14 @@ int b2m_heatmap_project(const float* heat, int64_t k, int64_t m_fg, const int32_
 size_t b2m_mask_nms_workspace_bytes(int64_t k);
 int b2m_mask_nms(const uint32_t* masks, int64_t k, int64_t words, float th, uint8_t* keep,
                  int32_t* n_keep, void* workspace, size_t workspace_bytes, b2m_stream_t stream);
+/* Per-instance majority label (np.bincount + argmax, models/detection_net.py:461-466) on bit-packed masks:
+ * counts int32[k, n_labels] (zeroed inside), best int32[k] = arg-max, lowest label on ties. label int32[n_vox]. */
+int b2m_mask_label_vote(const uint32_t* masks, int64_t k, int64_t words, int64_t n_vox, const int32_t* label,
+                        int32_t n_labels, int32_t* counts, int32_t* best, b2m_stream_t stream);
+/* Per-segment mode of per-voxel labels (torch.mode, models/detection_net.py:398-410; S3DIS branch):
+ * counts int32[n_seg, n_labels] (zeroed inside), best int32[n_seg] = mode, lowest label on ties. */
+int b2m_segment_label_vote(const int64_t* seg, const int32_t* label, int64_t n, int64_t n_seg, int32_t n_labels,
+                           int32_t* counts, int32_t* best, b2m_stream_t stream);
 /* unpack bit masks to bool bytes uint8[k, n_vox] */
 int b2m_unpack_masks(const uint32_t* masks, int64_t k, int64_t words, int64_t n_vox, uint8_t* out,
                      b2m_stream_t stream);

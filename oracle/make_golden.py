@@ -122,6 +122,163 @@ def golden_net():
     np.savez_compressed(os.path.join(OUT, "selection_net_small.npz"), **out)
     print({k: float(v) for k, v in out.items() if k.startswith("loss_")})
 
+VARIANTS = ("s3dis", "arkit", "maxpool")
+
+
+def variant_config(kind):
+    """(cfg, number of classes, make_batch kwargs) of the extra parity configurations:
+    s3dis   : configs/s3dis_fold1.txt (per-voxel semantics head on the un-pooled tensor, 13 classes, score weight 3) plus
+              the optional IoU loss of models/model.py:91-129 switched on (use_bb_iou_loss, weight 1), so that L4 is pinned;
+    arkit   : configs/arkitscenes.txt (4 cm voxels, 28 classes, loss weights 0.5 / 3 / 0.3);
+    maxpool : configs/scannet.txt with max_pool_segments_detection_net (MinkowskiGlobalMaxPooling, detection_net.py:352)."""
+    from box2mask_b200.selection_net import default_config
+    if kind == "s3dis":
+        cfg = default_config(network_heads=["mlp_offsets", "mlp_bounds", "mlp_bb_scores", "mlp_per_vox_semantics"],
+                             eval_ths=[0.5, 0.03, 0.3, 0.6], batch_size=4, loss_weight_bb_scores=3,
+                             mlp_bb_scores_start_epoch=0, use_bb_iou_loss=True, loss_weight_bb_iou=1.0)
+        return cfg, 13, dict(n=2, seed=21, scale=0.14, density=1.2e4, n_classes=13)
+    if kind == "arkit":
+        cfg = default_config(voxel_size=0.04, eval_ths=[0.5, 0.05, 0.4, 0.6], batch_size=4, loss_weight_bb_scores=3,
+                             loss_weight_semantics=0.3, mlp_bb_scores_start_epoch=0)
+        return cfg, 28, dict(n=2, seed=22, scale=0.3, density=1.2e4, voxel_size=0.04, n_classes=28)
+    if kind == "maxpool":
+        cfg = default_config(max_pool_segments_detection_net=True, mlp_bb_scores_start_epoch=0)
+        return cfg, 20, dict(n=2, seed=23, scale=0.14, density=1.2e4)
+    raise ValueError(kind)
+
+
+def variant_batch(kind):
+    from box2mask_b200.synthetic import make_batch
+    cfg, n_cls, kw = variant_config(kind)
+    kw = dict(kw)
+    batch = make_batch(kw.pop("n"), **kw)
+    if kind == "s3dis":     # per-voxel labels = the label of the voxel's superpoint (models/dataloader.py S3DIS loader)
+        batch["gt_per_vox_semantics"] = batch["gt_semantics"][batch["pooling_ids"]]
+    return cfg, n_cls, batch
+
+
+def golden_variants():
+    """The reference's own Model / SelectionNet (models/model.py, models/detection_net.py, unmodified, over
+    oracle/me_shim.py) on the three extra configurations: eval-mode head outputs, train-mode losses (incl. the IoU
+    loss and the per-voxel semantics loss) and a few gradients -> tests/golden/selection_net_variants.npz."""
+    from box2mask_b200.synthetic import label_maps
+    from oracle import me_shim
+    from oracle.selection_net import seeded_state_dict
+    me_shim.install()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    orig_to = torch.Tensor.to
+
+    def to_cpu(self, *a, **k):
+        a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
+        return orig_to(self, *a, **k)
+    torch.Tensor.to = to_cpu
+    import models.model as ref_model
+    out = {}
+    try:
+        for kind in VARIANTS:
+            cfg, n_cls, batch = variant_batch(kind)
+            valid, id2idx, is_fg = label_maps(n_cls)
+            model = ref_model.Model(cfg, valid, id2idx, None, is_fg, device="cpu")
+            net = model.detection_model
+            shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+            net.load_state_dict(seeded_state_dict(shapes, seed=5))
+            out[kind + "_n_keys"] = np.int64(len(shapes))
+            model.eval()
+            pred = model.get_prediction(batch, with_grad=False, to_cpu=True, min_size=False)
+            for k, v in pred.items():
+                if k == "vox_feats":
+                    continue                     # the un-pooled trunk output (8 MB): the per-voxel head covers it
+                # per-voxel outputs: every 4th row keeps the fixture small
+                out["%s_eval_%s" % (kind, k)] = v.numpy()[::4] if v.shape[0] > 5000 else v.numpy()
+            model.train()
+            if kind == "s3dis":
+                # IoU loss (models/model.py:91-129): random ground truth never overlaps the predictions (IoU == 0, zero
+                # gradient), so the ground-truth boxes of this variant are the train-mode predictions plus noise.
+                with torch.no_grad():
+                    _, p0 = model.compute_loss_detection(batch, epoch=0)
+                g = torch.Generator().manual_seed(99)
+                batch["gt_bb_offsets"] = (p0["mlp_offsets"] + 0.05 * torch.randn(p0["mlp_offsets"].shape, generator=g)).detach()
+                batch["gt_bb_bounds"] = (p0["mlp_bounds"].clamp(min=0.06) *
+                                         (0.8 + 0.4 * torch.rand(p0["mlp_bounds"].shape, generator=g))).detach()
+                out["s3dis_gt_bb_offsets"] = batch["gt_bb_offsets"].numpy()
+                out["s3dis_gt_bb_bounds"] = batch["gt_bb_bounds"].numpy()
+                net.load_state_dict(seeded_state_dict(shapes, seed=5))      # undo the running-statistics update
+            losses, pred = model.compute_loss_detection(batch, epoch=0)
+            losses["optimization_loss"].backward()
+            for k, v in losses.items():
+                if k.endswith("_loss") or k == "bb_target_scores":
+                    out["%s_loss_%s" % (kind, k)] = np.float64(float(v))
+            params = dict(net.named_parameters())
+            for k in ("block8.1.conv2.kernel", "mlp_offsets.6.kernel", "mlp_bounds.6.kernel"):
+                out["%s_gradnorm_%s" % (kind, k)] = np.float64(float(params[k].grad.norm()))
+            print(kind, "voxels", batch["vox_coords"].shape[0], "superpoints", batch["input_location"].shape[0],
+                  {k: round(float(v), 5) for k, v in out.items() if k.startswith(kind + "_loss_")})
+    finally:
+        torch.Tensor.to = orig_to
+    np.savez_compressed(os.path.join(OUT, "selection_net_variants.npz"), **out)
+
+
+def decode_inputs_s3dis(seed=13):
+    """One scene (the reference's S3DIS branch only works at batch size 1, detection_net.py:395-396) with per-voxel
+    semantics logits, per-scene `vox_segments` and a `vox2point` map."""
+    from box2mask_b200.synthetic import make_batch
+    batch = make_batch(1, seed=seed, scale=0.3, density=6.0e3, n_classes=13)
+    rng = np.random.default_rng(seed)
+    loc = batch["input_location"].numpy()
+    s = len(loc)
+    centres = rng.uniform(0.2, 1.2, (7, 3)).astype(np.float32)
+    sizes = rng.uniform(0.15, 0.5, (7, 3)).astype(np.float32)
+    which = rng.integers(0, 7, s)
+    c = centres[which] + rng.normal(0, 0.03, (s, 3)).astype(np.float32)
+    n_vox = batch["vox_coords"].shape[0]
+    seg = batch["pooling_ids"].numpy()
+    # per-voxel logits: a per-segment preferred class plus noise, so that the per-segment mode is non-trivial
+    seg_cls = rng.integers(0, 13, s)
+    logits = rng.normal(0, 1, (n_vox, 13)).astype(np.float32)
+    logits[np.arange(n_vox), seg_cls[seg]] += 1.5
+    pred = {
+        "mlp_offsets": torch.from_numpy((c - loc).astype(np.float32)),
+        "mlp_bounds": torch.from_numpy((sizes[which] * rng.uniform(0.85, 1.15, (s, 3))).astype(np.float32)),
+        "mlp_bb_scores": torch.from_numpy(rng.normal(0, 2, (s, 1)).astype(np.float32)),
+        "mlp_per_vox_semantics": torch.from_numpy(logits),
+    }
+    batch["vox_segments"] = [seg.copy()]
+    batch["vox2point"] = [torch.from_numpy(rng.integers(0, n_vox, int(1.5 * n_vox))).long()]
+    return batch, pred
+
+
+def golden_decode_s3dis():
+    """The reference's detection2mask with requires_voxel_outputs=True (per-voxel semantics -> per-segment torch.mode,
+    no mask-NMS; models/detection_net.py:378-381,395-415,449-451) -> tests/golden/decode_s3dis.npz."""
+    from types import SimpleNamespace
+    from box2mask_b200.synthetic import label_maps
+    from oracle import me_shim
+    me_shim.install()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import models.detection_net as ref_det
+    cfg, _, _ = variant_config("s3dis")
+    valid, _, is_fg = label_maps(13)
+    batch, pred = decode_inputs_s3dis()
+    stub = SimpleNamespace(semantic_valid_class_ids=valid, is_foreground=is_fg, requires_voxel_outputs=True)
+    if not hasattr(np, "bool"):          # the reference uses the removed alias np.bool (detection_net.py:451)
+        np.bool = bool
+    out = {}
+    for mode in ("eval", "train"):
+        res = ref_det.SelectionNet.detection2mask(stub, batch, {k: v.clone() for k, v in pred.items()}, cfg, mode, True,
+                                                  *cfg.eval_ths)
+        for name, r in res.items():
+            out["%s_%s_conf" % (mode, name)] = np.asarray(r["conf"], dtype=np.float32)
+            out["%s_%s_label_id" % (mode, name)] = np.asarray(r["label_id"], dtype=np.int32)
+            out["%s_%s_mask" % (mode, name)] = np.packbits(np.asarray(r["mask"], dtype=bool), axis=1)
+            out["%s_%s_mask_shape" % (mode, name)] = np.array(r["mask"].shape)
+            if mode == "train":
+                out["train_%s_reps" % name] = np.asarray(r["cluster_representatives"], dtype=np.int64)
+            print("s3dis", mode, name, "instances", len(r["conf"]), "mask", tuple(r["mask"].shape))
+    np.savez_compressed(os.path.join(OUT, "decode_s3dis.npz"), **out)
+
+
 def decode_inputs(seed=11):
     """A small seeded batch + head outputs whose boxes form clusters (shared by the golden and the tests)."""
     from box2mask_b200.synthetic import make_batch
@@ -177,6 +334,8 @@ if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference not mounted at %s" % REF)
     os.makedirs(OUT, exist_ok=True)
-    golden_nms()
-    golden_net()
-    golden_decode()
+    only = sys.argv[1:]
+    for name, fn in (("nms", golden_nms), ("net", golden_net), ("decode", golden_decode), ("variants", golden_variants),
+                     ("decode_s3dis", golden_decode_s3dis)):
+        if not only or name in only:
+            fn()

@@ -180,6 +180,19 @@ def detection_loss(pred, batch, cfg, epoch, semantic_id2idx):
     if "mlp_bounds" in cfg.network_heads:
         parts["bounds_loss"] = torch.mean(torch.sum(torch.abs(sel(pred["mlp_bounds"]) - sel(batch["gt_bb_bounds"])), 1))
         total = total + cfg.loss_weight_bb_bounds * parts["bounds_loss"]
+    if getattr(cfg, "use_bb_iou_loss", False):
+        # optional IoU loss, models/model.py:91-129: 1 - IoU with union clamped from below by 1e-6 (no +eps)
+        loc = sel(batch["input_location"])
+        pb = torch.clamp(sel(pred["mlp_bounds"]), min=cfg.min_bb_size)
+        pc, gc, gb = sel(pred["mlp_offsets"]) + loc, sel(batch["gt_bb_offsets"]) + loc, sel(batch["gt_bb_bounds"])
+        pr, gt = torch.cat([pc - pb, pc + pb], 1), torch.cat([gc - gb, gc + gb], 1)
+        area1 = (pr[:, 3] - pr[:, 0]) * (pr[:, 4] - pr[:, 1]) * (pr[:, 5] - pr[:, 2])
+        area2 = (gt[:, 3] - gt[:, 0]) * (gt[:, 4] - gt[:, 1]) * (gt[:, 5] - gt[:, 2])
+        wh = (torch.min(pr[:, 3:], gt[:, 3:]) - torch.max(pr[:, :3], gt[:, :3])).clamp(min=0)
+        overlap = wh[:, 0] * wh[:, 1] * wh[:, 2]
+        union = torch.max(area1 + area2 - overlap, overlap.new_tensor([1e-6]))
+        parts["iou_loss"] = torch.mean(1.0 - overlap / union)
+        total = total + cfg.loss_weight_bb_iou * parts["iou_loss"]
     if "mlp_bb_scores" in cfg.network_heads:
         w = cfg.loss_weight_bb_scores if epoch >= cfg.mlp_bb_scores_start_epoch else 0
         loc = sel(batch["input_location"])
@@ -194,5 +207,9 @@ def detection_loss(pred, batch, cfg, epoch, semantic_id2idx):
         gt = semantic_id2idx[batch["gt_semantics"]]
         parts["semantics_loss"] = F.cross_entropy(pred["mlp_semantics"], gt, ignore_index=-100)
         total = total + cfg.loss_weight_semantics * parts["semantics_loss"]
+    if "mlp_per_vox_semantics" in cfg.network_heads:       # models/model.py:213-224
+        gt = semantic_id2idx[batch["gt_per_vox_semantics"]]
+        parts["per_vox_semantics_loss"] = F.cross_entropy(pred["mlp_per_vox_semantics"], gt, ignore_index=-100)
+        total = total + cfg.loss_weight_per_vox_semantics * parts["per_vox_semantics_loss"]
     parts["optimization_loss"] = total
     return parts

@@ -424,3 +424,90 @@ def test_detection2mask_matches_reference_golden(golden_dir):
             assert np.array_equal(r["mask"].numpy(), ref)
             if mode == "train":
                 assert np.array_equal(r["cluster_representatives"].numpy(), g["train_%s_reps" % name])
+
+
+def test_detection2mask_s3dis_branch_matches_reference_golden(golden_dir):
+    """S3DIS decode (per-voxel semantics head -> per-segment mode, no mask-NMS; models/detection_net.py:378-381,395-415,
+    449-451) on the GPU against the reference's own detection2mask (tests/golden/decode_s3dis.npz)."""
+    from types import SimpleNamespace
+    from box2mask_b200 import decode
+    from box2mask_b200.synthetic import label_maps
+    from oracle.make_golden import decode_inputs_s3dis, variant_config
+    g = np.load(os.path.join(golden_dir, "decode_s3dis.npz"))
+    cfg, _, _ = variant_config("s3dis")
+    valid, _, is_fg = label_maps(13)
+    batch, pred = decode_inputs_s3dis()
+    net = SimpleNamespace(device=DEV, semantic_valid_class_ids=valid, is_foreground=is_fg, requires_voxel_outputs=True)
+    name = batch["scene"][0]["name"]
+    for mode in ("eval", "train"):
+        r = decode.detection2mask(net, batch, pred, cfg, mode, True, *cfg.eval_ths)[name]
+        assert np.allclose(r["conf"].numpy(), g["%s_%s_conf" % (mode, name)], rtol=0, atol=2e-7)
+        assert np.array_equal(np.asarray(r["label_id"]), g["%s_%s_label_id" % (mode, name)])
+        shape = tuple(g["%s_%s_mask_shape" % (mode, name)])
+        ref = np.unpackbits(g["%s_%s_mask" % (mode, name)], axis=1)[:, :shape[1]].astype(bool)
+        assert tuple(r["mask"].shape) == shape and np.array_equal(r["mask"].numpy(), ref)
+        if mode == "train":
+            assert np.array_equal(r["cluster_representatives"].numpy(), g["train_%s_reps" % name])
+
+
+def test_label_vote_kernels():
+    rng = np.random.default_rng(3)
+    n_vox, k, n_lab = 20011, 37, 21
+    label = rng.integers(0, n_lab, n_vox).astype(np.int32)
+    masks = rng.random((k, n_vox)) < rng.random((k, 1)) * 0.3
+    masks[5] = False                                                     # an empty mask votes for label 0
+    packed = ops.pack_masks_torch(torch.from_numpy(masks).to(DEV))
+    best, counts = ops.mask_label_vote(packed, torch.from_numpy(label).to(DEV), n_vox, n_lab)
+    ref_counts = np.stack([np.bincount(label[m], minlength=n_lab) for m in masks])
+    assert np.array_equal(counts.cpu().numpy(), ref_counts)
+    assert np.array_equal(best.cpu().numpy(), ref_counts.argmax(1))       # np.argmax: lowest label on ties
+    seg = rng.integers(0, 500, n_vox)
+    seg[:40] = 7
+    label[:40] = np.tile([4, 2], 20)                                      # a tie: torch.mode / np.argmax take the lower label
+    label[seg == 7] = np.where(np.arange((seg == 7).sum()) % 2 == 0, 4, 2)
+    best, counts = ops.segment_label_vote(torch.from_numpy(seg).to(DEV), torch.from_numpy(label).to(DEV), 500, n_lab)
+    for sid in (0, 7, 123, 499):
+        sel = torch.from_numpy(label[seg == sid]).long()
+        if len(sel):
+            assert int(best[sid]) == int(torch.mode(sel)[0]), sid
+    assert int(counts.sum()) == n_vox
+
+
+def test_nms_clustering_drop_in_cluster_lists(golden_dir):
+    """decode.NMS_clustering keeps the reference's return values: representatives, per-cluster member lists in
+    descending-score order, heat-maps (models/iou_nms.py:68-105) — against the reference-generated fixture."""
+    from box2mask_b200.decode import NMS_clustering
+    g = np.load(os.path.join(golden_dir, "nms_medium.npz"))
+    reps, clusters, heat = NMS_clustering(torch.from_numpy(g["boxes"]).to(DEV), float(g["th"]))
+    assert np.array_equal(reps.cpu().numpy(), g["reps"]) and np.array_equal(heat.cpu().numpy(), g["heat"])
+    assert [len(c) for c in clusters] == g["cluster_sizes"].tolist()
+    assert np.array_equal(torch.cat(clusters).cpu().numpy(), g["cluster_members"])
+
+
+def test_sparse_tensor_validates_and_deduplicates():
+    """ME.SparseTensor contract (models/model.py:43): out-of-range coordinates raise, duplicate coordinates collapse onto
+    their first occurrence with the features re-indexed (unique_index / inverse_mapping); unique input keeps its order."""
+    import box2mask_b200
+    ME = box2mask_b200.install_as_minkowski_engine()
+    rng = np.random.default_rng(0)
+    base = np.unique(rng.integers(0, 40, (3000, 3)), axis=0).astype(np.int32)
+    coords = np.concatenate([np.zeros((len(base), 1), np.int32), base], 1)
+    feats = torch.from_numpy(rng.normal(size=(len(coords), 6)).astype(np.float32))
+    st = ME.SparseTensor(feats, torch.from_numpy(coords), device=DEV)
+    assert st.unique_index is None and torch.equal(st.C.cpu(), torch.from_numpy(coords)) and torch.equal(st.F.cpu(), feats)
+    dup_rows = rng.integers(0, len(coords), 500)
+    c2 = np.concatenate([coords, coords[dup_rows]], 0)
+    perm = rng.permutation(len(c2))
+    c2 = c2[perm]
+    f2 = torch.from_numpy(rng.normal(size=(len(c2), 6)).astype(np.float32))
+    st2 = ME.SparseTensor(f2, torch.from_numpy(c2), device=DEV)
+    assert len(st2) == len(coords)
+    _, first = np.unique(c2, axis=0, return_index=True)
+    ui = np.sort(first)                                                   # first occurrences, in input order
+    assert np.array_equal(st2.unique_index.cpu().numpy(), ui)
+    assert torch.equal(st2.C.cpu(), torch.from_numpy(c2[ui])) and torch.equal(st2.F.cpu(), f2[ui])
+    assert np.array_equal(c2[ui][st2.inverse_mapping.cpu().numpy()], c2)
+    bad = coords.copy()
+    bad[3, 2] = 40000
+    with pytest.raises(RuntimeError):
+        ME.SparseTensor(feats, torch.from_numpy(bad), device=DEV)

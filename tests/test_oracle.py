@@ -235,3 +235,27 @@ def test_voxelize_restatement_invariants():
     assert np.array_equal(r["unique_vox_segments"][r["seg2vox"]], r["vox_segments"])
     ids = ovz.to_unique([np.array([5, 5, 9]), np.array([2, 7, 7])])
     assert ids.tolist() == [0, 0, 1, 2, 3, 3]
+
+
+def test_decode_scene_voxel_semantics_matches_reference(golden_dir):
+    """S3DIS branch of detection2mask (per-voxel semantics -> per-segment mode, no mask-NMS): the oracle against the
+    fixture produced by the reference's own code (tests/golden/decode_s3dis.npz)."""
+    from box2mask_b200.synthetic import label_maps
+    from oracle.make_golden import decode_inputs_s3dis, variant_config
+    g = np.load(os.path.join(golden_dir, "decode_s3dis.npz"))
+    cfg, _, _ = variant_config("s3dis")
+    _, _, is_fg = label_maps(13)
+    batch, pred = decode_inputs_s3dis()
+    boxes = onms.to_boxes(batch["input_location"], pred["mlp_offsets"], pred["mlp_bounds"], torch.sigmoid(pred["mlp_bb_scores"]))
+    labels = torch.argmax(pred["mlp_per_vox_semantics"], 1)
+    r = onms.decode_scene_voxel_semantics(boxes, labels, batch["vox_segments"][0], batch["seg2vox"][0], is_fg,
+                                          cfg.eval_ths[0], cfg.eval_ths[1], cfg.eval_ths[2])
+    name = batch["scene"][0]["name"]
+    assert np.array_equal(r["conf"].numpy(), g["train_%s_conf" % name])
+    assert np.array_equal(r["label_id"], g["train_%s_label_id" % name])
+    shape = tuple(g["train_%s_mask_shape" % name])
+    ref = np.unpackbits(g["train_%s_mask" % name], axis=1)[:, :shape[1]].astype(bool)
+    assert np.array_equal(r["mask"].numpy(), ref)
+    assert np.array_equal(r["representatives"].numpy(), g["train_%s_reps" % name])
+    ev = np.unpackbits(g["eval_%s_mask" % name], axis=1)[:, :int(g["eval_%s_mask_shape" % name][1])].astype(bool)
+    assert np.array_equal(r["mask"][:, batch["vox2point"][0]].numpy(), ev)
