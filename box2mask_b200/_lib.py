@@ -33,6 +33,9 @@ SIGNATURES = {
     "b2m_kernel_map_sort_workspace_bytes": (c_size_t, [c_int64]),
     "b2m_kernel_map_sort": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P, _P, _P, c_size_t, _P]),
     "b2m_conv_forward": (c_int32, [_P, c_int64, c_int32, _P, _P, _P, c_int32, c_int64, _P, c_int32, _P, _P, _P]),
+    "b2m_conv_forward_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
+    "b2m_conv_forward_ex": (c_int32, [_P, c_int64, c_int32, _P, _P, _P, c_int32, c_int64, _P, c_int32, _P, _P, _P, _P, _P,
+                                      c_int32, _P, c_int32, _P, c_size_t, _P]),
     "b2m_conv_wgrad": (c_int32, [_P, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int32, c_int64, _P, _P]),
     "b2m_colstats": (c_int32, [_P, c_int64, c_int32, _P, _P]),
     "b2m_bn_forward": (c_int32, [_P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, c_float, c_float, c_int32, _P, c_int32,

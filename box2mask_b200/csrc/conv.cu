@@ -181,9 +181,35 @@ struct FwdArgs {
   int cps, ncg, a_slot_bytes;   // KPACK == 1: 64-wide chunks per A stage (1 or 2), stages per offset, bytes of an A slot
   int off_b, off_stage, off_csum, off_bars, tmem_cols;
   int ablate;   // debug builds (B2M_ABLATE env): 1 = no A gathers, 2 = no MMAs, 4 = no epilogue stores, 8 = no B copies
+  // fused epilogue (all optional): v = acc * scale[col] + shift[col] (+ residual[row][col]) (ReLU); statistics are
+  // taken of v. Eval-mode BatchNorm folded into the convolution, bias + ReLU of the MLP heads, fp32 logits.
+  const float* ep_scale; const float* ep_shift; const uint16_t* ep_res; int ep_relu;
+  float* y32; int c_store;      // fp32 output [n_out, c_store] (c_store <= c_n real columns) instead of the bf16 y
+  // offsets split over gridDim.z CTAs (levels with few row tiles): slice z accumulates offset groups
+  // [z * kg_per, (z + 1) * kg_per) and writes its fp32 partial tile to part[z][n_out][c_n]; conv_finalize_kernel sums
+  // the slices in a fixed order (deterministic), applies the epilogue and takes the statistics.
+  float* part; int ksplit, kg_per;
+  int off_ep;
 };
 
-__device__ __forceinline__ MaskBits fwd_tile_mask(const FwdArgs& a, int tile) {
+// bits [lo, hi) of a 128-bit mask
+__device__ __forceinline__ uint32_t range_word(int lo, int hi, int wd) {
+  const int b0 = max(lo - 32 * wd, 0), b1 = min(hi - 32 * wd, 32);
+  if (b1 <= b0) return 0u;
+  const uint32_t upto = (b1 == 32) ? 0xFFFFFFFFu : ((1u << b1) - 1u);
+  return upto & ~((1u << b0) - 1u);       // b0 < 32 here
+}
+// the kernel offsets this CTA accumulates: all of them, or slice blockIdx.z of the offset groups (a.ksplit > 1)
+__device__ __forceinline__ MaskBits fwd_slice_mask(const FwdArgs& a) {
+  MaskBits m;
+  if (a.ksplit <= 1) { m.w0 = m.w1 = m.w2 = m.w3 = 0xFFFFFFFFu; return m; }
+  const int lo = (int)blockIdx.z * a.kg_per * a.kpack, hi = min(a.nkg, ((int)blockIdx.z + 1) * a.kg_per) * a.kpack;
+  m.w0 = range_word(lo, hi, 0); m.w1 = range_word(lo, hi, 1); m.w2 = range_word(lo, hi, 2); m.w3 = range_word(lo, hi, 3);
+  return m;
+}
+// Offsets present in a 128-row tile, restricted to this CTA's slice. EVERY role (gather warps, weight loader, MMA
+// issuers, epilogue) derives its stage sequence from this one function, which is what keeps them in step.
+__device__ __forceinline__ MaskBits fwd_tile_mask(const FwdArgs& a, int tile, const MaskBits& sl) {
   MaskBits m = mask_zero();
   if (tile < a.n_tiles) {
     if (a.gmask == nullptr) { m.w0 = 1u; return m; }  // identity map (kvol == 1)
@@ -194,6 +220,7 @@ __device__ __forceinline__ MaskBits fwd_tile_mask(const FwdArgs& a, int tile) {
       const MaskBits m2 = mask_load(a.gmask, g0 + 1, a.mwords);
       m.w0 |= m2.w0; m.w1 |= m2.w1; m.w2 |= m2.w2; m.w3 |= m2.w3;
     }
+    m.w0 &= sl.w0; m.w1 &= sl.w1; m.w2 &= sl.w2; m.w3 &= sl.w3;
   }
   return m;
 }
@@ -256,6 +283,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
   const int n0 = blockIdx.y * a.ntile;
   const int nch = a.nfull + a.rem;
   const int nst = (KPACK == 1) ? a.ncg : nch;     // pipeline stages (and weight slots) per offset group
+  const MaskBits sl = fwd_slice_mask(a);
   if (warp == 0) B2M_TRACE(0);
 
   if (warp == 4 && lane == 0) {
@@ -267,8 +295,16 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
   }
   if (warp == 6) { tmem_alloc(smem_u32(tmem_ptr_s), (uint32_t)a.tmem_cols); tmem_relinquish(); }
   if (warp == 7 && lane == 0) { tma_prefetch_desc(&tm_main); tma_prefetch_desc(&tm_rem); }
-  if (warp < kEpiWarps)
+  if (warp < kEpiWarps) {
     for (int i = tid; i < 2 * a.ntile; i += kEpiWarps * 32) reinterpret_cast<double*>(smem + a.off_csum)[i] = 0.0;
+    if (a.ep_scale != nullptr || a.ep_shift != nullptr) {
+      float* ep = reinterpret_cast<float*>(smem + a.off_ep);
+      for (int i = tid; i < a.ntile; i += kEpiWarps * 32) {
+        ep[i] = a.ep_scale ? __ldg(a.ep_scale + n0 + i) : 1.f;
+        ep[a.ntile + i] = a.ep_shift ? __ldg(a.ep_shift + n0 + i) : 0.f;
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -276,12 +312,19 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
   if (warp == 0) B2M_TRACE(1);
 
   if (warp < kEpiWarps) {
-    // ================= epilogue warps: TMEM -> registers -> (staging for the column statistics) + row stores ====
+    // ================= epilogue warps: TMEM -> registers -> fused epilogue -> statistics + row stores ====
     // A lane owns one output row: its 32 (16) accumulator columns of a chunk go to global memory straight from
     // registers (64 contiguous bytes per row); the transposed copy in shared memory only feeds the per-column
     // sum / sum of squares, which accumulate in fp64 in shared memory and reach colsum once per CTA.
+    // Fused epilogue (optional): v = acc * scale[col] + shift[col] (+ residual[row][col]) (ReLU) - eval-mode BatchNorm
+    // folded into the convolution, bias + ReLU of the MLP heads. Split mode (a.part): the raw fp32 accumulators go to
+    // this slice's partial tile instead and conv_finalize_kernel does the rest.
     const uint32_t stage_a = smem_base + a.off_stage + warp * (32 * kStagePitch * 4);
     const uint32_t csum_a = smem_base + a.off_csum;
+    const uint32_t ep_a = smem_base + a.off_ep;              // [2][ntile] floats: scale, shift of this CTA's columns
+    const bool ep_affine = (a.ep_scale != nullptr) || (a.ep_shift != nullptr);
+    const bool split = a.part != nullptr;
+    float* part = split ? a.part + (int64_t)blockIdx.z * a.n_out * a.c_n : nullptr;
     int wi = 0;
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
       const int par = wi & 1;
@@ -291,12 +334,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       for (int t = 0; t < a.T; ++t) {
         const int tile = w * a.T + t;
         if (tile >= a.n_tiles) break;
-        const MaskBits m = fwd_tile_mask(a, tile);
+        const MaskBits m = fwd_tile_mask(a, tile, sl);
         const bool has_acc = (m.w0 | m.w1 | m.w2 | m.w3) != 0;
         const int64_t pos = (int64_t)tile * kTileM + warp * 32 + lane;  // this lane's row (position in `order`)
         int32_t orow = -1;
         if (pos < a.n_out) orow = a.order ? __ldg(a.order + pos) : (int32_t)pos;
-        uint16_t* yrow = a.y + (int64_t)(orow >= 0 ? orow : 0) * a.c_n + n0;
+        const int64_t rbase = (int64_t)(orow >= 0 ? orow : 0) * a.c_n + n0;
         const int nchunk32 = (a.ntile + 31) >> 5;
         for (int cc = 0; cc < nchunk32; ++cc) {
           const int cw = min(32, a.ntile - cc * 32);   // 32 or 16
@@ -307,6 +350,46 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
             if (cw == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
             tmem_ld_wait();
           } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+          if (split) {
+            // raw fp32 accumulators of this offset slice: 128 contiguous bytes per row
+            if (orow >= 0) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (q * 4 < cw)
+                  *reinterpret_cast<uint4*>(part + rbase + cc * 32 + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            }
+            continue;
+          }
+          if (ep_affine) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < cw)
+                v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), ld_shared_f32(ep_a + (cc * 32 + j) * 4),
+                                            ld_shared_f32(ep_a + (a.ntile + cc * 32 + j) * 4)));
+          }
+          if (a.ep_res != nullptr && orow >= 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < cw) {
+                const uint4 r = __ldg(reinterpret_cast<const uint4*>(a.ep_res + rbase + cc * 32 + q * 8));
+                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(rb[e]);
+                  v[q * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e]) + f.x);
+                  v[q * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e + 1]) + f.y);
+                }
+              }
+            }
+          }
+          if (a.ep_relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
+          }
+          if (ep_affine && orow < 0) {      // padding rows of the last tile must not enter the statistics
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0u;
           }
@@ -328,15 +411,26 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
             }
           }
           if (orow >= 0 && !B2M_ABLATE(a, 2)) {
+            if (a.y32 != nullptr) {
+              // fp32 rows of c_store real columns (class logits): scalar stores, the row pitch is not 16-byte aligned
+              float* yr = a.y32 + (int64_t)orow * a.c_store;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q * 8 < cw) {
-                uint4 o;
-                __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+              for (int j = 0; j < 32; ++j) {
+                const int col = n0 + cc * 32 + j;
+                if (j < cw && col < a.c_store) yr[col] = __uint_as_float(v[j]);
+              }
+            } else {
+              uint16_t* yrow = a.y + rbase;
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  ob[e] = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
-                *reinterpret_cast<uint4*>(yrow + cc * 32 + q * 8) = o;
+              for (int q = 0; q < 4; ++q) {
+                if (q * 8 < cw) {
+                  uint4 o;
+                  __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    ob[e] = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+                  *reinterpret_cast<uint4*>(yrow + cc * 32 + q * 8) = o;
+                }
               }
             }
           }
@@ -349,7 +443,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       if (warp == 0 && wi == 0) B2M_TRACE(31);
     }
     if (warp == 0) B2M_TRACE(32);
-    if (a.colsum != nullptr) {
+    if (a.colsum != nullptr && !split) {
       named_bar_sync(1, kEpiWarps * 32);   // all four epilogue warps have added their last tile
       const double* cs = reinterpret_cast<const double*>(smem + a.off_csum);
       for (int i = tid; i < 2 * a.ntile; i += kEpiWarps * 32) {
@@ -398,8 +492,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
         const int par = wi & 1;
         mbar_wait(acc_empty + 8 * par, ((uint32_t)(wi >> 1) & 1u) ^ 1u, 2);
         tc_fence_after();
-        const MaskBits m0 = fwd_tile_mask(a, w * a.T);
-        const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
+        const MaskBits m0 = fwd_tile_mask(a, w * a.T, sl);
+        const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1, sl) : mask_zero();
         const MaskBits mu = mask_or(m0, m1);
         const uint32_t d = tmem_base + (uint32_t)((par * a.T + me) * a.colstride);
         uint32_t acc = 0;
@@ -503,8 +597,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     Ring rb;
     rb.init(SB);
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
-      const MaskBits m0 = fwd_tile_mask(a, w * a.T);
-      const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1) : mask_zero();
+      const MaskBits m0 = fwd_tile_mask(a, w * a.T, sl);
+      const MaskBits m1 = (a.T > 1) ? fwd_tile_mask(a, w * a.T + 1, sl) : mask_zero();
       const MaskBits mu = mask_or(m0, m1);
       for (int kg = next_group<KPACK>(mu, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mu, kg + 1, a.nkg, a.mwords)) {
         for (int c = 0; c < nst; ++c) {
@@ -567,7 +661,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
         St s; s.valid = false; s.w = 0; s.kg = 0; s.c = 0; s.slot = 0; s.phase = 0;
         while (w < a.n_work) {
           if (fresh) {
-            mt = fwd_tile_mask(a, w * a.T + t);
+            mt = fwd_tile_mask(a, w * a.T + t, sl);
             kg = next_group<1>(mt, 0, a.nkg, a.mwords);
             d = p - turn; if (d < 0) d += np;
             fresh = false;
@@ -634,7 +728,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       }
     } else
     for (int w = has_work ? (int)blockIdx.x : a.n_work; w < a.n_work; w += gridDim.x) {
-      const MaskBits mt = fwd_tile_mask(a, w * a.T + t);
+      const MaskBits mt = fwd_tile_mask(a, w * a.T + t, sl);
       for (int kg = next_group<KPACK>(mt, 0, a.nkg, a.mwords); kg < a.nkg; kg = next_group<KPACK>(mt, kg + 1, a.nkg, a.mwords)) {
         const uint32_t sub = mask_bits(mt, kg * KPACK, KPACK);
         // jump straight to the chunks of this offset group whose turn is this warp's (stage index = turn + d)
@@ -748,6 +842,89 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// finalize of an offset-split convolution
+// ------------------------------------------------------------------------------------------------
+// v[row][col] = sum over slices z (ascending: deterministic) of part[z][row][col]; then the same fused epilogue as
+// conv_fwd_kernel (scale/shift, residual, ReLU), bf16 (or fp32) store and the per-column sum / sum of squares of v.
+// Thread (rl, g) owns the 8 columns of group g for rows rl, rl + rows-per-pass, ... (coalesced 32-byte fp32 pieces).
+constexpr int kFinThreads = 256;
+__global__ void __launch_bounds__(kFinThreads)
+conv_finalize_kernel(const float* __restrict__ part, int nslices, int64_t n, int c, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const uint16_t* __restrict__ residual, int relu,
+                     uint16_t* __restrict__ y, float* __restrict__ y32, int c_store, double* __restrict__ colsum) {
+  extern __shared__ float fin_sh[];   // [rows per pass][c][2]
+  const int G = c / 8;
+  const int rpp = kFinThreads / G;
+  const int g = threadIdx.x % G, rl = threadIdx.x / G;
+  float s1[8], s2[8], sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s1[i] = 0.f; s2[i] = 0.f;
+    sc[i] = scale ? scale[g * 8 + i] : 1.f;
+    sh[i] = shift ? shift[g * 8 + i] : 0.f;
+  }
+  const bool affine = scale != nullptr || shift != nullptr;
+  if (rl < rpp) {
+    for (int64_t r = (int64_t)blockIdx.x * rpp + rl; r < n; r += (int64_t)gridDim.x * rpp) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      for (int z = 0; z < nslices; ++z) {
+        const float4* p = reinterpret_cast<const float4*>(part + ((int64_t)z * n + r) * c + g * 8);
+        const float4 a0 = __ldg(p), a1 = __ldg(p + 1);
+        v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+        v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+      }
+      if (affine) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
+      }
+      if (residual) {
+        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(residual + r * c) + g);
+        const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(rb[e]);
+          v[2 * e] += f.x; v[2 * e + 1] += f.y;
+        }
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
+      if (y32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (g * 8 + i < c_store) y32[r * c_store + g * 8 + i] = v[i];
+      } else {
+        uint4 o;
+        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        reinterpret_cast<uint4*>(y + r * c)[g] = o;
+      }
+    }
+  }
+  if (colsum == nullptr) return;
+  if (rl < rpp) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      fin_sh[(rl * c + g * 8 + i) * 2] = s1[i];
+      fin_sh[(rl * c + g * 8 + i) * 2 + 1] = s2[i];
+    }
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < c; col += kFinThreads) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int r = 0; r < rpp; ++r) { t1 += fin_sh[(r * c + col) * 2]; t2 += fin_sh[(r * c + col) * 2 + 1]; }
+    atomicAdd(colsum + col, (double)t1);
+    atomicAdd(colsum + c + col, (double)t2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // wgrad kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgEpi = 4;                                       // warps 0-3: epilogue (TMEM lane quarters)
@@ -764,6 +941,7 @@ struct WgArgs {
   int wa, nab;    // X operand: row bytes of a block (128 / 64 / 32) and blocks per A stage (nab * wa / 2 == 128 M rows)
   int wb, nbb;    // dY operand: row bytes of a block and number of column blocks
   int a_slots, b_slots, b_bytes, off_b, off_bars, tmem_cols;
+  int store;      // 1: one CTA owns each dW element (no row splits): plain stores, zeros for offsets without pairs
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -846,13 +1024,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
     const int nchunk32 = (a.c_out + 31) / 32;
     for (int q = 0; q < nq; ++q) {
-      if (!((used >> q) & 1u)) continue;
+      const bool has = ((used >> q) & 1u) != 0;
+      if (!has && !a.store) continue;
       for (int cc = 0; cc < nchunk32; ++cc) {
         const int cw = min(32, a.c_out - cc * 32);
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * a.colstride + cc * 32);
-        if (cw == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-        tmem_ld_wait();
+        if (has) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * a.colstride + cc * 32);
+          if (cw == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (j < cw) st_shared_f32(tr + (lane * kStagePitch + j) * 4, __uint_as_float(v[j]));
@@ -869,7 +1053,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               const uint32_t src = tr + (r * kStagePitch + c4) * 4;
               const float4 val = make_float4(ld_shared_f32(src), ld_shared_f32(src + 4), ld_shared_f32(src + 8),
                                              ld_shared_f32(src + 12));
-              atomicAdd(reinterpret_cast<float4*>(a.dw + ((int64_t)k * a.c_in + ci) * a.c_out + cc * 32 + c4), val);
+              float4* dst = reinterpret_cast<float4*>(a.dw + ((int64_t)k * a.c_in + ci) * a.c_out + cc * 32 + c4);
+              if (a.store) *dst = val; else atomicAdd(dst, val);
             }
           }
         }
@@ -1207,24 +1392,71 @@ extern "C" int b2m_pack_weights_batched(const float* const* kernels, uint16_t* c
   return B2M_OK;
 }
 
+// Offset slices for a convolution with few row tiles (the deep levels): the serial chain of kvol x chunks pipeline
+// stages per tile is what a deep-level launch costs (~1 us per stage with so few CTAs in flight), so the offsets are
+// dealt to up to `sms / (row tiles x column tiles)` CTAs per tile; the slices' fp32 partial tiles are summed in a
+// fixed order by conv_finalize_kernel (deterministic, unlike atomics). Returns 1 when the launch should not split.
+static int conv_offset_slices(int64_t n_out, int32_t c_n, int32_t kvol, int32_t c_red, int* ntiles_n_out) {
+  int ntiles_n = 1;
+  while (c_n / ntiles_n > 256 || (c_n % ntiles_n) != 0 || ((c_n / ntiles_n) % 16) != 0) {
+    ++ntiles_n;
+    if (ntiles_n > 8) { *ntiles_n_out = 0; return 1; }
+  }
+  const int64_t row_tiles = (n_out + kTileM - 1) / kTileM;
+  const int sms = num_sms();
+  const int kpack = conv_kpack(c_red);
+  const int nkg = (kvol + kpack - 1) / kpack;
+  int slices = 1;
+  if (!g_opt_nosplit && nkg > 1 && row_tiles * ntiles_n * 2 <= sms) {
+    // 256-wide outputs: two 128-wide column tiles (a 64 KB weight slot per stage would leave two slots)
+    if (c_n / ntiles_n > 128 && (c_n / ntiles_n) % 32 == 0) ntiles_n *= 2;
+    int want = (int)(sms / (row_tiles * ntiles_n));
+    if (want > nkg) want = nkg;
+    if (want < 1) want = 1;
+    const int per = (nkg + want - 1) / want;
+    slices = (nkg + per - 1) / per;
+  } else {
+    // Few row tiles but nothing to split over (1x1 convolutions): spread the output columns over more CTAs.
+    while (row_tiles * ntiles_n * 2 <= sms && (c_n / ntiles_n) % 32 == 0 && c_n / ntiles_n >= 64) ntiles_n *= 2;
+  }
+  *ntiles_n_out = ntiles_n;
+  return slices;
+}
+
+extern "C" size_t b2m_conv_forward_workspace_bytes(int64_t n_out, int32_t c_red, int32_t kvol, int32_t c_n) {
+  if (n_out <= 0 || c_n <= 0 || kvol <= 0 || c_red <= 0) return 0;
+  int ntiles_n = 0;
+  const int slices = conv_offset_slices(n_out, c_n, kvol, c_red, &ntiles_n);
+  return slices > 1 ? (size_t)slices * (size_t)n_out * (size_t)c_n * 4 : 0;
+}
+
 extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, const int32_t* nbr, const int32_t* order,
                                 const uint32_t* group_mask, int32_t kvol, int64_t n_out, const uint16_t* packed_w,
                                 int32_t c_n, uint16_t* y, double* colsum, b2m_stream_t stream) {
-  if (!x || !packed_w || !y || kvol <= 0 || n_out < 0 || n_in < 0) return B2M_ERR_INVALID_ARGUMENT;
+  return b2m_conv_forward_ex(x, n_in, c_red, nbr, order, group_mask, kvol, n_out, packed_w, c_n, y, colsum, nullptr, nullptr,
+                             nullptr, 0, nullptr, 0, nullptr, 0, stream);
+}
+
+extern "C" int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_red, const int32_t* nbr, const int32_t* order,
+                                   const uint32_t* group_mask, int32_t kvol, int64_t n_out, const uint16_t* packed_w,
+                                   int32_t c_n, uint16_t* y, double* colsum, const float* scale, const float* shift,
+                                   const uint16_t* residual, int32_t relu, float* y32, int32_t c_store, void* workspace,
+                                   size_t workspace_bytes, b2m_stream_t stream) {
+  if (!x || !packed_w || (!y && !y32) || kvol <= 0 || n_out < 0 || n_in < 0) return B2M_ERR_INVALID_ARGUMENT;
   if (!nbr && kvol != 1) return B2M_ERR_INVALID_ARGUMENT;
   if (nbr && !group_mask) return B2M_ERR_INVALID_ARGUMENT;
+  if (y32 && (c_store <= 0 || c_store > c_n)) return B2M_ERR_INVALID_ARGUMENT;
   if (c_red <= 0 || (c_red % 16 != 0 && c_red != 8) || c_n <= 0 || c_n % 16 != 0 || c_n > 512 || kvol > 128) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n_out == 0) return B2M_OK;
   if (n_out >= ((int64_t)1 << 31) - 256 || n_in >= ((int64_t)1 << 31) - 256) return B2M_ERR_UNSUPPORTED_SHAPE;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return B2M_ERR_INVALID_ARGUMENT;
-  int ntiles_n = 1;
-  while (c_n / ntiles_n > 256 || (c_n % ntiles_n) != 0 || ((c_n / ntiles_n) % 16) != 0) {
-    ++ntiles_n;
-    if (ntiles_n > 8) return B2M_ERR_UNSUPPORTED_SHAPE;
-  }
-  // Few row tiles (the deep, 256-wide levels): split the output columns over more CTAs so that the serial
-  // chain of kvol * chunks stages per tile runs on narrower (faster) MMAs on otherwise idle SMs.
-  {
+  if (residual && (reinterpret_cast<uintptr_t>(residual) & 15) != 0) return B2M_ERR_INVALID_ARGUMENT;
+  int ntiles_n = 0;
+  int slices = conv_offset_slices(n_out, c_n, kvol, c_red, &ntiles_n);
+  if (ntiles_n == 0) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (slices > 1 && (!workspace || workspace_bytes < (size_t)slices * (size_t)n_out * (size_t)c_n * 4)) {
+    // no (or too small a) workspace: run unsplit, like round 1 (columns spread over more CTAs instead)
+    slices = 1;
     const int64_t row_tiles = (n_out + kTileM - 1) / kTileM;
     while (row_tiles * ntiles_n * 2 <= num_sms() && (c_n / ntiles_n) % 32 == 0 && c_n / ntiles_n >= 64) ntiles_n *= 2;
   }
@@ -1235,6 +1467,14 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   a.ntile = c_n / ntiles_n;
   a.kpack = conv_kpack(c_red);
   a.nkg = (kvol + a.kpack - 1) / a.kpack;
+  a.ksplit = slices;
+  a.kg_per = (a.nkg + slices - 1) / slices;
+  a.part = slices > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
+  // split launches leave the epilogue (and the statistics) to conv_finalize_kernel
+  a.ep_scale = slices > 1 ? nullptr : scale; a.ep_shift = slices > 1 ? nullptr : shift;
+  a.ep_res = slices > 1 ? nullptr : residual; a.ep_relu = slices > 1 ? 0 : (relu ? 1 : 0);
+  a.y32 = slices > 1 ? nullptr : y32; a.c_store = c_store;
+  if (slices > 1) a.colsum = nullptr;
   a.nfull = conv_nfull(c_red);
   a.rem = conv_rem(c_red);
   a.wa = (a.kpack > 1 && a.kpack < 8) ? c_red * 2 : 128;
@@ -1258,9 +1498,10 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   // the lower time per offset = stages * max(that, 0.5 us issuer floor) wins (ties: the larger stage).
   const int stage_bytes = kEpiWarps * 32 * kStagePitch * 4;
   const int csum_bytes = 2 * a.ntile * 8;
+  const int ep_bytes = 2 * a.ntile * 4;
   {
     const int nch = a.nfull + a.rem;
-    const int budget = 227 * 1024 - 1024 - 256 - stage_bytes - csum_bytes - 16 * 32;
+    const int budget = 227 * 1024 - 1024 - 256 - stage_bytes - csum_bytes - ep_bytes - 16 * 32;
     const int force = g_opt_cps;
     float best_cost = 1e30f;
     a.a_slots = 0;
@@ -1297,7 +1538,8 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   a.off_b = a.a_slots * a.a_slot_bytes;
   a.off_stage = a.off_b + a.b_slots * a.b_bytes;
   a.off_csum = (a.off_stage + stage_bytes + 15) / 16 * 16;
-  a.off_bars = (a.off_csum + csum_bytes + 15) / 16 * 16;
+  a.off_ep = (a.off_csum + csum_bytes + 15) / 16 * 16;
+  a.off_bars = (a.off_ep + ep_bytes + 15) / 16 * 16;
   a.tmem_cols = pow2_cols(2 * a.T * a.colstride);
   if (a.tmem_cols > 512) return B2M_ERR_UNSUPPORTED_SHAPE;
   a.ablate = 0;
@@ -1322,7 +1564,12 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
   int gx = sms / ntiles_n;                                  // keep the total CTA count near one per SM
   if (gx < 1) gx = 1;
   if (gx > a.n_work) gx = a.n_work;
-  dim3 grid((unsigned)gx, (unsigned)ntiles_n);
+  if (slices > 1) {
+    gx = sms / (ntiles_n * slices);
+    if (gx < 1) gx = 1;
+    if (gx > a.n_work) gx = a.n_work;
+  }
+  dim3 grid((unsigned)gx, (unsigned)ntiles_n, (unsigned)slices);
   const cudaStream_t st = (cudaStream_t)stream;
   switch (a.kpack) {
     case 1: conv_fwd_kernel<1><<<grid, kFwdThreads, smem_bytes, st>>>(tm_main, tm_rem, a); break;
@@ -1331,6 +1578,15 @@ extern "C" int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, 
     default: conv_fwd_kernel<8><<<grid, kFwdThreads, smem_bytes, st>>>(tm_main, tm_rem, a); break;
   }
   B2M_CHECK_LAUNCH();
+  if (slices > 1) {
+    const int rpp = kFinThreads / (c_n / 8);
+    int64_t blocks = (n_out + rpp - 1) / rpp;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const size_t sh = colsum ? (size_t)rpp * c_n * 2 * sizeof(float) : 0;
+    conv_finalize_kernel<<<(unsigned)blocks, kFinThreads, sh, st>>>(a.part, slices, n_out, c_n, scale, shift, residual,
+                                                                  relu ? 1 : 0, y, y32, c_store, colsum);
+    B2M_CHECK_LAUNCH();
+  }
   return B2M_OK;
 }
 
@@ -1341,7 +1597,10 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
   if (!nbr && kvol != 1) return B2M_ERR_INVALID_ARGUMENT;
   if (nbr && !group_mask) return B2M_ERR_INVALID_ARGUMENT;
   if (c_in <= 0 || c_in % 8 != 0 || c_out <= 0 || c_out % 16 != 0 || c_out > 256 || kvol > 128) return B2M_ERR_UNSUPPORTED_SHAPE;
-  if (n_out == 0) return B2M_OK;
+  if (n_out == 0) {
+    if (cudaMemsetAsync(dw, 0, (size_t)kvol * c_in * c_out * 4, (cudaStream_t)stream) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+    return B2M_OK;
+  }
   if (n_out >= ((int64_t)1 << 31) - 256 || n_in >= ((int64_t)1 << 31) - 256) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) != 0) return B2M_ERR_INVALID_ARGUMENT;
   WgArgs a;
@@ -1364,11 +1623,28 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
   a.tmem_cols = pow2_cols(G * a.colstride);
   const int64_t total_groups = (n_out + kWgRows - 1) / kWgRows;
   const int sms = num_sms();
-  int64_t splits = sms / ((int64_t)columns * mtiles);
-  if (splits < 1) splits = 1;
-  if (splits > total_groups) splits = total_groups;
+  // Row splits. Plenty of row groups: one CTA per SM, as many row splits as fit (the kernel is throughput bound). Few row
+  // groups (the deep levels, where dW is as large as the activations): every extra row split adds a full set of fp32
+  // atomics over dW (measured: 140 CTAs x 256 KB of red.global.add for a 7 MB dW = the whole 50 us of a launch), while
+  // a CTA's serial chain is groups x accumulators stages of ~0.6 us. Pick the split count that minimises
+  // chain + atomics (1 us per MB of atomics, a third of that for the plain stores of the unsplit case).
+  int64_t max_splits = sms / ((int64_t)columns * mtiles);
+  if (max_splits < 1) max_splits = 1;
+  if (max_splits > total_groups) max_splits = total_groups;
+  int64_t splits = max_splits;
+  if (total_groups * columns * mtiles < 8 * (int64_t)sms) {
+    const double dw_mb = (double)kvol * c_in * c_out * 4.0 / 1e6;
+    double best = 1e30;
+    for (int64_t sp = 1; sp <= max_splits; ++sp) {
+      const int64_t gpc = (total_groups + sp - 1) / sp;
+      const double chain = 3.0 + 0.6 * (double)gpc * G;
+      const double atom = (sp == 1) ? dw_mb / 3.0 : (double)sp * dw_mb;
+      if (chain + atom < best - 1e-9) { best = chain + atom; splits = sp; }
+    }
+  }
   a.groups_per_cta = (int)((total_groups + splits - 1) / splits);
   splits = (total_groups + a.groups_per_cta - 1) / a.groups_per_cta;
+  a.store = (splits == 1) ? 1 : 0;
   a.b_bytes = a.nbb * kWgRows * a.wb;
   if (a.b_bytes < 1024) a.b_bytes = 1024;
   a.b_bytes = (a.b_bytes + 1023) / 1024 * 1024;
@@ -1388,6 +1664,8 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
       return B2M_ERR_CUDA_LAUNCH;
     dc->wg_attr = true;
   }
+  if (!a.store && cudaMemsetAsync(dw, 0, (size_t)kvol * c_in * c_out * 4, (cudaStream_t)stream) != cudaSuccess)
+    return B2M_ERR_CUDA_LAUNCH;
   dim3 grid((unsigned)columns, (unsigned)splits, (unsigned)mtiles);
   conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>(tm_x, tm_dy, a);
   B2M_CHECK_LAUNCH();

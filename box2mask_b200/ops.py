@@ -292,21 +292,48 @@ class WeightPacker:
             "pack_weights_batched"), nbytes=sum(k.numel() * 4 for k in self.kernels) + 16 * self.total)
 
 
-def conv_forward(x, kmap, packed_w, kvol, n_out, c_n, colsum=None):
-    """y bf16[n_out, c_n] = sum_k x[nbr[k]] @ B[k] over a sorted KernelMap (None = identity, kvol 1);
-    colsum f64[2*c_n] (zeroed by the caller) optional."""
+class Workspace:
+    """Scratch for the offset-split convolutions (fp32 partial tiles of the deep levels): one growing buffer per
+    (device, stream); a call's partials are consumed by the finalize kernel launched inside the same C-ABI call, so
+    stream order makes reuse by the next call safe."""
+    _buf = {}
+
+    @classmethod
+    def get(cls, nbytes, device):
+        key = (torch.device(device), torch.cuda.current_stream(device).cuda_stream)
+        buf = cls._buf.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 1 << 22), dtype=torch.uint8, device=device)
+            cls._buf[key] = buf
+        return buf
+
+
+def conv_forward(x, kmap, packed_w, kvol, n_out, c_n, colsum=None, scale=None, shift=None, residual=None, relu=False,
+                 out_fp32_cols=None):
+    """y bf16[n_out, c_n] = epilogue(sum_k x[nbr[k]] @ B[k]) over a sorted KernelMap (None = identity, kvol 1).
+    Epilogue (optional): * scale[c_n] + shift[c_n] (+ residual bf16[n_out, c_n]) (ReLU). colsum f64[2*c_n] (zeroed by
+    the caller) accumulates the statistics of the result. out_fp32_cols = c: return fp32 [n_out, c] (the first c
+    columns) instead of bf16."""
     lib = _lib_or_raise()
     _cuda(x, torch.bfloat16, "x")
     nbr = kmap.nbr if kmap is not None else None
     order = kmap.order if kmap is not None else None
     gmask = kmap.gmask if kmap is not None else None
-    y = torch.empty((n_out, c_n), dtype=torch.bfloat16, device=x.device)
-    _run("conv_forward", 1, lambda: check(lib.b2m_conv_forward(
+    y = y32 = None
+    if out_fp32_cols is None:
+        y = torch.empty((n_out, c_n), dtype=torch.bfloat16, device=x.device)
+    else:
+        y32 = torch.empty((n_out, int(out_fp32_cols)), dtype=torch.float32, device=x.device)
+    ws_bytes = lib.b2m_conv_forward_workspace_bytes(n_out, x.shape[1], kvol, c_n)
+    ws = Workspace.get(ws_bytes, x.device) if ws_bytes else None
+    _run("conv_forward", 2 if ws_bytes else 1, lambda: check(lib.b2m_conv_forward_ex(
         ptr(x), x.shape[0], x.shape[1], ptr(nbr), ptr(order), ptr(gmask), kvol, n_out, ptr(packed_w), c_n, ptr(y),
-        ptr(colsum), stream_ptr()), "conv_forward"), flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] * c_n,
+        ptr(colsum), ptr(scale), ptr(shift), ptr(residual), int(bool(relu)), ptr(y32),
+        int(out_fp32_cols) if out_fp32_cols is not None else 0, ptr(ws), ws_bytes, stream_ptr()), "conv_forward"),
+        flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] * c_n,
         nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] + 2.0 * n_out * c_n,
         tag="k%d %d->%d n_in=%d n_out=%d" % (kvol, x.shape[1], c_n, x.shape[0], n_out))
-    return y
+    return y if y32 is None else y32
 
 
 def conv_wgrad(x, dy, kmap, kvol, n_out):
@@ -317,7 +344,7 @@ def conv_wgrad(x, dy, kmap, kvol, n_out):
     order = kmap.order if kmap is not None else None
     gmask = kmap.gmask if kmap is not None else None
     c_in, c_out = x.shape[1], dy.shape[1]
-    dw = torch.zeros((kvol, c_in, c_out), dtype=torch.float32, device=x.device)
+    dw = torch.empty((kvol, c_in, c_out), dtype=torch.float32, device=x.device)    # overwritten (zero-filled inside if needed)
     _run("conv_wgrad", 1, lambda: check(lib.b2m_conv_wgrad(
         ptr(x), x.shape[0], c_in, ptr(dy), c_out, ptr(nbr), ptr(order), ptr(gmask), kvol, n_out, ptr(dw), stream_ptr()),
         "conv_wgrad"),

@@ -153,7 +153,26 @@ int b2m_pack_weights_batched(const float* const* kernels, uint16_t* const* packe
 int b2m_conv_forward(const uint16_t* x, int64_t n_in, int32_t c_red, const int32_t* nbr, const int32_t* order,
                      const uint32_t* group_mask, int32_t kvol, int64_t n_out, const uint16_t* packed_w,
                      int32_t c_n, uint16_t* y, double* colsum, b2m_stream_t stream);
-/* dw[k, ci, co] += sum_j x[nbr[k][j], ci] * dy[order[j], co]   (fp32, caller-zeroed, atomically accumulated)
+/* The same with a fused epilogue and the offset-split path (all extras optional / NULL):
+ *   v = acc * scale[col] + shift[col] (+ residual[row, col]) (ReLU if relu)      scale, shift float[c_n]; residual bf16[n_out, c_n]
+ *   - eval-mode BatchNorm folded into the convolution (scale = gamma / sqrt(var + eps), shift = beta - mean * scale),
+ *     the residual add and ReLU of a BasicBlock (models/resnet.py:70-83), bias + ReLU of the MLP heads
+ *     (models/detection_net.py:170-194; scale NULL, shift = bias);
+ *   - y32 != NULL: the result is written as fp32 rows of c_store <= c_n real columns (class logits of a head whose
+ *     width was padded to a multiple of 16) instead of bf16 y;
+ *   - colsum accumulates the statistics of v (after the epilogue);
+ *   - workspace of b2m_conv_forward_workspace_bytes(n_out, c_red, kvol, c_n) bytes (0 = not needed): on levels with few
+ *     128-row tiles the kernel offsets are dealt to several CTAs per tile, each writes an fp32 partial tile into the
+ *     workspace and a finalize kernel sums them in a fixed order (deterministic) and applies the epilogue. Without a
+ *     workspace the launch runs unsplit. */
+size_t b2m_conv_forward_workspace_bytes(int64_t n_out, int32_t c_red, int32_t kvol, int32_t c_n);
+int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_red, const int32_t* nbr, const int32_t* order,
+                        const uint32_t* group_mask, int32_t kvol, int64_t n_out, const uint16_t* packed_w,
+                        int32_t c_n, uint16_t* y, double* colsum, const float* scale, const float* shift,
+                        const uint16_t* residual, int32_t relu, float* y32, int32_t c_store, void* workspace,
+                        size_t workspace_bytes, b2m_stream_t stream);
+/* dw[k, ci, co] = sum_j x[nbr[k][j], ci] * dy[order[j], co]   (fp32; dw is OVERWRITTEN: with one CTA per element
+ * - few row groups - by plain stores, otherwise zero-filled inside and accumulated with fp32 vector reductions)
  * over a sorted kernel map. x bf16[n_in, c_in], dy bf16[n_out, c_out]; c_in % 8 == 0, c_out % 16 == 0,
  * c_out <= 256. */
 int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t* dy, int32_t c_out,

@@ -170,6 +170,58 @@ def test_conv_forward(kvol, c_in, c_out, n):
     assert torch.allclose(colsum[c_out:].cpu(), (ref * ref).sum(0), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("kvol,c_in,c_out,n", [(27, 256, 256, 700), (27, 96, 96, 515), (8, 128, 96, 3000), (125, 8, 32, 3000)])
+def test_conv_forward_offset_split_equals_unsplit(kvol, c_in, c_out, n):
+    """Few row tiles: the offsets are split over CTAs and summed by the finalize kernel in a fixed order. Same inputs with
+    the split switched off (b2m_set_option) must agree to fp32 summation-order noise, and the split run is deterministic."""
+    from box2mask_b200 import _lib
+    nbr_np, x, w, n = _conv_case(kvol, c_in, c_out, n, seed=3)
+    nbr = ops.sort_kernel_map(torch.from_numpy(nbr_np).to(DEV))
+    xd, wp = x.to(DEV).to(torch.bfloat16), ops.pack_weights(w.to(DEV), 0)
+    assert _lib.load().b2m_conv_forward_workspace_bytes(n, c_in, kvol, c_out) > 0
+    cs1 = torch.zeros(2 * c_out, dtype=torch.float64, device=DEV)
+    y1 = ops.conv_forward(xd, nbr, wp, kvol, n, c_out, cs1)
+    y1b = ops.conv_forward(xd, nbr, wp, kvol, n, c_out)
+    assert torch.equal(y1, y1b)
+    _lib.set_option(_lib.OPT_SPLIT_OFFSETS, 1)
+    try:
+        assert _lib.load().b2m_conv_forward_workspace_bytes(n, c_in, kvol, c_out) == 0
+        cs0 = torch.zeros(2 * c_out, dtype=torch.float64, device=DEV)
+        y0 = ops.conv_forward(xd, nbr, wp, kvol, n, c_out, cs0)
+    finally:
+        _lib.set_option(_lib.OPT_SPLIT_OFFSETS, 0)
+    d = (y1.float() - y0.float()).abs()
+    assert bool((d <= 2 ** -7 * y0.float().abs() + 1e-6).all()), float(d.max())     # at most one bf16 ulp apart
+    assert float((d > 0).float().mean()) < 0.02
+    assert torch.allclose(cs1, cs0, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("kvol,c_in,c_out,n", [(27, 96, 96, 515), (27, 128, 96, 40000), (1, 96, 96, 30000), (8, 256, 256, 1500)])
+def test_conv_forward_fused_epilogue(kvol, c_in, c_out, n):
+    """Fused epilogue: v = acc * scale + shift + residual, ReLU (eval-mode BatchNorm folded into the convolution, the
+    residual add of a BasicBlock), statistics of v, on the split and the unsplit path; fp32 output of the first c columns."""
+    nbr_np, x, w, n = _conv_case(kvol, c_in, c_out, n, seed=11)
+    torch.manual_seed(1)
+    scale, shift = torch.rand(c_out) + 0.5, torch.randn(c_out)
+    res = so.bf16_round(torch.randn(n, c_out))
+    acc = so.sparse_conv(x.double(), nbr_np, w.double(), n_out=n)
+    ref = torch.relu(acc * scale.double() + shift.double() + res.double())
+    nbr = ops.sort_kernel_map(torch.from_numpy(nbr_np).to(DEV)) if nbr_np is not None else None
+    xd, wp = x.to(DEV).to(torch.bfloat16), ops.pack_weights(w.to(DEV), 0)
+    cs = torch.zeros(2 * c_out, dtype=torch.float64, device=DEV)
+    y = ops.conv_forward(xd, nbr, wp, kvol, n, c_out, cs, scale=scale.to(DEV), shift=shift.to(DEV),
+                         residual=res.to(DEV).to(torch.bfloat16), relu=True)
+    err = (y.float().cpu().double() - ref).abs()
+    assert bool((err <= 8e-3 * ref.abs() + 2e-2).all()), float(err.max())
+    assert torch.allclose(cs[:c_out].cpu(), ref.sum(0), rtol=1e-4, atol=2e-2)
+    assert torch.allclose(cs[c_out:].cpu(), (ref * ref).sum(0), rtol=1e-4, atol=2e-2)
+    # bias only (scale = None), no ReLU, fp32 logits of the first 13 columns
+    y32 = ops.conv_forward(xd, nbr, wp, kvol, n, c_out, shift=shift.to(DEV), out_fp32_cols=13)
+    ref32 = (acc + shift.double())[:, :13]
+    assert y32.shape == (n, 13) and y32.dtype == torch.float32
+    assert torch.allclose(y32.cpu().double(), ref32, rtol=1e-4, atol=1e-3)
+
+
 def test_conv_forward_real_maps_and_dgrad(scene_coords):
     """Real kernel maps (k3 at L0, k2s2 down/up); dgrad through the mirrored / transposed weight packing."""
     c = torch.from_numpy(scene_coords).to(DEV)
