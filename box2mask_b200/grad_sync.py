@@ -65,3 +65,118 @@ class FlatGradSync:
         for h in self._handles:
             h.remove()
         self._handles = []
+
+
+
+class TrunkGradSync:
+    """Gradient averaging for a network whose trunk runs on the trunk executor (box2mask_b200/trunk.py), overlapped
+    with the backward pass (the DistributedDataParallel contract of /root/reference/models/model.py:24).
+
+    The executor writes the trunk gradients into one flat fp32 buffer in order of completion. > 90 % of the bytes belong
+    to the 256-wide deep levels, and they are complete as soon as backward has climbed back to tensor-stride level 3 on
+    the encoder side - while the full-resolution encoder layers (a few milliseconds of convolutions) are still to
+    come. So:
+      bucket 1  flat[0 : end of `conv4p8s2`]   all-reduced on a side stream from inside backward (on_bucket). While
+                it is in flight the persistent convolution kernels are capped to leave `free_sms` SMs to the NCCL
+                kernels (b2m_set_option(B2M_OPT_MAX_CTAS)); without the cap each NCCL CTA forces a second wave of
+                convolution CTAs (measured in round 1: 45 -> 57 ms per step under DDP).
+      bucket 2  the rest of the trunk (full-resolution encoder, a few MB) + the MLP heads, all-reduced at the end of
+                backward; the main stream then waits for bucket 1.
+    Parameters outside the trunk (the heads) are gathered into a small flat buffer like FlatGradSync does."""
+
+    def __init__(self, net, process_group=None, free_sms=8):
+        ex = net.trunk_executor()
+        self.ex, self.group = ex, process_group
+        self.world = dist.get_world_size(process_group)
+        trunk_ids = {id(p) for p in ex.program.parameters()}
+        self.other = [p for p in net.parameters() if p.requires_grad and id(p) not in trunk_ids]
+        dev = ex.program.parameters()[0].device
+        self.dev = dev
+        sizes = [p.numel() for p in self.other]
+        self.other_flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.other_views = [v.view_as(p) for v, p in zip(torch.split(self.other_flat, sizes), self.other)]
+        self._avg = dist.get_backend(process_group) == "nccl"
+        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self.free_sms = int(free_sms)
+        self.cut = None
+        self.syncs = 0
+        self._bucket1_done = None
+        self._queued = False
+        self.enabled = True
+        ex.bucket_after = "conv4p8s2"
+        ex.on_bucket = self._bucket1
+        ex.on_done = self._trunk_done
+        self._handles = [p.register_post_accumulate_grad_hook(self._on_other_grad) for p in self.other]
+        with torch.no_grad():     # all ranks start from rank 0's parameters and buffers (DDP's constructor does the same)
+            for t in list(net.parameters()) + list(net.buffers()):
+                dist.broadcast(t, src=dist.get_global_rank(process_group, 0) if process_group else 0, group=process_group)
+
+    def _reduce(self, t):
+        if self._avg:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.world)
+        self.syncs += 1
+
+    def _queue_finish(self):
+        if self.enabled and not self._queued:
+            self._queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._finish)
+
+    def _on_other_grad(self, _p):
+        self._queue_finish()
+
+    def _bucket1(self):
+        """Inside backward, right after the last deep-level unit: everything before `cut` is final."""
+        if not self.enabled:
+            return
+        grads = self.ex.grads
+        unit = next(u for u in self.ex.program.units if u.name == self.ex.bucket_after)
+        self.cut = grads.end_of(unit.bn.bn.bias)
+        if self.comm_stream is None:          # CPU (gloo) tests: no streams, reduce in place right away
+            self._reduce(grads.flat[:self.cut])
+            return
+        from . import _lib
+        cur = torch.cuda.current_stream(self.dev)
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            self._reduce(grads.flat[:self.cut])
+            self._bucket1_done = torch.cuda.Event()
+            self._bucket1_done.record(self.comm_stream)
+        sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        _lib.set_option(_lib.OPT_MAX_CTAS, max(sms - self.free_sms, 1))     # applies to the launches enqueued from here on
+
+    def _trunk_done(self):
+        self._queue_finish()
+
+    @torch.no_grad()
+    def _finish(self):
+        """End of the whole backward pass (autograd engine callback)."""
+        self._queued = False
+        grads = self.ex.grads
+        if self.comm_stream is not None:
+            from . import _lib
+            _lib.set_option(_lib.OPT_MAX_CTAS, 0)
+        if grads is not None and self.cut is not None:
+            self._reduce(grads.flat[self.cut:])
+        have = [(v, p.grad) for v, p in zip(self.other_views, self.other) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        missing = [v for v, p in zip(self.other_views, self.other) if p.grad is None]
+        if missing:
+            torch._foreach_zero_(missing)
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        if self.other:
+            self._reduce(self.other_flat)
+            for v, p in zip(self.other_views, self.other):
+                p.grad = v
+        if self._bucket1_done is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self._bucket1_done)
+            self._bucket1_done = None
+        self.cut = None
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+        self.ex.on_bucket = self.ex.on_done = None

@@ -229,7 +229,8 @@ class _GlobalPool(nn.Module):
         out = fn.apply(feats.contiguous(), ids, s)
         coords = torch.zeros((s, 4), dtype=torch.int32, device=out.device)
         coords[:, 0] = torch.arange(s, dtype=torch.int32, device=out.device)
-        return SparseTensor(out, coords, device=out.device)
+        from .sparse_tensor import CoordinateManager
+        return SparseTensor(out, coordinate_manager=CoordinateManager(coords))   # unique by construction
 
 
 class MinkowskiGlobalAvgPooling(_GlobalPool):
@@ -265,7 +266,14 @@ def prepack_conv_weights(module):
         state = (convs, ops.WeightPacker(jobs, convs[0].kernel.device))
         module.__dict__["_b2m_packer"] = state
     packer = state[1]
+    versions = tuple(m.kernel._version for m in convs)
+    # Inference only: skip the packing when no kernel was modified since the last one. In training mode the images are
+    # ALWAYS rebuilt: fused optimizers (torch.optim.Adam(fused=True)) update parameters without bumping `_version`.
+    if not module.training and module.__dict__.get("_b2m_packed_versions") == (id(packer), versions):
+        return
     packer.run()
+    # recorded for eval-mode packings only, so that the first inference pass after training always repacks
+    module.__dict__["_b2m_packed_versions"] = None if module.training else (id(packer), versions)
     for i, m in enumerate(convs):
         m.__dict__["_prepacked"] = (packer.buffers[2 * i], packer.buffers[2 * i + 1], m.kernel._version,
                                     _round16(m.in_channels), _dgrad_mode(m))

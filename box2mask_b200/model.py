@@ -39,12 +39,18 @@ class Model:
         self.net = self.detection_model   # the un-wrapped network (state-dict owner)
         self.grad_sync = None
         if cfg.multigpu:
-            # models/model.py:23-25: gradient averaging over the scene-sharded ranks + SyncBatchNorm. The default is one
-            # flat all-reduce after backward (grad_sync.py: overlapping NCCL with the persistent conv kernels costs more
-            # than the sub-millisecond collective); cfg.grad_sync = "ddp" keeps torch's bucketed, overlapped DDP.
-            if getattr(cfg, "grad_sync", "flat") == "ddp":
+            # models/model.py:23-25: gradient averaging over the scene-sharded ranks + SyncBatchNorm.
+            # cfg.grad_sync: "overlap" (default) = the deep levels' gradients all-reduced from inside backward on a side
+            # stream (grad_sync.TrunkGradSync); "flat" = one all-reduce after backward; "ddp" = torch's bucketed DDP.
+            mode = getattr(cfg, "grad_sync", "overlap")
+            if mode == "ddp":
+                self.net.use_trunk_executor = False      # DDP needs autograd's per-parameter hooks
                 self.detection_model = torch.nn.parallel.DistributedDataParallel(
                     self.detection_model, device_ids=[torch.device(device).index], gradient_as_bucket_view=True)
+            elif mode == "overlap" and self.net.use_trunk_executor:
+                # deep-level gradients all-reduced on a side stream from inside the trunk's backward pass
+                from .grad_sync import TrunkGradSync
+                self.grad_sync = TrunkGradSync(self.net, free_sms=getattr(cfg, "grad_sync_free_sms", 8))
             else:
                 from .grad_sync import FlatGradSync
                 self.grad_sync = FlatGradSync(self.net)

@@ -336,7 +336,9 @@ def conv_forward(x, kmap, packed_w, kvol, n_out, c_n, colsum=None, scale=None, s
     return y if y32 is None else y32
 
 
-def conv_wgrad(x, dy, kmap, kvol, n_out):
+def conv_wgrad(x, dy, kmap, kvol, n_out, out=None):
+    """dw f32 [kvol, c_in, c_out] (overwritten). out: optional destination with kvol * c_in * c_out contiguous floats
+    (e.g. a slice of a flat gradient buffer)."""
     lib = _lib_or_raise()
     _cuda(x, torch.bfloat16, "x")
     _cuda(dy, torch.bfloat16, "dy")
@@ -344,7 +346,12 @@ def conv_wgrad(x, dy, kmap, kvol, n_out):
     order = kmap.order if kmap is not None else None
     gmask = kmap.gmask if kmap is not None else None
     c_in, c_out = x.shape[1], dy.shape[1]
-    dw = torch.empty((kvol, c_in, c_out), dtype=torch.float32, device=x.device)    # overwritten (zero-filled inside if needed)
+    if out is not None:
+        if out.numel() != kvol * c_in * c_out or out.dtype != torch.float32 or not out.is_contiguous():
+            raise _lib.B2MError("conv_wgrad: out must hold kvol * c_in * c_out contiguous floats")
+        dw = out
+    else:
+        dw = torch.empty((kvol, c_in, c_out), dtype=torch.float32, device=x.device)    # overwritten (zero-filled inside if needed)
     _run("conv_wgrad", 1, lambda: check(lib.b2m_conv_wgrad(
         ptr(x), x.shape[0], c_in, ptr(dy), c_out, ptr(nbr), ptr(order), ptr(gmask), kvol, n_out, ptr(dw), stream_ptr()),
         "conv_wgrad"),
@@ -383,7 +390,7 @@ def bn_forward(x, sums, gamma, beta, running_mean, running_var, momentum, eps, t
 
 
 def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, want_dresidual, n_stat=None,
-                reduce_hook=None, n_stat_dev=None):
+                reduce_hook=None, n_stat_dev=None, dgamma=None, dbeta=None):
     """n_stat_dev: optional f64[1] device tensor with the global row count (SyncBN, no host round trip).
     reduce_hook(red) -> all-reduced copy of red: only dx uses it; dgamma / dbeta stay this rank's own sums."""
     lib = _lib_or_raise()
@@ -398,8 +405,10 @@ def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, wan
         red = reduce_hook(red)  # SyncBN: (sum_g, sum_g*xhat) summed over ranks, in a NEW buffer
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dresidual else None
-    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
-    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    if dgamma is None:
+        dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+    if dbeta is None:
+        dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
     _run("bn_backward_apply", 1, lambda: check(lib.b2m_bn_backward_apply(
         ptr(x), ptr(out), ptr(dout), n, n if n_stat is None else int(n_stat), c, ptr(save_mean), ptr(save_invstd),
         ptr(gamma), ptr(red), ptr(red_local), ptr(n_stat_dev), int(bool(relu)), int(bool(training)), ptr(dx), ptr(dres),

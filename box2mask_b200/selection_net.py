@@ -134,6 +134,9 @@ class SelectionNet(nn.Module):
                 self.requires_voxel_outputs = True
         self.global_avg_pool = ME.MinkowskiGlobalAvgPooling()
         self.global_max_pool = ME.MinkowskiGlobalMaxPooling()
+        # The U-Net trunk runs as one hand-scheduled autograd node (box2mask_b200/trunk.py) unless switched off; the
+        # module-by-module path below it is the drop-in surface the reference's own SelectionNet class uses.
+        self.use_trunk_executor = bool(getattr(cfg, "trunk_executor", False))
         self._init_weights()
 
     # -- construction helpers ---------------------------------------------------------------------
@@ -177,16 +180,10 @@ class SelectionNet(nn.Module):
         ME.prepack_conv_weights(self)      # every conv's forward and dgrad weight image, one launch per step
         x.coordinate_manager.wait_ready()  # maps prefetched on a side stream (Model.prefetch_coordinates), if any
         x.coordinate_manager.prepare(*self.coordinate_plan())   # no-op for levels / maps that already exist
-        stem = conv_bn_act(self.conv0p1s1, self.bn0, x, relu=True)
-        out, skips = stem, []
-        for conv, bn, block, _ in ENCODER:
-            out = conv_bn_act(getattr(self, conv), getattr(self, bn), out, relu=True)
-            out = getattr(self, block)(out)
-            skips.append(out)
-        for conv, bn, block, _, skip in DECODER:
-            out = conv_bn_act(getattr(self, conv), getattr(self, bn), out, relu=True)
-            out = ME.cat(out, stem if skip < 0 else skips[skip])
-            out = getattr(self, block)(out)
+        if self.use_trunk_executor:
+            out = x._like(self.trunk_executor().run(x), 1)
+        else:
+            out = self.forward_trunk_modules(x)
 
         outputs = {}
         if self.requires_voxel_outputs:
@@ -199,7 +196,8 @@ class SelectionNet(nn.Module):
             pooled = fn.apply(out.F.contiguous(), ids, s)
             coords = torch.zeros((s, 4), dtype=torch.int32, device=pooled.device)
             coords[:, 0] = torch.arange(s, dtype=torch.int32, device=pooled.device)
-            out = ME.SparseTensor(pooled, coords, device=pooled.device)
+            # one row per superpoint, keyed by its id: unique by construction, so no coordinate validation pass
+            out = ME.SparseTensor(pooled, coordinate_manager=ME.CoordinateManager(coords))
         for head in self.cfg.network_heads:
             src = outputs["vox_feats"] if (self.requires_voxel_outputs and "per_vox" in head) else out
             res = self.network_heads[head](src)
@@ -207,6 +205,28 @@ class SelectionNet(nn.Module):
                 res = self.relu(res)
             outputs[head] = res
         return outputs
+
+    def trunk_executor(self):
+        ex = self.__dict__.get("_trunk_executor")
+        if ex is None:
+            from .trunk import TrunkExecutor
+            ex = TrunkExecutor(self)
+            self.__dict__["_trunk_executor"] = ex
+        return ex
+
+    def forward_trunk_modules(self, x):
+        """The trunk module by module (the reference's own forward order, models/detection_net.py:235-337)."""
+        stem = conv_bn_act(self.conv0p1s1, self.bn0, x, relu=True)
+        out, skips = stem, []
+        for conv, bn, block, _ in ENCODER:
+            out = conv_bn_act(getattr(self, conv), getattr(self, bn), out, relu=True)
+            out = getattr(self, block)(out)
+            skips.append(out)
+        for conv, bn, block, _, skip in DECODER:
+            out = conv_bn_act(getattr(self, conv), getattr(self, bn), out, relu=True)
+            out = ME.cat(out, stem if skip < 0 else skips[skip])
+            out = getattr(self, block)(out)
+        return out
 
     def get_prediction(self, batch, with_grad=True, to_cpu=False, to_numpy=False, min_size=True):
         """/root/reference/models/detection_net.py:493-521."""

@@ -1,0 +1,365 @@
+"""Trunk executor: the U-Net part of SelectionNet as ONE autograd node with a hand-scheduled forward and backward.
+
+The reference runs the trunk module by module through autograd (/root/reference/models/detection_net.py:235-337,
+models/resnet.py:70-83): ~250 modules, ~540 kernel calls per training step, and on the round-1 build 31 ms of Python
+dispatch per step around 40 ms of GPU work. The trunk is a STATIC program - 81 units of
+convolution -> BatchNorm (+ residual) (+ ReLU) and 7 channel concatenations - so this module compiles it once into a
+step list and executes it directly against the C-ABI ops:
+
+  training forward   conv (column statistics in its epilogue) -> one BatchNorm(+residual)(+ReLU) pass per unit
+  training backward  the reverse list: BatchNorm backward -> wgrad straight into the flat gradient buffer -> dgrad, where
+                     the gradient that is already pending for the unit's input (residual branch, skip connection) is
+                     added in the dgrad epilogue instead of by a separate elementwise pass
+  eval forward       ONE kernel per unit: eval-mode BatchNorm folded into per-column scale/shift of the convolution
+                     epilogue, with the residual add and the ReLU ("BatchNorm and ReLU are fused into the epilogue")
+
+Gradients of the trunk parameters live in one flat fp32 buffer in order of completion during backward (deep levels
+first... see TrunkProgram.param_order), which is what lets data-parallel training start the all-reduce of the deep
+levels' gradients (>90 % of the bytes) on a side stream while the full-resolution encoder layers are still running
+(box2mask_b200/grad_sync.py: TrunkGradSync).
+
+Numerics are those of the module-by-module path (box2mask_b200/me/nn.py), which stays available as the drop-in surface
+and is what the reference's own SelectionNet class runs on; tests compare the two.
+"""
+import torch
+
+from . import ops
+from .me.nn import _dgrad_mode, _round16
+
+
+class Unit:
+    """conv -> BatchNorm (+ residual) (+ ReLU). src / dst / res are tensor ids of the program."""
+    __slots__ = ("name", "conv", "bn", "src", "dst", "res", "relu", "map", "need_dx", "level")
+
+    def __init__(self, name, conv, bn, src, dst, res, relu, map_key, need_dx, level):
+        self.name, self.conv, self.bn, self.src, self.dst, self.res, self.relu = name, conv, bn, src, dst, res, relu
+        self.map, self.need_dx, self.level = map_key, need_dx, level
+
+
+class Cat:
+    __slots__ = ("a", "b", "dst", "ca", "cb")
+
+    def __init__(self, a, b, dst, ca, cb):
+        self.a, self.b, self.dst, self.ca, self.cb = a, b, dst, ca, cb
+
+
+class TrunkProgram:
+    """The step list of a SelectionNet trunk (built once per network)."""
+
+    def __init__(self, net):
+        from .selection_net import DECODER, ENCODER
+        self.net = net
+        self.steps = []
+        self._next = 1                      # tensor id 0 = the network input
+        nlev = len(ENCODER)
+
+        def new():
+            self._next += 1
+            return self._next - 1
+
+        def unit(name, conv, bn, src, res, relu, map_key, level, need_dx=True):
+            dst = new()
+            self.steps.append(Unit(name, conv, bn, src, dst, res, relu, map_key, need_dx, level))
+            return dst
+
+        def stage(name, blocks, x, level):
+            for i, blk in enumerate(blocks):
+                pre = "%s.%d" % (name, i)
+                h = unit(pre + ".conv1", blk.conv1, blk.norm1, x, None, True, ("sub", level, 3), level)
+                r = x
+                if blk.downsample is not None:
+                    r = unit(pre + ".downsample", blk.downsample[0], blk.downsample[1], x, None, False, ("id", level), level)
+                x = unit(pre + ".conv2", blk.conv2, blk.norm2, h, r, True, ("sub", level, 3), level)
+            return x
+
+        stem = unit("conv0p1s1", net.conv0p1s1, net.bn0, 0, None, True, ("sub", 0, net.conv0p1s1.kernel_size), 0, need_dx=False)
+        out, skips = stem, []
+        for l, (conv, bn, block, _) in enumerate(ENCODER):
+            out = unit(conv, getattr(net, conv), getattr(net, bn), out, None, True, ("down", l), l + 1)
+            out = stage(block, getattr(net, block), out, l + 1)
+            skips.append(out)
+        level = nlev
+        for conv, bn, block, width, skip in DECODER:
+            level -= 1
+            up = unit(conv, getattr(net, conv), getattr(net, bn), out, None, True, ("up", level), level)
+            other = stem if skip < 0 else skips[skip]
+            cb = net.conv0p1s1.out_channels if skip < 0 else ENCODER[skip][3]
+            dst = new()
+            self.steps.append(Cat(up, other, dst, width, cb))
+            out = stage(block, getattr(net, block), dst, level)
+        self.out_id = out
+        self.units = [s for s in self.steps if isinstance(s, Unit)]
+        # Parameters in order of gradient completion during backward = reverse program order. `deep_units`: the units
+        # whose gradients are final once backward has left tensor-stride level DEEP_LEVEL on the encoder side.
+        self.param_order = []
+        for u in reversed(self.units):
+            self.param_order += [u.conv.kernel, u.bn.bn.weight, u.bn.bn.bias]
+
+    def parameters(self):
+        return self.param_order
+
+
+def _fold_bn(bn):
+    """Eval-mode BatchNorm as per-column (scale, shift): y = x * scale + shift. Cached on the module, refreshed when
+    any of its tensors changes (version counters)."""
+    b = bn.bn
+    key = (b.weight._version, b.bias._version, b.running_mean._version, b.running_var._version, b.weight.data_ptr())
+    cached = bn.__dict__.get("_b2m_fold")
+    if cached is None or cached[0] != key:
+        with torch.no_grad():
+            scale = (b.weight.float() * torch.rsqrt(b.running_var.float() + b.eps)).contiguous()
+            shift = (b.bias.float() - b.running_mean.float() * scale).contiguous()
+        cached = (key, scale, shift)
+        bn.__dict__["_b2m_fold"] = cached
+    return cached[1], cached[2]
+
+
+class _Maps:
+    """Kernel maps of one batch by program key."""
+
+    def __init__(self, cm):
+        self.cm = cm
+
+    def get(self, key):
+        """-> (forward KernelMap or None, backward KernelMap or None, n_out)"""
+        cm, kind = self.cm, key[0]
+        if kind == "sub":
+            km = cm.submanifold_map(2 ** key[1], key[2])
+            return km, km, km.n_out
+        if kind == "id":
+            return None, None, cm.levels[2 ** key[1]].shape[0]
+        down, up = cm.stride2_maps(2 ** key[1])
+        if kind == "down":
+            return down, up, down.n_out
+        return up, down, up.n_out
+
+
+def _packed(conv):
+    pre = conv.__dict__.get("_prepacked")
+    if pre is None or pre[2] != conv.kernel._version:
+        raise RuntimeError("trunk executor: convolution weights are not packed for this step (prepack_conv_weights)")
+    return pre[0], pre[1]
+
+
+def _sync_group(bn, training):
+    g = getattr(bn, "process_group", None)
+    if g is None or not training or not torch.distributed.is_initialized():
+        return None
+    if g == "default":
+        g = torch.distributed.group.WORLD
+        bn.process_group = g
+    return g
+
+
+class GradBuffer:
+    """Flat fp32 gradient buffer of the trunk parameters, laid out in order of completion during backward; each
+    parameter's `.grad` is pointed at its slice after backward (no copies, like grad_sync.FlatGradSync)."""
+
+    def __init__(self, program):
+        params = program.parameters()
+        dev = params[0].device
+        sizes = [p.numel() for p in params]
+        self.params = params
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.views = [v.view_as(p) for v, p in zip(torch.split(self.flat, sizes), params)]
+        self.index = {id(p): i for i, p in enumerate(params)}
+        self.offsets = [0]
+        for n in sizes:
+            self.offsets.append(self.offsets[-1] + n)
+
+    def view(self, p):
+        return self.views[self.index[id(p)]]
+
+    def end_of(self, param):
+        """flat offset just past `param` (everything before it in completion order included)"""
+        return self.offsets[self.index[id(param)] + 1]
+
+    def stale(self):
+        return any(p.device != self.flat.device for p in self.params)
+
+
+class TrunkFn(torch.autograd.Function):
+    """feats bf16/f32 [N0, C_in] -> trunk output bf16 [N0, 96]. `anchor` is a dummy differentiable scalar that keeps
+    this node in the graph (the trunk parameters are reached through `ex`, not through autograd inputs: their
+    gradients are written into ex.grads and attached to the parameters by backward)."""
+
+    @staticmethod
+    def forward(ctx, anchor, feats, ex, cm):
+        ctx.ex, ctx.cm = ex, cm
+        out, ctx.saved = ex.forward_train(feats, cm)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ctx.ex.backward(ctx.saved, ctx.cm, dout.contiguous())
+        ctx.saved = None
+        return None, None, None, None
+
+
+class TrunkExecutor:
+    def __init__(self, net):
+        self.net = net
+        self.program = TrunkProgram(net)
+        self.grads = None
+        self.anchor = None
+        # data-parallel hooks (grad_sync.TrunkGradSync): on_bucket() fires inside backward right after the unit named
+        # bucket_after (every gradient of the flat buffer up to grads.end_of(bucket_after) is then enqueued), on_done()
+        # after the last unit
+        self.on_bucket = None
+        self.bucket_after = None
+        self.on_done = None
+
+    # ---------------------------------------------------------------------------------------------
+    def _input(self, feats, unit):
+        if feats.dtype == torch.float32:
+            return ops.cast_pad_bf16(feats.contiguous(), _round16(unit.conv.in_channels))
+        if feats.dtype != torch.bfloat16:
+            raise TypeError("features must be float32 or bfloat16")
+        return feats.contiguous()
+
+    def run(self, x):
+        """x: SparseTensor input -> features of the last full-resolution stage, bf16 [N0, 96]."""
+        net = self.net
+        cm = x.coordinate_manager
+        training = net.training and torch.is_grad_enabled()
+        if not net.training:
+            return self.forward_eval(x.F, cm)
+        if not training:
+            out, _ = self.forward_train(x.F, cm)     # training-mode BatchNorm without a graph (validation in train mode)
+            return out
+        if self.grads is None or self.grads.stale():
+            self.grads = GradBuffer(self.program)
+        if self.anchor is None or self.anchor.device != x.F.device:
+            self.anchor = torch.zeros((), device=x.F.device, requires_grad=True)
+        return TrunkFn.apply(self.anchor, x.F, self, cm)
+
+    # ---------------------------------------------------------------------------------------------
+    def forward_eval(self, feats, cm):
+        prog, maps = self.program, _Maps(cm)
+        T = {0: self._input(feats, prog.units[0])}
+        last_use = self._last_use()
+        for i, st in enumerate(prog.steps):
+            if isinstance(st, Cat):
+                T[st.dst] = torch.cat([T[st.a], T[st.b]], 1)
+            else:
+                km_f, _, n_out = maps.get(st.map)
+                scale, shift = _fold_bn(st.bn)
+                res = T[st.res] if st.res is not None else None
+                T[st.dst] = ops.conv_forward(T[st.src], km_f, _packed(st.conv)[0], st.conv.kernel_volume, n_out,
+                                             st.conv.out_channels, None, scale, shift, res, st.relu)
+            for tid in last_use.get(i, ()):
+                T.pop(tid, None)
+        return T[prog.out_id]
+
+    def _last_use(self):
+        lu = self.__dict__.get("_lu")
+        if lu is None:
+            last = {}
+            for i, st in enumerate(self.program.steps):
+                for tid in ((st.a, st.b) if isinstance(st, Cat) else (st.src, st.res)):
+                    if tid is not None:
+                        last[tid] = i
+            lu = {}
+            for tid, i in last.items():
+                lu.setdefault(i, []).append(tid)
+            self._lu = lu
+        return lu
+
+    # ---------------------------------------------------------------------------------------------
+    def forward_train(self, feats, cm):
+        prog, maps = self.program, _Maps(cm)
+        T = {0: self._input(feats, prog.units[0])}
+        saved = []
+        torch._foreach_add_([u.bn.bn.num_batches_tracked for u in prog.units], 1)     # one launch for all 81 counters
+        for st in prog.steps:
+            if isinstance(st, Cat):
+                T[st.dst] = torch.cat([T[st.a], T[st.b]], 1)
+                continue
+            conv, b = st.conv, st.bn.bn
+            km_f, _, n_out = maps.get(st.map)
+            x = T[st.src]
+            c_out = conv.out_channels
+            dev = x.device
+            group = _sync_group(st.bn, True)
+            colsum = ops.ZeroArena.take(2 * c_out + 1, dev) if group is not None else ops.ZeroArena.take(2 * c_out, dev)
+            y = ops.conv_forward(x, km_f, _packed(conv)[0], conv.kernel_volume, n_out, c_out, colsum[:2 * c_out])
+            n_stat, count = n_out, None
+            if group is not None:
+                sums = colsum.clone()
+                sums[-1] = float(n_out)
+                torch.distributed.all_reduce(sums, group=group)
+                count, n_stat = sums[-1:], 0
+            else:
+                sums = colsum
+                if n_out <= 1:
+                    raise ValueError("Expected more than 1 value per channel when training")
+            momentum = b.momentum if b.momentum is not None else 1.0 / float(b.num_batches_tracked)
+            res = T[st.res] if st.res is not None else None
+            out, mean, invstd = ops.bn_forward(y, sums, b.weight.detach(), b.bias.detach(), b.running_mean, b.running_var,
+                                               momentum, b.eps, True, res, st.relu, n_stat)
+            saved.append((x, y, out, mean, invstd, count, n_stat))
+            T[st.dst] = out
+        return T[prog.out_id], saved
+
+    # ---------------------------------------------------------------------------------------------
+    def backward(self, saved, cm, dout):
+        prog, maps, grads = self.program, _Maps(cm), self.grads
+        # gradients are WRITTEN into the flat buffer; anything already accumulated on the parameters (a caller that does
+        # not zero the gradients between backward passes) is carried over and added back at the end
+        carry = None
+        if any(p.grad is not None for p in grads.params):
+            carry = torch.zeros_like(grads.flat)
+            for p, v in zip(grads.params, torch.split(carry, [q.numel() for q in grads.params])):
+                if p.grad is not None:
+                    v.view_as(p).copy_(p.grad)
+        G = {prog.out_id: dout}
+        si = len(saved)
+        for st in reversed(prog.steps):
+            if isinstance(st, Cat):
+                g = G.pop(st.dst)
+                self._acc(G, st.a, g[:, :st.ca].contiguous())
+                self._acc(G, st.b, g[:, st.ca:].contiguous())
+                continue
+            si -= 1
+            x, y, out, mean, invstd, count, n_stat = saved[si]
+            saved[si] = None
+            conv, b = st.conv, st.bn.bn
+            km_f, km_b, n_out = maps.get(st.map)
+            g_out = G.pop(st.dst)
+            group = _sync_group(st.bn, True)
+            hook = None
+            if group is not None:
+                def hook(red, group=group):
+                    tot = red.clone()
+                    torch.distributed.all_reduce(tot, group=group)
+                    return tot
+            dx_bn, dres, _, _ = ops.bn_backward(y, out, g_out, mean, invstd, b.weight.detach(), st.relu, True,
+                                                st.res is not None, n_stat, hook, count,
+                                                dgamma=grads.view(b.weight), dbeta=grads.view(b.bias))
+            if st.res is not None:
+                self._acc(G, st.res, dres)
+            kview = grads.view(conv.kernel)
+            if kview.shape[-2] == x.shape[1]:
+                ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out, out=kview)
+            else:     # the 6-channel input padded to 8: wgrad over the padded width, the real rows are copied out
+                dw = ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out)
+                kview.copy_(dw[:, :kview.shape[-2], :].reshape(kview.shape))
+            if st.need_dx:
+                # the gradient already pending for this unit's input (residual branch / skip connection) is added in
+                # the dgrad epilogue instead of by a separate elementwise pass
+                pending = G.get(st.src)
+                G[st.src] = ops.conv_forward(dx_bn, km_b, _packed(conv)[1], conv.kernel_volume, x.shape[0], x.shape[1],
+                                             residual=pending)
+            if self.on_bucket is not None and st.name == self.bucket_after:
+                self.on_bucket()
+        if carry is not None:
+            grads.flat.add_(carry)
+        for p, v in zip(grads.params, grads.views):
+            p.grad = v
+        if self.on_done is not None:
+            self.on_done()
+
+    @staticmethod
+    def _acc(G, tid, g):
+        cur = G.get(tid)
+        G[tid] = g if cur is None else cur.add_(g)

@@ -440,3 +440,46 @@ def test_reference_selection_net_forward_over_b2m(setup):
                     "vs tests/golden/selection_net_small.npz (same code over the CPU oracle):\n" + "\n".join(report) + "\n")
     finally:
         sys.path.remove(stage)
+
+
+def test_trunk_executor_matches_module_path(setup):
+    """The hand-scheduled trunk (box2mask_b200/trunk.py: one autograd node, dgrad-epilogue gradient fusion, flat gradient
+    buffer; eval mode: BatchNorm folded into the convolution epilogue) against the module-by-module path on the same
+    kernels. Training mode: identical kernels in the same order up to the fused gradient adds -> heads cosine >= 0.9999,
+    every kernel gradient cosine >= 0.995 on a well-conditioned batch. Eval mode: the folded path skips the intermediate
+    bf16 rounding of the convolution output -> heads cosine >= 0.9999 against the module path."""
+    g, _, cfg, model, sd, id2idx = setup
+    batch = _strip_batch(n_scenes=4, length_m=45.0, width_vox=4, seed=2)
+    net = model.net
+    res = {}
+    for executor in (False, True):
+        net.use_trunk_executor = executor
+        model.load_state_dict(sd)
+        model.train()
+        for p in model.parameters():
+            p.grad = None
+        losses, pred = model.compute_loss_detection(batch, epoch=0)
+        losses["optimization_loss"].backward()
+        res[executor] = ({h: pred[h].detach().float().cpu() for h in cfg.network_heads}, float(losses["optimization_loss"]),
+                         {k: p.grad.detach().float().cpu().clone() for k, p in net.named_parameters()},
+                         {k: v.detach().float().cpu().clone() for k, v in net.state_dict().items() if "running" in k})
+    try:
+        (h0, l0, g0, b0), (h1, l1, g1, b1) = res[False], res[True]
+        assert min(_cos(h0[h], h1[h]) for h in h0) >= 0.9999, {h: _cos(h0[h], h1[h]) for h in h0}
+        assert abs(l0 - l1) <= 5e-3 * abs(l0)
+        cos = {k: _cos(g0[k], g1[k]) for k in g0 if float(g0[k].norm()) > 0}
+        worst = sorted(cos.items(), key=lambda kv: kv[1])[:8]
+        print("executor vs modules, worst gradient cosines:", worst)
+        assert min(cos.values()) >= 0.995, worst
+        for k in b0:
+            assert torch.allclose(b0[k], b1[k], rtol=2e-2, atol=2e-3), k
+        # eval mode
+        model.load_state_dict(sd)
+        model.eval()
+        ev = {}
+        for executor in (False, True):
+            net.use_trunk_executor = executor
+            ev[executor] = model.get_prediction(batch, with_grad=False, to_cpu=True, min_size=False)
+        assert min(_cos(ev[False][h], ev[True][h]) for h in cfg.network_heads) >= 0.9999
+    finally:
+        net.use_trunk_executor = False
