@@ -144,6 +144,49 @@ __global__ void kmap_stride2_kernel(const int4* __restrict__ fine, int64_t n_fin
   }
 }
 
+// Kernel map of a level from the maps of the next COARSER level (no hashing): the coordinate o + d * ts (|d| <= 1 for a
+// 3^3 kernel, <= 2 for 5^3) lies in the parent cell of o shifted by dP in {-1, 0, 1}^3, so
+//   nbr[k][o] = nbr_down[child slot of the target][ nbr3_coarse[kP][ parent[o] ] ]
+// two dependent reads of small dense tables (the coarse 3^3 map and the 8-slot child table of the stride-2 map) that
+// neighbouring rows share, instead of a random probe of a hash table per (row, offset). With s = child slot of o inside
+// its parent (0/1 per axis): dP = floor((s + d) / 2), target slot = (s + d) - 2 dP. Exact: a coordinate exists iff its
+// parent cell exists and has that child. group_mask (optional, zeroed by the caller) receives the per-64-row-group
+// offset bits (for maps that are not re-ordered afterwards, i.e. the 125-offset map).
+__global__ void kmap_from_coarse_kernel(const int4* __restrict__ coords, int64_t n, int ts, int ksize,
+                                        const int32_t* __restrict__ parent, const int32_t* __restrict__ nbr3_coarse,
+                                        const int32_t* __restrict__ nbr_down, int64_t coarse_pitch,
+                                        int32_t* __restrict__ nbr, int64_t pitch, uint32_t* __restrict__ group_mask, int words) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int kvol = ksize * ksize * ksize;
+  if (gid >= pitch * kvol) return;             // pitch is a multiple of 128: whole warps leave together
+  const int64_t row = gid % pitch;
+  const int k = (int)(gid / pitch);
+  int32_t r = -1;
+  if (row < n) {
+    const int h = ksize / 2;
+    const int dx = k % ksize - h, dy = (k / ksize) % ksize - h, dz = k / (ksize * ksize) - h;
+    if (dx == 0 && dy == 0 && dz == 0) {
+      r = (int32_t)row;
+    } else {
+      const int4 c = __ldg(coords + row);
+      const int cs = 2 * ts;
+      const int px = (c.y - floor_to_multiple(c.y, cs)) / ts + dx;     // position inside the parent cell, in [-2, 3]
+      const int py = (c.z - floor_to_multiple(c.z, cs)) / ts + dy;
+      const int pz = (c.w - floor_to_multiple(c.w, cs)) / ts + dz;
+      const int qx = (px + 2) / 2 - 1, qy = (py + 2) / 2 - 1, qz = (pz + 2) / 2 - 1;   // floor(p / 2) in {-1, 0, 1}
+      const int kp = (qx + 1) + 3 * (qy + 1) + 9 * (qz + 1);
+      const int slot = (px - 2 * qx) + 2 * (py - 2 * qy) + 4 * (pz - 2 * qz);
+      const int32_t pc = __ldg(nbr3_coarse + (int64_t)kp * coarse_pitch + __ldg(parent + row));
+      if (pc >= 0) r = __ldg(nbr_down + (int64_t)slot * coarse_pitch + pc);
+    }
+  }
+  nbr[gid] = r;
+  if (group_mask != nullptr) {
+    const unsigned any = __ballot_sync(0xffffffffu, r >= 0);
+    if ((threadIdx.x & 31) == 0 && any && row < n) atomicOr(group_mask + (row >> 6) * words + (k >> 5), 1u << (k & 31));
+  }
+}
+
 __global__ void kmap_count_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int64_t pitch, int32_t* __restrict__ counts) {
   const int k = blockIdx.y;
   int local = 0;
@@ -319,6 +362,26 @@ extern "C" int b2m_kernel_map_submanifold(const int32_t* coords, int64_t n, int3
   kmap_submanifold_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const int4*>(coords), n, tensor_stride, kernel_size,
       reinterpret_cast<const unsigned long long*>(table_keys), table_vals, (uint64_t)(capacity - 1), nbr, pitch);
+  B2M_CHECK_LAUNCH();
+  return B2M_OK;
+}
+
+extern "C" int b2m_kernel_map_from_coarse(const int32_t* coords, int64_t n, int32_t tensor_stride, int32_t kernel_size,
+                                          const int32_t* parent_row, const int32_t* nbr3_coarse, const int32_t* nbr_down,
+                                          int64_t n_coarse, int32_t* nbr, uint32_t* group_mask, b2m_stream_t stream) {
+  if (kernel_size != 3 && kernel_size != 5) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (n == 0) return B2M_OK;
+  if (!coords || !parent_row || !nbr3_coarse || !nbr_down || !nbr || n < 0 || n_coarse <= 0 || tensor_stride <= 0)
+    return B2M_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kvol = kernel_size * kernel_size * kernel_size;
+  const int words = (kvol + 31) / 32;
+  const int64_t pitch = b2m_map_pitch(n);
+  if (group_mask)
+    if (cudaMemsetAsync(group_mask, 0, (size_t)((n + 63) / 64) * words * 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  kmap_from_coarse_kernel<<<cdiv(pitch * kvol, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, tensor_stride,
+                                                                  kernel_size, parent_row, nbr3_coarse, nbr_down,
+                                                                  b2m_map_pitch(n_coarse), nbr, pitch, group_mask, words);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }

@@ -19,6 +19,10 @@ class CoordinateManager:
         self.tables = {}                # stride -> ops.HashTable
         self.sub_maps = {}              # (stride, ksize) -> sorted ops.KernelMap over the level's rows
         self.stride2 = {}               # fine stride -> (KernelMap down [8, N_coarse], KernelMap up [8, N_fine])
+        # unsorted tables kept for the hash-free construction of the next finer level's maps (ops.kernel_map_from_coarse)
+        self.parents = {}               # fine stride -> parent row of every fine row, int32 [N_fine]
+        self.raw_down = {}              # fine stride -> unsorted child table int32 [8, pitch(N_coarse)]
+        self.raw_k3 = {}                # stride -> unsorted 3^3 table of that level
 
     def coords(self, stride):
         return self.levels[stride]
@@ -52,8 +56,24 @@ class CoordinateManager:
     def submanifold_map(self, stride, ksize):
         key = (stride, ksize)
         if key not in self.sub_maps:
-            nbr = ops.kernel_map_submanifold(self.levels[stride], stride, ksize, self.table(stride))
-            self.sub_maps[key] = ops.sort_kernel_map(nbr, self.levels[stride].shape[0])
+            coords = self.levels[stride]
+            n = coords.shape[0]
+            coarse = self.raw_k3.get(2 * stride)
+            if ksize in (3, 5) and coarse is not None and stride in self.parents and n > 0:
+                # two reads of the coarser level's dense tables per entry instead of a hash probe
+                n_coarse = self.levels[2 * stride].shape[0]
+                if ksize == 5:      # 125 offsets: never re-ordered, the group masks come out of the same kernel
+                    nbr, gmask = ops.kernel_map_from_coarse(coords, stride, ksize, self.parents[stride], coarse,
+                                                            self.raw_down[stride], n_coarse, want_gmask=True)
+                    self.sub_maps[key] = ops.KernelMap(nbr, None, gmask, ksize ** 3, n)
+                    return self.sub_maps[key]
+                nbr = ops.kernel_map_from_coarse(coords, stride, ksize, self.parents[stride], coarse,
+                                                 self.raw_down[stride], n_coarse)
+            else:
+                nbr = ops.kernel_map_submanifold(coords, stride, ksize, self.table(stride))
+            if ksize == 3 and stride > 1 and (stride // 2) in self.parents:
+                self.raw_k3[stride] = nbr          # a finer level exists: its maps will be derived from this table
+            self.sub_maps[key] = ops.sort_kernel_map(nbr, n)
         return self.sub_maps[key]
 
     def stride2_maps(self, fine_stride):
@@ -63,6 +83,7 @@ class CoordinateManager:
             coarse, parent = ops.downsample_coords(fine, 2 * fine_stride)
             self.levels[2 * fine_stride] = coarse
             nbr_down, nbr_up = ops.kernel_map_stride2(fine, parent, coarse.shape[0], fine_stride)
+            self.parents[fine_stride], self.raw_down[fine_stride] = parent, nbr_down
             self.stride2[fine_stride] = (ops.sort_kernel_map(nbr_down, coarse.shape[0]),
                                          ops.sort_kernel_map(nbr_up, fine.shape[0]))
         return self.stride2[fine_stride]
@@ -87,8 +108,12 @@ class CoordinateManager:
         for _ in range(int(n_strided)):
             self.stride2_maps(s)
             s *= 2
-        for stride, ksize in sub_kernels:
-            self.submanifold_map(int(stride), int(ksize))
+        # coarsest level first: each finer level's table is derived from the coarser one (only the coarsest is hashed);
+        # at equal stride the 3^3 map first (the 5^3 map does not feed anything)
+        for stride, ksize in sorted(((int(a), int(b)) for a, b in sub_kernels), key=lambda t: (-t[0], t[1])):
+            self.submanifold_map(stride, ksize)
+        self.raw_k3.clear()        # construction scratch: the consumers only need the sorted maps
+        self.raw_down.clear()
 
     def _tensors(self):
         for t in self.levels.values():
@@ -102,6 +127,8 @@ class CoordinateManager:
             for t in (m.nbr, m.order, m.gmask, m.raw):
                 if t is not None:
                     yield t
+        for t in self.parents.values():
+            yield t
 
     def wait_ready(self):
         """After a side-stream prepare(): make the current stream wait for the maps and tell the caching allocator

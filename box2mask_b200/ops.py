@@ -159,6 +159,22 @@ def kernel_map_submanifold(coords, tensor_stride, kernel_size, table):
     return nbr
 
 
+def kernel_map_from_coarse(coords, tensor_stride, kernel_size, parent_row, nbr3_coarse, nbr_down, n_coarse, want_gmask=False):
+    """The table of kernel_map_submanifold built without hashing from the next coarser level's (unsorted) 3^3 table and
+    child table (b2m_kernel_map_from_coarse). -> nbr int32[K^3, pitch(n)] (and gmask int32[groups, words] of the unsorted
+    table when want_gmask)."""
+    lib = _lib_or_raise()
+    _cuda(coords, torch.int32, "coords")
+    n = coords.shape[0]
+    kvol = kernel_size ** 3
+    nbr = torch.empty((kvol, map_pitch(n)), dtype=torch.int32, device=coords.device)
+    gmask = torch.empty(((n + 63) // 64, (kvol + 31) // 32), dtype=torch.int32, device=coords.device) if want_gmask else None
+    _run("kernel_map_from_coarse", 1, lambda: check(lib.b2m_kernel_map_from_coarse(
+        ptr(coords), n, int(tensor_stride), int(kernel_size), ptr(parent_row), ptr(nbr3_coarse), ptr(nbr_down), int(n_coarse),
+        ptr(nbr), ptr(gmask), stream_ptr()), "kernel_map_from_coarse"), nbytes=20 * n + 4 * n * kvol)
+    return (nbr, gmask) if want_gmask else nbr
+
+
 def kernel_map_stride2(fine_coords, parent_row, n_coarse, fine_stride):
     lib = _lib_or_raise()
     n_fine = fine_coords.shape[0]

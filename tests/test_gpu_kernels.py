@@ -88,6 +88,44 @@ def test_strided_levels_bit_exact(scene_coords):
         assert np.array_equal(nbr.cpu().numpy()[:, :len(cur_np)], so.kernel_map_submanifold(cur_np, ts, 3)), level
 
 
+def test_hierarchical_kernel_maps_bit_exact(scene_coords):
+    """CoordinateManager.prepare builds only the coarsest level's 3^3 map by hashing; every finer level's map (and the
+    5^3 map of the input level) is derived from the coarser level's tables (b2m_kernel_map_from_coarse). All of them
+    must equal the oracle's tables entry by entry."""
+    from box2mask_b200.me.sparse_tensor import CoordinateManager
+    for coords_np in (scene_coords, None):
+        if coords_np is None:      # negative coordinates, unsorted input rows
+            rng = np.random.default_rng(9)
+            xyz = np.unique(rng.integers(-40, 40, (6000, 3)), axis=0)
+            coords_np = _coords(xyz)[rng.permutation(len(xyz))]
+        cm = CoordinateManager(torch.from_numpy(coords_np).to(DEV))
+        cm.prepare(7, [(1, 5)] + [(2 ** l, 3) for l in range(8)])
+        assert not cm.raw_k3 and len(cm.tables) == 1 and 128 in cm.tables     # one hash table: the coarsest level
+        cur = coords_np
+        for l in range(8):
+            ts = 2 ** l
+            assert np.array_equal(cm.levels[ts].cpu().numpy(), cur), l
+            for k in ((3, 5) if l == 0 else (3,)):
+                km = cm.sub_maps[(ts, k)]
+                ref = so.kernel_map_submanifold(cur, ts, k)
+                n = len(cur)
+                got = km.nbr.cpu().numpy()[:, :n]
+                if km.order is not None:
+                    order = km.order.cpu().numpy()[:n]
+                    unsorted = np.empty_like(got)
+                    unsorted[:, order] = got
+                    got = unsorted
+                assert np.array_equal(got, ref), (l, k)
+                assert bool((km.nbr[:, n:] == -1).all())
+                if k == 5:       # group masks of the unsorted 125-offset table, produced by the same kernel
+                    g = (n + 63) // 64
+                    bits = np.unpackbits(km.gmask.cpu().numpy().view(np.uint8).reshape(g, 16), axis=1, bitorder="little")[:, :125]
+                    ref_bits = np.pad(ref >= 0, ((0, 0), (0, g * 64 - n))).reshape(125, g, 64).any(2).T
+                    assert np.array_equal(bits.astype(bool), ref_bits)
+            if l < 7:
+                cur, _ = so.downsample_coords(cur, 2 * ts)
+
+
 @pytest.mark.parametrize("block_rows", [4096, 0])
 def test_sorted_kernel_map(scene_coords, block_rows):
     """b2m_kernel_map_sort: a permutation of the rows, stable inside (block, mask) classes; the pair set is unchanged."""
