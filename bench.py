@@ -39,16 +39,17 @@ def peaks():
 
 
 def conv_traffic():
-    """DRAM bytes (read + write) per convolution launch, averaged over the conv launches of one training step, from
-    the committed ncu capture (profiles/*conv_dram*.json, written by tools/ncu_conv_traffic.py); None if absent."""
+    """(DRAM bytes (read + write) per convolution launch, source file): averaged over the conv launches of one training
+    step, from the newest committed ncu capture (profiles/*conv_dram*.json, written by tools/ncu_conv_traffic.py). It is
+    NOT measured in this run (ncu cannot run inside a timed benchmark), so the line names the file it came from."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*conv_dram*.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*conv_dram*.json")), key=os.path.getmtime)
     if not files:
-        return None
+        return None, None
     try:
-        return float(json.load(open(files[-1]))["dram_bytes_per_launch"])
+        return float(json.load(open(files[-1]))["dram_bytes_per_launch"]), "profiles/" + os.path.basename(files[-1])
     except Exception:
-        return None
+        return None, None
 
 
 def make_scenes(n, seed, scale):
@@ -109,14 +110,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model(device, multigpu, grad_sync="flat"):
+def build_model(device, multigpu, grad_sync="flat", trunk_executor=True, overlap_wgrad=True):
     from box2mask_b200.model import Model
     from box2mask_b200.selection_net import default_config
     from box2mask_b200.synthetic import label_maps
-    cfg = default_config(multigpu=multigpu, mlp_bb_scores_start_epoch=0, grad_sync=grad_sync)
+    cfg = default_config(multigpu=multigpu, mlp_bb_scores_start_epoch=0, grad_sync=grad_sync, trunk_executor=trunk_executor)
     valid, id2idx, is_fg = label_maps(20)
     torch.manual_seed(0)
     model = Model(cfg, valid, id2idx, None, is_fg, device=device)
+    if trunk_executor:
+        model.net.trunk_executor().overlap_wgrad = overlap_wgrad
     model.train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)     # models/training.py:37-38
     return model, opt, cfg
@@ -132,7 +135,8 @@ def train_step(model, opt, batch):
 
 
 def cpu_reference_step(scenes, threads):
-    """The CPU oracle (ME-CPU-algorithm restatement): fwd + losses + bwd on a bounded sample; returns seconds."""
+    """The CPU oracle (ME-CPU-algorithm restatement): fwd + losses + bwd + Adam step on a bounded sample; returns
+    seconds."""
     from box2mask_b200.selection_net import SelectionNet, default_config
     from box2mask_b200.synthetic import collate, label_maps
     from oracle.selection_net import OracleNet, detection_loss, seeded_state_dict
@@ -145,9 +149,11 @@ def cpu_reference_step(scenes, threads):
             v.requires_grad_(True)
     _, id2idx, _ = label_maps(20)
     b = collate(scenes)
+    opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-3)      # models/training.py:37-38
     t0 = time.time()
     out = OracleNet(sd, cfg, training=True).forward(b["vox_coords"].numpy(), b["vox_features"], b["pooling_ids"])
     detection_loss(out, b, cfg, 0, id2idx)["optimization_loss"].backward()
+    opt.step()
     return time.time() - t0
 
 
@@ -163,16 +169,16 @@ def run_reference(args):
         t = cpu_reference_step(scenes, threads)
         if i >= args.warmup:
             times.append(t)
-    ms = 1e3 * float(np.mean(times))
+    ms = 1e3 * float(np.median(times))
     val = len(scenes) / (ms / 1e3)
-    sample = "2 ScanNet-shape scenes (%d voxels) fwd+loss+bwd per step, oracle port of ME's CPU algorithm" % sum(
-        len(s["vox_coords"]) for s in scenes)
+    sample = "2 ScanNet-shape scenes (%d voxels) fwd+loss+bwd+Adam per step (median of %d steps after %d warm-up), oracle " \
+             "port of ME's CPU algorithm" % (sum(len(s["vox_coords"]) for s in scenes), len(times), args.warmup)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "scenes/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs/scannet.txt training step (fwd+bwd+box-vote loss), ScanNet-shape scenes, "
-                               "bounded sample of 2 scenes/step on CPU"},
+                               "bounded sample of 2 scenes/step on CPU (per-scene throughput; the GPU arm steps 8 scenes)"},
         "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -188,13 +194,17 @@ def main():
     ap.add_argument("--scale", type=float, default=SCENE_SCALE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-bn", action="store_true")
-    ap.add_argument("--grad-sync", default="flat", choices=["flat", "ddp"],
+    ap.add_argument("--grad-sync", default="overlap", choices=["overlap", "flat", "ddp"],
                     help="flat: one all-reduce of the flat gradient buffer after backward (box2mask_b200/grad_sync.py); "
                          "ddp: torch DistributedDataParallel buckets overlapped with backward")
-    ap.add_argument("--regions", type=int, default=3, help="timed regions of --steps steps each; the fastest is reported")
+    ap.add_argument("--regions", type=int, default=3, help="timed regions of --steps steps each; the median is reported")
     ap.add_argument("--prefetch", action="store_true",
                     help="build the coordinate maps one step ahead on a side stream (Model.prefetch_coordinates); measured "
                          "slower than building them inside the step: the persistent conv kernels leave the side stream no SMs")
+    ap.add_argument("--no-trunk-executor", action="store_true", help="run the trunk module by module through autograd")
+    ap.add_argument("--no-wgrad-overlap", action="store_true", help="weight gradients on the main stream")
+    ap.add_argument("--gather-mode", default="cpasync", choices=["cpasync", "tma"],
+                    help="how the convolution kernels fetch feature rows (b2m_set_option B2M_OPT_GATHER_MODE)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -215,10 +225,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from box2mask_b200 import ops
     ops._lib.load()      # fail loudly if the CUDA library is missing
+    ops._lib.set_option(ops._lib.OPT_GATHER_MODE, 1 if args.gather_mode == "tma" else 0)
 
     scenes = make_scenes(args.scenes, seed=10 + rank, scale=args.scale)
     rng = np.random.default_rng(rank)
-    model, opt, cfg = build_model(dev, multigpu=world > 1, grad_sync=args.grad_sync)
+    model, opt, cfg = build_model(dev, multigpu=world > 1, grad_sync=args.grad_sync,
+                                  trunk_executor=not args.no_trunk_executor, overlap_wgrad=not args.no_wgrad_overlap)
     if world > 1 and not args.sync_bn:
         for m in model.net.modules():      # per-rank BatchNorm statistics unless --sync-bn
             if hasattr(m, "process_group"):
@@ -278,18 +290,18 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     for i in range(max(args.warmup, len(dev_batches))):
         train_step(model, opt, dev_batches[i % len(dev_batches)])
-    # Each region times exactly `steps` steps between barrier + synchronize; the fastest of REGIONS regions is
-    # reported (a one-off host stall in one region is not a property of the path).
+    # Each region times exactly `steps` steps between barrier + synchronize; the MEDIAN of REGIONS regions is reported
+    # and every region's figure is kept in config.timing.
     REGIONS = max(1, args.regions)
     ms_all = []
     for r in range(REGIONS):
         ops.Profile.reset()
         ms_all.append(timed(dev_batches, args.steps, read_loss=False))
     launches = ops.Profile.launches
-    ms_step = min(ms_all)
+    ms_step = float(np.median(ms_all))
     clocks = sampler.stop() if sampler else None
     ms_e2e_all = [timed(host_batches, args.steps, read_loss=True) for _ in range(REGIONS)]
-    ms_e2e = min(ms_e2e_all)
+    ms_e2e = float(np.median(ms_e2e_all))
     h2d = int(np.mean([sum(b[k].numel() * b[k].element_size() for k in TENSOR_KEYS) for b in host_batches]))
 
     # instrumented pass: CUDA events around every C-ABI launch (same stream), for the roofline figures
@@ -305,6 +317,11 @@ def main():
         d = agg.setdefault(kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
         d["ms"] += a.elapsed_time(b_); d["flops"] += fl; d["bytes"] += by; d["launches"] += 1
     pk = peaks()
+    traffic, traffic_src = conv_traffic()
+    # bandwidth-bound kernel classes against the measured HBM copy bandwidth (algorithmic bytes / CUDA-event time)
+    hbm = {k: {"achieved": v["bytes"] / (v["ms"] * 1e-3) / 1e9, "peak": pk["gbs"], "unit": "GB/s",
+               "frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["gbs"], "ms_per_step": v["ms"] / prof_steps}
+           for k, v in agg.items() if v["bytes"] and v["ms"] and not v["flops"]}
     conv_ms = sum(agg[k]["ms"] for k in ("conv_forward", "conv_wgrad") if k in agg)
     conv_fl = sum(agg[k]["flops"] for k in ("conv_forward", "conv_wgrad") if k in agg)
     conv_n = sum(agg[k]["launches"] for k in ("conv_forward", "conv_wgrad") if k in agg)
@@ -322,11 +339,13 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         threads = min(16, os.cpu_count() or 1)
         sample_scenes = scenes[:2]
-        t = cpu_reference_step(sample_scenes, threads)
+        cpu_reference_step(sample_scenes, threads)                     # warm-up (allocator, thread pool), not timed
+        ts = [cpu_reference_step(sample_scenes, threads) for _ in range(3)]
+        t = float(np.median(ts))
         cpu = {"value": len(sample_scenes) / t, "unit": "scenes/s", "cores": threads, "kind": "port",
-               "sample": "2 of the bench's ScanNet-shape scenes (%d voxels), fwd+loss+bwd once, %.1f s; oracle port of "
-                         "ME's CPU algorithm (MinkowskiEngine 0.5.4 not installable offline)"
-                         % (sum(len(s["vox_coords"]) for s in sample_scenes), t)}
+               "sample": "2 of the bench's ScanNet-shape scenes (%d voxels), fwd+loss+bwd+Adam, median of 3 runs after one "
+                         "warm-up run (%s s); oracle port of ME's CPU algorithm (MinkowskiEngine 0.5.4 not installable "
+                         "offline)" % (sum(len(s["vox_coords"]) for s in sample_scenes), ", ".join("%.1f" % x for x in ts))}
     total_scenes = args.scenes * world
     line = {
         "metric": METRIC, "value": total_scenes / (ms_step * 1e-3), "unit": "scenes/s", "n_gpus": world,
@@ -337,7 +356,7 @@ def main():
                    "scenes_per_gpu": args.scenes, "voxels_per_gpu": voxels, "parallelism": "dp%d" % world,
                    "sync_bn": bool(args.sync_bn and world > 1),
                    "grad_sync": (args.grad_sync if world > 1 else None),
-                   "timing": "fastest of %d regions of %d steps each, ms/step of every region: value %s, e2e %s" % (
+                   "timing": "median of %d regions of %d steps each, ms/step of every region: value %s, e2e %s" % (
                        REGIONS, args.steps, ["%.2f" % m for m in ms_all], ["%.2f" % m for m in ms_e2e_all]),
                    "coordinate_maps": "built one step ahead on a side stream" if args.prefetch else "built inside the step",
                    "cache": "inputs larger than L2: every full-resolution activation is >= 235 MB (L2 is 126 MB) and "
@@ -347,10 +366,12 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tflops"], "traffic": conv_traffic(), "peak_source": pk["src"] + " sustained bf16",
+                     "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": pk["src"] + " sustained bf16",
                      "kernel": "conv_fwd_kernel + conv_wgrad_kernel (all %d launches/step)" % (conv_n // max(prof_steps, 1)),
                      "algorithmic_flops_per_step": conv_fl / max(prof_steps, 1),
                      "kernel_ms_per_step": conv_ms / max(prof_steps, 1)},
+        "roofline_hbm": hbm,
         "cpu_baseline": cpu,
         "kernels": breakdown,
     }

@@ -38,6 +38,8 @@ SIGNATURES = {
     "b2m_conv_forward_ex": (c_int32, [_P, c_int64, c_int32, _P, _P, _P, c_int32, c_int64, _P, c_int32, _P, _P, _P, _P, _P,
                                       c_int32, _P, c_int32, _P, c_size_t, _P]),
     "b2m_conv_wgrad": (c_int32, [_P, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int32, c_int64, _P, _P]),
+    "b2m_conv_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
+    "b2m_conv_wgrad_ex": (c_int32, [_P, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int32, c_int64, _P, _P, c_size_t, _P]),
     "b2m_colstats": (c_int32, [_P, c_int64, c_int32, _P, _P]),
     "b2m_bn_forward": (c_int32, [_P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, c_float, c_float, c_int32, _P, c_int32,
                                  _P, _P, _P, _P]),
@@ -99,7 +101,7 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
-OPT_MAX_CTAS, OPT_CHUNKS_PER_STAGE, OPT_SPLIT_OFFSETS = 1, 2, 3
+OPT_MAX_CTAS, OPT_CHUNKS_PER_STAGE, OPT_SPLIT_OFFSETS, OPT_GATHER_MODE, OPT_WGRAD_ROWS, OPT_ISSUER = 1, 2, 3, 4, 5, 6
 
 
 def set_option(option, value):

@@ -187,6 +187,14 @@ __device__ __forceinline__ void umma_stage_bf16(uint32_t d_tmem, uint32_t a_lo, 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// the same with an ignore-src predicate: `zero` != 0 writes 16 zero bytes and makes no memory request (LDGSTS.ZFILL)
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool zero) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t}"
+      ::"r"(dst), "l"(src), "r"((uint32_t)zero) : "memory");
+}
 // mbarrier arrive that fires when all prior cp.async of this thread have landed (counts as a normal arrival)
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");

@@ -190,6 +190,8 @@ struct FwdArgs {
   // the slices in a fixed order (deterministic), applies the epilogue and takes the statistics.
   float* part; int ksplit, kg_per;
   int off_ep;
+  int lean_off; // 1 = general MMA issue loop even where the lean one applies (b2m_set_option B2M_OPT_ISSUER, tests)
+  int ldgsts;   // KPACK == 1: A rows fetched by cp.async (LDGSTS) from every lane of the gather warps instead of TMA gather4
 };
 
 // bits [lo, hi) of a 128-bit mask
@@ -265,6 +267,52 @@ __device__ __forceinline__ void umma_chunk2(uint32_t d, uint32_t a_lo, uint32_t 
   umma_bf16_lohi(d, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// cp.async (LDGSTS) row gathers into UMMA tiles
+// ------------------------------------------------------------------------------------------------
+// One gather4 costs the issuing warp ~76 cycles PER LANE (the operands travel to uniform registers one lane at a
+// time), so a warp needs ~2400 cycles to request the 128 rows of a chunk and a ring slot turns around in ~5700 cycles:
+// with 3 slots per ring that, not bandwidth, set the stage rate of round 1. A cp.async is an ordinary SIMT
+// instruction: a warp requests 4 rows x 128 bytes (8 lanes per row, so every request is a full 128-byte line piece)
+// per instruction and the whole chunk in ~32 instructions + address arithmetic; completion is reported to the stage's
+// mbarrier by cp.async.mbarrier.arrive.noinc from every lane (fire and forget). The writes go through the generic
+// proxy: the MMA issuer executes fence.proxy.async after its wait on the stage barrier.
+//
+// R[u] holds the gathered row index (-1 = none: zero-filled, no memory request) of tile row 32 * u + lane.
+// 128 rows x 64 channels -> SW128 tile (row r at r * 128, 16-byte piece j at (j ^ (r & 7)) * 16);
+// `pieces` = 16-byte pieces of the chunk that exist in the tensor (8, or fewer for a zero-padded last chunk).
+template <int NROWS>
+__device__ __forceinline__ void ldgsts_rows_sw128(uint32_t dst, const uint8_t* __restrict__ src, uint32_t row_bytes,
+                                                  const int (&R)[NROWS / 32], int lane, int pieces) {
+  const int j = lane & 7, s = lane >> 3;
+  const uint32_t d_even = dst + (uint32_t)(s * 128 + ((j ^ s) << 4));
+  const uint32_t d_odd = dst + (uint32_t)((4 + s) * 128 + ((j ^ (4 + s)) << 4));
+  const uint8_t* src_lane = src + j * 16;
+  const bool colok = j < pieces;
+#pragma unroll
+  for (int i = 0; i < NROWS / 4; ++i) {
+    const int r = __shfl_sync(0xFFFFFFFFu, R[i >> 3], ((4 * i) & 31) + s);
+    const bool ok = colok && r >= 0;
+    // (a row without a neighbour reads nothing: the address only has to be well formed)
+    cp_async16_zfill(((i & 1) ? d_odd : d_even) + (uint32_t)((i >> 1) * 1024),
+                     src_lane + (uint64_t)(uint32_t)max(r, 0) * (uint64_t)row_bytes, !ok);
+  }
+}
+// NROWS rows x 32 channels -> SW64 tile (row r at r * 64, 16-byte piece j at (j ^ ((r >> 1) & 3)) * 16)
+template <int NROWS>
+__device__ __forceinline__ void ldgsts_rows_sw64(uint32_t dst, const uint8_t* __restrict__ src, uint32_t row_bytes,
+                                                 const int (&R)[NROWS / 32], int lane) {
+  const int j = lane & 3, s = lane >> 2;
+  const uint32_t d0 = dst + (uint32_t)(s * 64 + ((j ^ ((lane >> 3) & 3)) << 4));
+  const uint8_t* src_lane = src + j * 16;
+#pragma unroll
+  for (int i = 0; i < NROWS / 8; ++i) {
+    const int r = __shfl_sync(0xFFFFFFFFu, R[i >> 2], ((8 * i) & 31) + s);
+    cp_async16_zfill(d0 + (uint32_t)(i * 512), src_lane + (uint64_t)(uint32_t)max(r, 0) * (uint64_t)row_bytes, r < 0);
+  }
+}
+
 // KPACK = offsets per A stage: 1 (c_red >= 48: 64-wide chunks), 2 / 4 (c_red 32 / 16: SW64 / SW32 sub-tiles),
 // 8 (c_red 8: cp.async path). A template parameter so that the single-thread MMA issue loop has no mode branches.
 template <int KPACK>
@@ -287,7 +335,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
   if (warp == 0) B2M_TRACE(0);
 
   if (warp == 4 && lane == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, KPACK == 1 ? a.cps : 1); mbar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, KPACK == 1 ? (a.ldgsts == 1 ? 32 * a.cps : a.cps) : 1); mbar_init(a_empty + 8 * s, 1); }
     // every tile's MMA issuer releases a B slot / completes an accumulator set: T arrivals each
     for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, a.T); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full + 8 * s, a.T); mbar_init(acc_empty + 8 * s, kEpiWarps); }
@@ -486,6 +534,92 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       uint32_t st_a = a_step, st_b = b_step, st_c = b_chunk, st_last = (uint32_t)(nst - 1);
       // keep them in registers: re-deriving them from the kernel parameters costs constant-bank loads on the issue path
       asm volatile("" : "+r"(last_c0_rem), "+r"(last_c1), "+r"(st_a), "+r"(st_b), "+r"(st_c), "+r"(st_last));
+#ifndef B2M_DEBUG_BUILD
+      if (KPACK == 1 && a.mwords == 1 && !a.lean_off) {
+        // ---- lean issue loop (kernel volumes <= 32: the offsets of a tile are ONE mask word) ----
+        // ncu's instruction-level samples of the general loop below (profiles/r2_ncu_fwd_96_cpasync_issuer.txt): 37 % of
+        // the issuer's time went into loop control (mask word selection, bit scans, kernel parameters re-read from the
+        // constant bank), 17 % into the two barrier waits taken one after the other, 8 % into the proxy fence, 13 % into
+        // the MMAs. Here: the issuer never needs the offset NUMBER (what a slot holds is the producers' business), only
+        // whether its own tile takes part in each set bit of the work item's union mask; every loop-invariant lives in a
+        // register; the waits on the weight slot and the A slot are issued back to back; the masks of the next work
+        // item are loaded while this one runs; MMAs and commits of a stage are one straight-line block.
+        const uint32_t nst_r = (uint32_t)nst, T_r = (uint32_t)a.T, SAr_r = (uint32_t)SAr, SB_r = (uint32_t)SB;
+        const uint32_t two_f = two ? 1u : 0u, fence_f = (a.ldgsts == 1) ? 1u : 0u;
+        const uint32_t af0 = a_full + 8 * abase, ae0 = a_empty + 8 * abase;
+        const uint32_t slice_w = sl.w0;
+        const int n_tiles_r = a.n_tiles, n_work_r = a.n_work, stride_r = (int)gridDim.x;
+        const uint32_t* gm = a.gmask;
+        const int64_t ngroups = (a.n_out + 63) / 64;
+        const uint32_t colstride_r = (uint32_t)a.colstride;
+        // masks of tiles (tile0, tile0 + 1) of a work item; the same values every other role derives (fwd_tile_mask)
+        auto load_masks = [&](int w, uint32_t& q0, uint32_t& q1) {
+          q0 = 0u; q1 = 0u;
+          if (w >= n_work_r) return;
+          const int t0 = w * (int)T_r;
+          if (gm == nullptr) { q0 = (t0 < n_tiles_r) ? 1u : 0u; q1 = (T_r > 1 && t0 + 1 < n_tiles_r) ? 1u : 0u; return; }
+          const int64_t g0 = 2 * (int64_t)t0;
+          if (t0 < n_tiles_r) { q0 = __ldg(gm + g0); if (g0 + 1 < ngroups) q0 |= __ldg(gm + g0 + 1); }
+          if (T_r > 1 && t0 + 1 < n_tiles_r) { q1 = __ldg(gm + g0 + 2); if (g0 + 3 < ngroups) q1 |= __ldg(gm + g0 + 3); }
+          q0 &= slice_w; q1 &= slice_w;
+        };
+        uint32_t ra_slot = 0, ra_phase = 0, rb_slot = 0, rb_phase = 0;
+        uint32_t a_fa = af0, a_ea = ae0, b_fa = b_full, b_ea = b_empty;
+        uint32_t q0, q1;
+        load_masks((int)blockIdx.x, q0, q1);
+        uint32_t wi = 0;
+        for (int w = blockIdx.x; w < n_work_r; w += stride_r, ++wi) {
+          const uint32_t par = wi & 1u;
+          uint32_t n0m, n1m;
+          load_masks(w + stride_r, n0m, n1m);                      // in flight during this work item
+          mbar_wait(acc_empty + 8 * par, ((wi >> 1) & 1u) ^ 1u, 2);
+          tc_fence_after();
+          const uint32_t mine = me ? q1 : q0;
+          uint32_t mu = q0 | q1;
+          const uint32_t d = tmem_base + (par * T_r + (uint32_t)me) * colstride_r;
+          uint32_t acc = 0;
+          while (mu) {
+            const uint32_t bit = mu & (0u - mu);
+            mu ^= bit;
+            const bool has = (mine & bit) != 0u;
+            for (uint32_t c = 0; c < nst_r; ++c) {
+              if (has) {
+                const uint32_t okb = mbar_try_wait(b_fa, rb_phase), oka = mbar_try_wait(a_fa, ra_phase);
+                if (!okb) mbar_wait(b_fa, rb_phase, 4);
+                if (!oka) mbar_wait(a_fa, ra_phase, 5);
+                if (fence_f) fence_proxy_async();      // cp.async wrote the slot through the generic proxy
+                tc_fence_after();
+                if (lead) {
+                  const bool last = (c == st_last);
+                  umma_stage_bf16(d, a_cur, b_cur, st_c, idesc, acc, last ? last_c0_rem : 0u, last ? last_c1 : two_f,
+                                  hi128, hi64, a_ea, b_ea);
+                }
+                acc = 1u;
+                const bool wrap = (++ra_slot == SAr_r);
+                ra_slot = wrap ? 0u : ra_slot;
+                ra_phase ^= wrap ? 1u : 0u;
+                a_cur = wrap ? a_ring_lo : a_cur + st_a;
+                a_fa = wrap ? af0 : a_fa + 8;
+                a_ea = wrap ? ae0 : a_ea + 8;
+              } else {
+                // the other tile uses this offset, this one does not: wait for the slice, then release it (see below)
+                mbar_wait(b_fa, rb_phase, 8);
+                if (lead) mbar_arrive(b_ea);
+              }
+              const bool wrapb = (++rb_slot == SB_r);
+              rb_slot = wrapb ? 0u : rb_slot;
+              rb_phase ^= wrapb ? 1u : 0u;
+              b_cur = wrapb ? b_ring_lo : b_cur + st_b;
+              b_fa = wrapb ? b_full : b_fa + 8;
+              b_ea = wrapb ? b_empty : b_ea + 8;
+            }
+          }
+          if (lead) umma_commit(acc_full + 8 * par);
+          q0 = n0m; q1 = n1m;
+        }
+      } else
+#endif
+      {
       int wi = 0;
       int nstage = 0;      // debug trace only
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
@@ -508,6 +642,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
               if (me == 0 && nstage == 0) B2M_TRACE(19);
               if (me == 0 && nstage >= 32 && nstage < 44) B2M_TRACE(101 + (nstage - 32) * 4);
               B2M_ISSUER_WAIT(a_full + 8 * aslot, ra.phase, 5);
+              if (KPACK == 1 && a.ldgsts == 1) fence_proxy_async();   // cp.async wrote the slot through the generic proxy
               tc_fence_after();
               if (me == 0 && nstage >= 32 && nstage < 44) B2M_TRACE(102 + (nstage - 32) * 4);
               if (me == 0 && nstage < 16) B2M_TRACE(40 + nstage);
@@ -588,6 +723,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
         }
         if (lead) umma_commit(acc_full + 8 * par);
         if (me == 0 && wi == 0) B2M_TRACE(21);
+      }
       }
     }
     __syncwarp();
@@ -702,6 +838,60 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
         return idx;
       };
       St cur = next();
+      if (a.ldgsts) {
+        // cp.async mode: lane l holds the row indices of tile rows l, 32 + l, 64 + l, 96 + l (four coalesced 128-byte
+        // loads per warp), loaded one stage ahead like the index quads of the TMA mode
+        auto load_rows = [&](const St& s, int (&R)[4]) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) R[u] = -1;
+          if (s.valid) {
+            const int64_t pos0 = (int64_t)(s.w * a.T + t) * kTileM + lane;
+            if (a.nbr) {
+              const int32_t* pr = a.nbr + (int64_t)s.kg * a.n_pitch + pos0;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) R[u] = __ldg(pr + 32 * u);
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) R[u] = (pos0 + 32 * u < a.n_out) ? (int)(pos0 + 32 * u) : -1;
+            }
+          }
+        };
+        const uint8_t* xb = reinterpret_cast<const uint8_t*>(a.x);
+        const uint32_t row_bytes = (uint32_t)a.c_red * 2u;
+        int R[4];
+        load_rows(cur, R);
+        while (cur.valid) {
+          const St nxt = next();
+          int Rn[4];
+          load_rows(nxt, Rn);                                  // in flight while this stage waits for its slot
+          const int ch = cur.c * NS + part;                    // this warp's chunk of the stage (may not exist)
+          const uint32_t a_s = smem_base + cur.slot * a.a_slot_bytes + part * kASlotBytes;
+          const uint32_t full = a_full + 8 * cur.slot;
+          mbar_wait(a_empty + 8 * cur.slot, cur.phase ^ 1u, 10);
+          if (ch < nch && !B2M_ABLATE(a, 0)) {
+            if (ch < a.nfull) {
+              const int left = (a.c_red - ch * 64) >> 3;       // 16-byte pieces of the tensor in this chunk
+              ldgsts_rows_sw128<128>(a_s, xb + ch * 128, row_bytes, R, lane, left < 8 ? left : 8);
+            } else {
+              ldgsts_rows_sw64<128>(a_s, xb + ch * 128, row_bytes, R, lane);
+            }
+          }
+          if (a.ldgsts == 1) {
+            cp_async_mbar_arrive_noinc(full);                  // every lane: the barrier counts 32 arrivals per warp
+          } else {
+            // mode 2: the warp waits for its copies, makes them visible to the async proxy itself and arrives once, so
+            // that the MMA issuer (the critical path) needs no proxy fence; the ring depth still bounds what is in
+            // flight because there are as many producer groups as slots
+            cp_async_wait_all();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) R[u] = Rn[u];
+          cur = nxt;
+        }
+      }
       int4 idx = load_idx(cur);
       int ntr = 0;       // debug trace only
       while (cur.valid) {
@@ -935,17 +1125,23 @@ constexpr int kWgRows = 64;
 constexpr int kWgASlotBytes = 128 * kWgRows * 2;                // 16 KB: M = 128 x 64 reduction rows
 
 struct WgArgs {
-  const uint16_t* x; const int32_t* nbr; const int32_t* order; const uint32_t* gmask; float* dw;
+  const uint16_t* x; const uint16_t* dy; const int32_t* nbr; const int32_t* order; const uint32_t* gmask; float* dw;
   int64_t n_out, n_pitch;
   int c_in, c_out, kvol, mwords, cpad, pk, G, colstride, groups_per_cta;
   int wa, nab;    // X operand: row bytes of a block (128 / 64 / 32) and blocks per A stage (nab * wa / 2 == 128 M rows)
   int wb, nbb;    // dY operand: row bytes of a block and number of column blocks
   int a_slots, b_slots, b_bytes, off_b, off_bars, tmem_cols;
   int store;      // 1: one CTA owns each dW element (no row splits): plain stores, zeros for offsets without pairs
+  int lda, ldb;   // X / dY rows fetched by cp.async from every lane of the gather warps instead of TMA gather4
+  int ncols;      // gridDim.x: accumulator q of column `col` holds offset slot col + ncols * q (interleaved assignment)
+  float* part;    // != nullptr: row split y writes its partial dW to part[y][kvol * c_in * c_out] with plain stores
+                  // (summed in a fixed order by wgrad_reduce_kernel: deterministic, no contended atomics)
 };
 
+template <int ROWS>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy, const WgArgs a) {
+  constexpr int kSlotA = 128 * ROWS * 2;     // bytes of an A slot: M = 128 channels x ROWS reduction rows
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_base = smem_u32(smem);
@@ -960,7 +1156,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 
   const int col = blockIdx.x;             // which G offset groups
   const int mt = blockIdx.z;              // M tile (input-channel block of 128) when c_in > 128
-  const int64_t total_groups = (a.n_out + kWgRows - 1) / kWgRows;
+  const int64_t total_groups = (a.n_out + ROWS - 1) / ROWS;
   // Row groups are dealt round-robin to the gridDim.y CTAs of a column: all CTAs then sweep the arrays together, so
   // the rows one CTA gathers (and the dY stage its column neighbours re-read) are still in L2 when the others need them.
   // With a contiguous range per CTA the 24 x 6 CTAs of a full-resolution launch streamed 24 distant regions and
@@ -968,13 +1164,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const int64_t g_begin = (int64_t)blockIdx.y;
   const int64_t g_end = total_groups;
   const int64_t g_step = (int64_t)gridDim.y;
-  const int kbase = col * a.G * a.pk;     // first kernel offset of accumulator 0
-  const int nq = min(a.G, (a.kvol - kbase + a.pk - 1) / a.pk);   // accumulators of this CTA that hold real offsets
+  // Accumulator q of this CTA holds offset slot col + ncols * q (slot = pk consecutive kernel offsets). Interleaved, not
+  // contiguous: contiguous runs of offsets are whole dz planes of the kernel, whose pair counts differ systematically
+  // (the plane through the centre holds the offsets that almost every voxel has), so the CTAs of different columns
+  // swept the rows at different speeds, drifted apart and pulled several regions of X / dY through L2 at once
+  // (ncu: L2 hit rate 51 %, 1.66 GB of DRAM reads for 0.47 GB of operands).
+  const int kslots_all = (a.kvol + a.pk - 1) / a.pk;
+  const int nq = (kslots_all - col + a.ncols - 1) / a.ncols;   // accumulators of this CTA that hold real offsets (<= G)
+  auto k_first = [&](int q) -> int { return (col + a.ncols * q) * a.pk; };   // first kernel offset of accumulator q
   if (warp == 0) B2M_TRACE(0);
 
   if (warp == kWgEpi && lane == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
-    for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, a.lda ? 32 : 1); mbar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, a.ldb ? 32 : 1); mbar_init(b_empty + 8 * s, 1); }
     mbar_init(accum_bar, 1);
     mbar_fence_init();
   }
@@ -987,23 +1189,26 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const uint32_t tmem_base = *tmem_ptr_s;
   if (warp == 0) B2M_TRACE(1);
 
+  // offsets present in reduction group g (ROWS rows = ROWS / 64 groups of the sorted map's masks)
+  const int64_t ngroups64 = (a.n_out + 63) / 64;
   auto group_mask = [&](int64_t g) -> MaskBits {
     if (a.gmask == nullptr) { MaskBits m = mask_zero(); m.w0 = 1u; return m; }
-    return mask_load(a.gmask, g, a.mwords);
+    MaskBits m = mask_load(a.gmask, g * (ROWS / 64), a.mwords);
+    if (ROWS == 128 && 2 * g + 1 < ngroups64) m = mask_or(m, mask_load(a.gmask, 2 * g + 1, a.mwords));
+    return m;
   };
-  // bit q set iff accumulator q (offsets kbase + q*pk .. + pk - 1) has a pair in a row group with mask m
+  // bit q set iff accumulator q (offsets k_first(q) .. + pk - 1) has a pair in a row group with mask m
+  const uint32_t pk_bits = (a.pk >= 32) ? 0xFFFFFFFFu : ((1u << a.pk) - 1u);
   auto acc_mask = [&](const MaskBits& m) -> uint32_t {
     if (a.gmask == nullptr) return 1u;
-    if (a.pk == 1) {                       // the nq <= 16 bits starting at kbase, possibly straddling two words
-      const int wd = kbase >> 5;
-      const uint32_t lo = mask_word(m, wd), hi = (wd < 3) ? mask_word(m, wd + 1) : 0u;
-      return __funnelshift_r(lo, hi, kbase & 31) & ((1u << nq) - 1u);
-    }
     uint32_t out = 0;
-    for (int q = 0; q < nq; ++q) {         // pk in {2,4,8,16} divides 32 and kbase % pk == 0: one word per accumulator
-      const int k0 = kbase + q * a.pk;
-      const uint32_t bits = (mask_word(m, k0 >> 5) >> (k0 & 31)) & ((a.pk == 32 ? 0u : (1u << a.pk)) - 1u);
-      out |= (bits != 0 ? 1u : 0u) << q;
+    if (a.mwords == 1) {                   // kernel volumes <= 32: one mask word
+      for (int q = 0; q < nq; ++q) out |= (((m.w0 >> k_first(q)) & pk_bits) != 0u ? 1u : 0u) << q;
+      return out;
+    }
+    for (int q = 0; q < nq; ++q) {         // pk in {1,2,4,8,16} divides 32 and k_first % pk == 0: one word per accumulator
+      const int k0 = k_first(q);
+      out |= (((mask_word(m, k0 >> 5) >> (k0 & 31)) & pk_bits) != 0u ? 1u : 0u) << q;
     }
     return out;
   };
@@ -1023,9 +1228,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const uint32_t tr = smem_base + warp * (32 * kStagePitch * 4);
     const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
     const int nchunk32 = (a.c_out + 31) / 32;
+    const bool plain = a.store || a.part != nullptr;     // this CTA owns the elements it writes
+    float* dwo = a.part ? a.part + (int64_t)blockIdx.y * ((int64_t)a.kvol * a.c_in * a.c_out) : a.dw;
     for (int q = 0; q < nq; ++q) {
       const bool has = ((used >> q) & 1u) != 0;
-      if (!has && !a.store) continue;
+      if (!has && !plain) continue;
       for (int cc = 0; cc < nchunk32; ++cc) {
         const int cw = min(32, a.c_out - cc * 32);
         uint32_t v[32];
@@ -1048,13 +1255,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const int mrow = warp * 32 + r;               // M row
             const int slot = mrow / a.cpad;               // which packed offset
             const int ci = mrow % a.cpad + mt * 128;
-            const int k = kbase + q * a.pk + slot;
+            const int k = k_first(q) + slot;
             if (slot < a.pk && k < a.kvol && ci < a.c_in) {
               const uint32_t src = tr + (r * kStagePitch + c4) * 4;
               const float4 val = make_float4(ld_shared_f32(src), ld_shared_f32(src + 4), ld_shared_f32(src + 8),
                                              ld_shared_f32(src + 12));
-              float4* dst = reinterpret_cast<float4*>(a.dw + ((int64_t)k * a.c_in + ci) * a.c_out + cc * 32 + c4);
-              if (a.store) *dst = val; else atomicAdd(dst, val);
+              float4* dst = reinterpret_cast<float4*>(dwo + ((int64_t)k * a.c_in + ci) * a.c_out + cc * 32 + c4);
+              if (plain) *dst = val; else atomicAdd(dst, val);
             }
           }
         }
@@ -1069,7 +1276,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const uint32_t wa = (uint32_t)a.wa, wb = (uint32_t)a.wb;
     // MN-major: LBO = stride between blocks (64 rows x row bytes each), SBO = stride between 8-row K groups
     const uint32_t hi_a = umma_desc_hi(8 * wa, wa), hi_b = umma_desc_hi(8 * wb, wb);
-    const uint32_t lbo_a = ((kWgRows * wa) >> 4) << 16, lbo_b = ((kWgRows * wb) >> 4) << 16;
+    const uint32_t lbo_a = ((ROWS * wa) >> 4) << 16, lbo_b = ((ROWS * wb) >> 4) << 16;
     const uint32_t kstep_a = (16 * wa) >> 4, kstep_b = (16 * wb) >> 4;     // descriptor units per K=16 step
     uint32_t used = 0;
     Ring ra, rb;
@@ -1081,20 +1288,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const uint32_t qm = acc_mask(m);
       if (!qm) continue;
       mbar_wait(b_full + 8 * rb.slot, rb.phase, 21);
+      if (a.ldb) fence_proxy_async();      // cp.async wrote the slot through the generic proxy
       if (g == g_begin) B2M_TRACE(19);
       const uint32_t b_lo = (((smem_base + a.off_b + rb.slot * a.b_bytes) >> 4) & 0x3FFFu) | lbo_b;
 #pragma unroll 1
       for (uint32_t rem = qm; rem; rem &= rem - 1) {
         const int q = __ffs(rem) - 1;
         mbar_wait(a_full + 8 * ra.slot, ra.phase, 22);
+        if (a.lda) fence_proxy_async();
         tc_fence_after();
         if (g == g_begin) B2M_TRACE(20);
         if (lead) {
-          const uint32_t a_lo = (((smem_base + ra.slot * kWgASlotBytes) >> 4) & 0x3FFFu) | lbo_a;
+          const uint32_t a_lo = (((smem_base + ra.slot * kSlotA) >> 4) & 0x3FFFu) | lbo_a;
           const uint32_t d = tmem_base + (uint32_t)(q * a.colstride);
           uint32_t acc = (used >> q) & 1u;
 #pragma unroll
-          for (int ks = 0; ks < kWgRows / 16; ++ks) {
+          for (int ks = 0; ks < ROWS / 16; ++ks) {
             umma_bf16_lohi(d, a_lo + ks * kstep_a, hi_a, b_lo + ks * kstep_b, hi_b, idesc, acc);
             acc = 1u;
           }
@@ -1131,7 +1340,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (!mine) { rb.next(); continue; }
       const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
       const uint32_t full = b_full + 8 * rb.slot;
-      const int64_t pos0 = g * kWgRows + 4 * (lane & 15);
+      if (a.ldb) {
+        // cp.async mode: lane l holds the rows at positions l and 32 + l of the group
+        int R[ROWS / 32];
+        const int64_t p0 = g * ROWS + lane;
+#pragma unroll
+        for (int u = 0; u < ROWS / 32; ++u) {
+          if (a.order) R[u] = (p0 + 32 * u < a.n_pitch) ? __ldg(a.order + p0 + 32 * u) : -1;
+          else R[u] = p0 + 32 * u < a.n_out ? (int)(p0 + 32 * u) : -1;
+        }
+        mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u, 23);
+        const uint8_t* dyb = reinterpret_cast<const uint8_t*>(a.dy);
+        const uint32_t row_bytes = (uint32_t)a.c_out * 2u;
+        for (int blk = 0; blk < a.nbb; ++blk) {
+          if (a.wb == 128) {
+            const int left = (a.c_out - blk * 64) >> 3;
+            ldgsts_rows_sw128<ROWS>(b_s + blk * (ROWS * 128), dyb + blk * 128, row_bytes, R, lane, left < 8 ? left : 8);
+          } else {
+            ldgsts_rows_sw64<ROWS>(b_s + blk * (ROWS * 64), dyb + blk * 64, row_bytes, R, lane);
+          }
+        }
+        cp_async_mbar_arrive_noinc(full);
+        rb.next();
+        continue;
+      }
+      const int64_t pos0 = g * ROWS + 4 * (lane & 15);
       int4 idx;
       if (a.order) {
         idx = ld_nc_int4(a.order + pos0);
@@ -1143,11 +1376,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u, 23);
       if (g == g_begin) B2M_TRACE(10);
-      if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(a.nbb * kWgRows * a.wb));
+      if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(a.nbb * ROWS * a.wb));
       __syncwarp();
       for (int it = lane; it < items; it += 32) {
         const int blk = it >> 4;
-        tma_gather4(b_s + blk * (kWgRows * a.wb) + (it & 15) * 4 * a.wb, &tm_dy, full, blk * 64, idx.x, idx.y, idx.z, idx.w);
+        tma_gather4(b_s + blk * (ROWS * a.wb) + (it & 15) * 4 * a.wb, &tm_dy, full, blk * 64, idx.x, idx.y, idx.z, idx.w);
       }
       __syncwarp();
       if (g == g_begin) B2M_TRACE(11);
@@ -1180,10 +1413,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const bool mine = true;
         if (mine && a.cpad == 8) {
           // cp.async path (8-channel input): lane = (offset slot j of 16, row half rh); one 16-byte piece per (row, offset)
-          const uint32_t a_s = smem_base + ra.slot * kWgASlotBytes;
+          const uint32_t a_s = smem_base + ra.slot * kSlotA;
           const int j = lane & 15, rh = lane >> 4;
-          const int k = kbase + q * a.pk + j;
-          const int32_t* nb = (a.nbr && k < a.kvol) ? a.nbr + (int64_t)k * a.n_pitch + g * kWgRows : nullptr;
+          const int k = k_first(q) + j;
+          const int32_t* nb = (a.nbr && k < a.kvol) ? a.nbr + (int64_t)k * a.n_pitch + g * ROWS : nullptr;
           mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u, 24);
 #pragma unroll 2
           for (int it = 0; it < 8; ++it) {
@@ -1192,7 +1425,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             if (nb) {
               idx = ld_nc_int4(nb + r0);
             } else if (!a.nbr && k < a.kvol) {
-              const int64_t q0 = g * kWgRows + r0;
+              const int64_t q0 = g * ROWS + r0;
               idx.x = q0 < a.n_out ? (int)q0 : -1;
               idx.y = q0 + 1 < a.n_out ? (int)q0 + 1 : -1;
               idx.z = q0 + 2 < a.n_out ? (int)q0 + 2 : -1;
@@ -1202,7 +1435,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int row = r0 + u;
-              const uint32_t dst = a_s + (j >> 3) * (kWgRows * 128) + row * 128 + (((j & 7) ^ (row & 7)) << 4);
+              const uint32_t dst = a_s + (j >> 3) * (ROWS * 128) + row * 128 + (((j & 7) ^ (row & 7)) << 4);
               if (iv[u] >= 0) cp_async16(dst, a.x + (int64_t)iv[u] * 8, 16u);
               else st_shared_zero16(dst);
             }
@@ -1211,12 +1444,55 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full + 8 * ra.slot);
-        } else if (mine) {
-          const uint32_t a_s = smem_base + ra.slot * kWgASlotBytes;
+        } else if (mine && a.lda) {
+          // cp.async mode (wa 128 or 64): block = 64 gathered rows x wa bytes; pk > 1: block b holds offset k0 + b,
+          // else the blocks are the 64-channel column blocks of one offset
+          const uint32_t a_s = smem_base + ra.slot * kSlotA;
           const uint32_t full = a_full + 8 * ra.slot;
-          const int k0 = kbase + q * a.pk;
+          const int k0 = k_first(q);
+          const int nslots = min(a.pk, a.kvol - k0);
+          const int64_t p0 = g * ROWS + lane;
+          const uint8_t* xb = reinterpret_cast<const uint8_t*>(a.x);
+          const uint32_t row_bytes = (uint32_t)a.c_in * 2u;
+          int R[4][ROWS / 32];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+#pragma unroll
+            for (int u = 0; u < ROWS / 32; ++u) {
+              R[b][u] = -1;
+              if (b < (a.pk > 1 ? nslots : 1) && p0 + 32 * u < a.n_pitch) {
+                if (a.nbr) R[b][u] = __ldg(a.nbr + (int64_t)(k0 + b) * a.n_pitch + p0 + 32 * u);
+                else R[b][u] = p0 + 32 * u < a.n_out ? (int)(p0 + 32 * u) : -1;
+              }
+            }
+          }
+          if (a.pk == 1) {                 // the column blocks of one offset share its rows
+#pragma unroll
+            for (int b = 1; b < 4; ++b)
+#pragma unroll
+              for (int u = 0; u < ROWS / 32; ++u) R[b][u] = R[0][u];
+          }
+          mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u, 24);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            if (b < a.nab && !(a.pk > 1 && b >= nslots)) {
+              if (a.wa == 128) {
+                const int col0 = (a.pk > 1) ? 0 : mt * 128 + b * 64;         // first channel of the block
+                const int left = (a.c_in - col0) >> 3;
+                ldgsts_rows_sw128<ROWS>(a_s + b * (ROWS * 128), xb + col0 * 2, row_bytes, R[b], lane,
+                                           left < 8 ? (left > 0 ? left : 0) : 8);
+              } else {
+                ldgsts_rows_sw64<ROWS>(a_s + b * (ROWS * 64), xb, row_bytes, R[b], lane);
+              }
+            }
+          }
+          cp_async_mbar_arrive_noinc(full);
+        } else if (mine) {
+          const uint32_t a_s = smem_base + ra.slot * kSlotA;
+          const uint32_t full = a_full + 8 * ra.slot;
+          const int k0 = k_first(q);
           const int nslots = min(a.pk, a.kvol - k0);            // packed offsets that exist
-          const int64_t pos0 = g * kWgRows + 4 * (lane & 15);
+          const int64_t pos0 = g * ROWS + 4 * (lane & 15);
           // index quads: lane handles items it = lane, lane + 32, ...; for pk == 1 every block uses offset k0
           int4 idx[4];
 #pragma unroll
@@ -1239,7 +1515,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u, 24);
           if (g == g_begin && p == 0) B2M_TRACE(12);
           const int nblk = (a.pk > 1) ? nslots : a.nab;
-          if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(nblk * kWgRows * a.wa));
+          if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(nblk * ROWS * a.wa));
           __syncwarp();
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -1247,7 +1523,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const int blk = it >> 4;
             if (it < items && !(a.pk > 1 && blk >= nslots)) {
               const int colx = (a.pk > 1) ? 0 : mt * 128 + blk * 64;
-              tma_gather4(a_s + blk * (kWgRows * a.wa) + (it & 15) * 4 * a.wa, &tm_x, full, colx, idx[u].x, idx[u].y, idx[u].z, idx[u].w);
+              tma_gather4(a_s + blk * (ROWS * a.wa) + (it & 15) * 4 * a.wa, &tm_x, full, colx, idx[u].x, idx[u].y, idx[u].z, idx[u].w);
             }
           }
           __syncwarp();
@@ -1267,6 +1543,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
+}
+
+// dw[i] = sum over row splits s (ascending: deterministic) of part[s][i]; one float4 per thread
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float4* __restrict__ part, int nsplits, int64_t n4, float4* __restrict__ dw) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 acc = __ldg(part + i);
+  for (int s2 = 1; s2 < nsplits; ++s2) {
+    const float4 v = __ldg(part + (int64_t)s2 * n4 + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  dw[i] = acc;
 }
 
 static int pow2_cols(int need) {
@@ -1331,7 +1620,11 @@ static DeviceCache* device_cache() {
 //   instead of forcing a second wave of conv CTAs.
 //   B2M_OPT_CHUNKS_PER_STAGE: force 1 or 2 64-wide chunks per pipeline stage of the forward kernel (0 = automatic).
 //   B2M_OPT_SPLIT_OFFSETS: 0 = automatic offset splitting on levels with few row tiles, 1 = never split (tests).
-static int g_opt_max_ctas = 0, g_opt_cps = 0, g_opt_nosplit = 0;
+//   B2M_OPT_GATHER_MODE: 0 = cp.async row gathers for reductions of >= 48 channels (the MMA issuer fences the proxies),
+//   1 = TMA gather4 (round 1), 2 = cp.async with the proxy fence on the producer side (forward kernel only).
+//   B2M_OPT_ISSUER: 1 = general MMA issue loop of the forward kernel everywhere (0 = lean loop where it applies).
+//   B2M_OPT_WGRAD_ROWS: 64 = wgrad pipeline stages of 64 reduction rows always (0 = 128 rows on large levels).
+static int g_opt_max_ctas = 0, g_opt_cps = 0, g_opt_nosplit = 0, g_opt_gather = 0, g_opt_wgrows = 0, g_opt_issuer = 0;
 static int num_sms() {
   const int sms = device_cache()->sms;
   const int cap = g_opt_max_ctas;
@@ -1342,6 +1635,9 @@ extern "C" int b2m_set_option(int32_t option, int64_t value) {
     case B2M_OPT_MAX_CTAS: g_opt_max_ctas = value > 0 ? (int)value : 0; return B2M_OK;
     case B2M_OPT_CHUNKS_PER_STAGE: g_opt_cps = (value == 1 || value == 2) ? (int)value : 0; return B2M_OK;
     case B2M_OPT_SPLIT_OFFSETS: g_opt_nosplit = value ? 1 : 0; return B2M_OK;
+    case B2M_OPT_GATHER_MODE: g_opt_gather = (value == 1 || value == 2) ? (int)value : 0; return B2M_OK;
+    case B2M_OPT_ISSUER: g_opt_issuer = value ? 1 : 0; return B2M_OK;
+    case B2M_OPT_WGRAD_ROWS: g_opt_wgrows = (value == 64) ? 64 : 0; return B2M_OK;
     default: return B2M_ERR_INVALID_ARGUMENT;
   }
 }
@@ -1542,6 +1838,10 @@ extern "C" int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_re
   a.off_bars = (a.off_ep + ep_bytes + 15) / 16 * 16;
   a.tmem_cols = pow2_cols(2 * a.T * a.colstride);
   if (a.tmem_cols > 512) return B2M_ERR_UNSUPPORTED_SHAPE;
+  a.ldgsts = (a.kpack == 1 && g_opt_gather != 1) ? (g_opt_gather == 2 ? 2 : 1) : 0;
+  // (measured on k27 256->256 over 1.22 M rows: 2.66 ms lean vs 2.45 ms general - with 256-wide tiles the tensor pipe, not
+  // the issue loop, paces the kernel, and the straight-line stage block gives the MMAs less slack; lean for tiles <= 128)
+  a.lean_off = (g_opt_issuer || a.ntile > 128) ? 1 : 0;
   a.ablate = 0;
 #ifdef B2M_DEBUG_BUILD
   if (const char* e = getenv("B2M_ABLATE")) a.ablate = atoi(e);
@@ -1590,21 +1890,26 @@ extern "C" int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_re
   return B2M_OK;
 }
 
-extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t* dy, int32_t c_out,
-                              const int32_t* nbr, const int32_t* order, const uint32_t* group_mask, int32_t kvol,
-                              int64_t n_out, float* dw, b2m_stream_t stream) {
-  if (!x || !dy || !dw || kvol <= 0 || n_out < 0 || n_in < 0) return B2M_ERR_INVALID_ARGUMENT;
-  if (!nbr && kvol != 1) return B2M_ERR_INVALID_ARGUMENT;
-  if (nbr && !group_mask) return B2M_ERR_INVALID_ARGUMENT;
+// plan_only: fill *ws_need with the partial-sum workspace the launch would use (0 = none) and return
+static int wgrad_run(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t* dy, int32_t c_out,
+                     const int32_t* nbr, const int32_t* order, const uint32_t* group_mask, int32_t kvol,
+                     int64_t n_out, float* dw, void* workspace, size_t workspace_bytes, bool plan_only, size_t* ws_need,
+                     b2m_stream_t stream) {
+  if (ws_need) *ws_need = 0;
+  if (plan_only) {
+    if (kvol <= 0 || n_out <= 0 || c_in <= 0 || c_out <= 0) return B2M_OK;
+  } else if (!x || !dy || !dw || kvol <= 0 || n_out < 0 || n_in < 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (!plan_only && !nbr && kvol != 1) return B2M_ERR_INVALID_ARGUMENT;
+  if (!plan_only && nbr && !group_mask) return B2M_ERR_INVALID_ARGUMENT;
   if (c_in <= 0 || c_in % 8 != 0 || c_out <= 0 || c_out % 16 != 0 || c_out > 256 || kvol > 128) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n_out == 0) {
     if (cudaMemsetAsync(dw, 0, (size_t)kvol * c_in * c_out * 4, (cudaStream_t)stream) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
     return B2M_OK;
   }
   if (n_out >= ((int64_t)1 << 31) - 256 || n_in >= ((int64_t)1 << 31) - 256) return B2M_ERR_UNSUPPORTED_SHAPE;
-  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) != 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (!plan_only && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) != 0) return B2M_ERR_INVALID_ARGUMENT;
   WgArgs a;
-  a.x = x; a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr; a.dw = dw;
+  a.x = x; a.dy = dy; a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr; a.dw = dw;
   a.n_out = n_out; a.n_pitch = b2m_map_pitch(n_out); a.c_in = c_in; a.c_out = c_out; a.kvol = kvol; a.mwords = (kvol + 31) / 32;
   a.cpad = c_in <= 8 ? 8 : (c_in <= 16 ? 16 : (c_in <= 32 ? 32 : (c_in <= 64 ? 64 : 128)));
   a.pk = 128 / a.cpad;
@@ -1612,6 +1917,8 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
   a.nab = 128 * 2 / a.wa;
   a.wb = (c_out == 16 || c_out == 32) ? c_out * 2 : 128;
   a.nbb = (c_out * 2 + a.wb - 1) / a.wb;
+  a.lda = (g_opt_gather != 1 && (a.cpad >= 64 || c_in == 32)) ? 1 : 0;      // SW128 blocks, or SW64 for exactly 32 channels
+  a.ldb = (g_opt_gather != 1 && a.wb >= 64) ? 1 : 0;
   const int mtiles = (c_in + 127) / 128;
   a.colstride = (c_out + 31) / 32 * 32;
   int G = 512 / a.colstride;
@@ -1621,7 +1928,11 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
   a.G = G;
   const int columns = (kslots + G - 1) / G;
   a.tmem_cols = pow2_cols(G * a.colstride);
-  const int64_t total_groups = (n_out + kWgRows - 1) / kWgRows;
+  // Reduction rows per pipeline stage. The MMA issuer pays ~1000 cycles of dependent barrier / fence / commit latency per
+  // stage whatever it holds, and a 64-row stage is only 4 MMAs (~270 cycles of tensor time): with cp.async gathers on
+  // both operands and enough rows, a stage is 128 rows (8 MMAs) of the union of the two 64-row groups' offsets.
+  const int rows = (a.lda && a.ldb && n_out >= 64 * 1024 && g_opt_wgrows != 64) ? 128 : 64;
+  const int64_t total_groups = (n_out + rows - 1) / rows;
   const int sms = num_sms();
   // Row splits. Plenty of row groups: one CTA per SM, as many row splits as fit (the kernel is throughput bound). Few row
   // groups (the deep levels, where dW is as large as the activations): every extra row split adds a full set of fp32
@@ -1631,27 +1942,41 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
   int64_t max_splits = sms / ((int64_t)columns * mtiles);
   if (max_splits < 1) max_splits = 1;
   if (max_splits > total_groups) max_splits = total_groups;
+  // With a workspace the row splits write partial sums with plain stores and wgrad_reduce_kernel adds them in a fixed
+  // order (deterministic; measured on the full-resolution layers: the 24 row splits' fp32 atomics on the same 1 MB of
+  // dW, issued by all CTAs in the same order at the same time, were 27 % of the launch): a split then costs a store and
+  // a read of dW at ~3 MB/us each instead of contended atomics.
+  const bool can_part = plan_only || workspace != nullptr;
+  const double dw_mb = (double)kvol * c_in * c_out * 4.0 / 1e6;
   int64_t splits = max_splits;
   if (total_groups * columns * mtiles < 8 * (int64_t)sms) {
-    const double dw_mb = (double)kvol * c_in * c_out * 4.0 / 1e6;
     double best = 1e30;
     for (int64_t sp = 1; sp <= max_splits; ++sp) {
       const int64_t gpc = (total_groups + sp - 1) / sp;
       const double chain = 3.0 + 0.6 * (double)gpc * G;
-      const double atom = (sp == 1) ? dw_mb / 3.0 : (double)sp * dw_mb;
+      const double atom = (sp == 1) ? dw_mb / 3.0 : (can_part ? 3.0 + (double)sp * dw_mb * 2.0 / 3.0 : (double)sp * dw_mb);
       if (chain + atom < best - 1e-9) { best = chain + atom; splits = sp; }
     }
   }
   a.groups_per_cta = (int)((total_groups + splits - 1) / splits);
   splits = (total_groups + a.groups_per_cta - 1) / a.groups_per_cta;
   a.store = (splits == 1) ? 1 : 0;
-  a.b_bytes = a.nbb * kWgRows * a.wb;
+  const size_t dw_bytes = (size_t)kvol * c_in * c_out * 4;
+  const size_t need = (splits > 1) ? (size_t)splits * dw_bytes : 0;
+  if (ws_need) *ws_need = need;
+  if (plan_only) return B2M_OK;
+  a.part = (splits > 1 && workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0)
+               ? reinterpret_cast<float*>(workspace) : nullptr;
+  a.ncols = columns;
+  const int a_slot_bytes = 128 * rows * 2;
+  a.b_bytes = a.nbb * rows * a.wb;
   if (a.b_bytes < 1024) a.b_bytes = 1024;
   a.b_bytes = (a.b_bytes + 1023) / 1024 * 1024;
-  a.b_slots = a.b_bytes >= 32768 ? 3 : 4;
-  a.a_slots = (227 * 1024 - 1024 - 256 - a.b_slots * a.b_bytes) / kWgASlotBytes;
+  a.b_slots = a.b_bytes >= 65536 ? 2 : (a.b_bytes >= 32768 ? 3 : 4);
+  a.a_slots = (227 * 1024 - 1024 - 256 - a.b_slots * a.b_bytes) / a_slot_bytes;
   if (a.a_slots > 10) a.a_slots = 10;
-  a.off_b = a.a_slots * kWgASlotBytes;
+  if (a.a_slots < 2) return B2M_ERR_UNSUPPORTED_SHAPE;
+  a.off_b = a.a_slots * a_slot_bytes;
   a.off_bars = a.off_b + a.b_slots * a.b_bytes;
   const int smem_bytes = a.off_bars + 16 * a.a_slots + 16 * a.b_slots + 64 + 1024;
   if (smem_bytes > 227 * 1024) return B2M_ERR_UNSUPPORTED_SHAPE;
@@ -1660,14 +1985,44 @@ extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, con
   if (!make_row_map(&tm_dy, dy, n_out, c_out, a.wb / 2)) return B2M_ERR_CUDA_LAUNCH;
   DeviceCache* dc = device_cache();
   if (!dc->wg_attr) {
-    if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return B2M_ERR_CUDA_LAUNCH;
     dc->wg_attr = true;
   }
-  if (!a.store && cudaMemsetAsync(dw, 0, (size_t)kvol * c_in * c_out * 4, (cudaStream_t)stream) != cudaSuccess)
+  if (!a.store && !a.part && cudaMemsetAsync(dw, 0, dw_bytes, (cudaStream_t)stream) != cudaSuccess)
     return B2M_ERR_CUDA_LAUNCH;
   dim3 grid((unsigned)columns, (unsigned)splits, (unsigned)mtiles);
-  conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>(tm_x, tm_dy, a);
+  if (rows == 128) conv_wgrad_kernel<128><<<grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>(tm_x, tm_dy, a);
+  else conv_wgrad_kernel<64><<<grid, kWgThreads, smem_bytes, (cudaStream_t)stream>>>(tm_x, tm_dy, a);
   B2M_CHECK_LAUNCH();
+  if (a.part) {
+    const int64_t n4 = (int64_t)(dw_bytes / 16);
+    wgrad_reduce_kernel<<<cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(a.part), (int)splits, n4,
+                                                                      reinterpret_cast<float4*>(dw));
+    B2M_CHECK_LAUNCH();
+  }
   return B2M_OK;
+}
+
+extern "C" int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t* dy, int32_t c_out,
+                              const int32_t* nbr, const int32_t* order, const uint32_t* group_mask, int32_t kvol,
+                              int64_t n_out, float* dw, b2m_stream_t stream) {
+  return wgrad_run(x, n_in, c_in, dy, c_out, nbr, order, group_mask, kvol, n_out, dw, nullptr, 0, false, nullptr, stream);
+}
+
+extern "C" size_t b2m_conv_wgrad_workspace_bytes(int64_t n_out, int32_t c_in, int32_t c_out, int32_t kvol) {
+  size_t need = 0;
+  if (wgrad_run(nullptr, 0, c_in, nullptr, c_out, nullptr, nullptr, nullptr, kvol, n_out, nullptr, nullptr, 0, true, &need,
+                nullptr) != B2M_OK)
+    return 0;
+  return need;
+}
+
+extern "C" int b2m_conv_wgrad_ex(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t* dy, int32_t c_out,
+                                 const int32_t* nbr, const int32_t* order, const uint32_t* group_mask, int32_t kvol,
+                                 int64_t n_out, float* dw, void* workspace, size_t workspace_bytes, b2m_stream_t stream) {
+  if ((reinterpret_cast<uintptr_t>(dw) & 15) != 0) workspace = nullptr;      // the reduce kernel writes float4s
+  return wgrad_run(x, n_in, c_in, dy, c_out, nbr, order, group_mask, kvol, n_out, dw, workspace, workspace_bytes, false, nullptr,
+                   stream);
 }

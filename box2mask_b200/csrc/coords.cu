@@ -207,6 +207,17 @@ __global__ void kmap_rowmask_kernel(const int32_t* __restrict__ nbr, int kvol, i
   keys[o] = ((unsigned long long)(o / block_rows) << 32) | m;
   idx[o] = (int32_t)o;
 }
+// the same with the block number packed right above the kvol mask bits in a 32-bit key (block bits + kvol <= 32):
+// half the key bytes and one radix pass fewer than the 64-bit form
+__global__ void kmap_rowmask32_kernel(const int32_t* __restrict__ nbr, int kvol, int64_t n_out, int64_t pitch, int block_rows,
+                                      unsigned int* __restrict__ keys, int32_t* __restrict__ idx) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  unsigned int m = 0;
+  for (int k = 0; k < kvol; ++k) m |= (unsigned int)(__ldg(nbr + (int64_t)k * pitch + o) >= 0) << k;
+  keys[o] = (kvol < 32 ? ((unsigned int)(o / block_rows) << kvol) : 0u) | m;
+  idx[o] = (int32_t)o;
+}
 
 __global__ void kmap_permute_kernel(const int32_t* __restrict__ nbr, int kvol, int64_t n_out, int64_t pitch,
                                     int32_t* __restrict__ order, int32_t* __restrict__ nbr_sorted) {
@@ -434,14 +445,26 @@ extern "C" int b2m_kernel_map_sort(const int32_t* nbr, int32_t kvol, int64_t n_o
     auto* keys_in = reinterpret_cast<unsigned long long*>(ws + w.off_keys_in);
     auto* keys_out = reinterpret_cast<unsigned long long*>(ws + w.off_keys_out);
     auto* idx_in = reinterpret_cast<int32_t*>(ws + w.off_idx_in);
-    kmap_rowmask_kernel<<<blocks, 256, 0, st>>>(nbr, kvol, n_out, pitch, block_rows, keys_in, idx_in);
-    B2M_CHECK_LAUNCH();
     int64_t nblk = (n_out + block_rows - 1) / block_rows;
-    int end_bit = 32;
-    while (((int64_t)1 << (end_bit - 32)) < nblk) ++end_bit;
+    int blk_bits = 0;
+    while (((int64_t)1 << blk_bits) < nblk) ++blk_bits;
     size_t cub_bytes = w.cub_bytes;
-    if (cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, keys_in, keys_out, idx_in, order, (int)n_out, 0, end_bit, st) != cudaSuccess)
-      return B2M_ERR_CUDA_LAUNCH;
+    if (blk_bits + kvol <= 32) {
+      // (block, mask) fits 32 bits: radix-sort only the significant bits of a 32-bit key
+      auto* k32_in = reinterpret_cast<unsigned int*>(keys_in);
+      auto* k32_out = reinterpret_cast<unsigned int*>(keys_out);
+      kmap_rowmask32_kernel<<<blocks, 256, 0, st>>>(nbr, kvol, n_out, pitch, block_rows, k32_in, idx_in);
+      B2M_CHECK_LAUNCH();
+      if (cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, k32_in, k32_out, idx_in, order, (int)n_out, 0,
+                                          blk_bits + kvol, st) != cudaSuccess)
+        return B2M_ERR_CUDA_LAUNCH;
+    } else {
+      kmap_rowmask_kernel<<<blocks, 256, 0, st>>>(nbr, kvol, n_out, pitch, block_rows, keys_in, idx_in);
+      B2M_CHECK_LAUNCH();
+      if (cub::DeviceRadixSort::SortPairs(ws + w.off_cub, cub_bytes, keys_in, keys_out, idx_in, order, (int)n_out, 0,
+                                          32 + blk_bits, st) != cudaSuccess)
+        return B2M_ERR_CUDA_LAUNCH;
+    }
     kmap_permute_kernel<<<cdiv(pitch * kvol, 256), 256, 0, st>>>(nbr, kvol, n_out, pitch, order, nbr_sorted);
     B2M_CHECK_LAUNCH();
   } else {

@@ -217,7 +217,11 @@ def sort_kernel_map(nbr, n_out=None, block_rows=None, keep_raw=False):
     if pitch != map_pitch(n_out):
         raise _lib.B2MError("neighbour table must have the padded pitch %d, got %d" % (map_pitch(n_out), pitch))
     if block_rows is None:
+        # blocks of >= 32768 rows (their features stay L2-resident while a block is swept); doubled while that lets the
+        # (block, mask) sort key fit 32 bits (one radix pass fewer, half the key bytes)
         block_rows = SORT_BLOCK_ROWS
+        while kvol <= 31 and block_rows < 262144 and (n_out + block_rows - 1) // block_rows > (1 << (32 - kvol)):
+            block_rows *= 2
     words = (kvol + 31) // 32
     order = torch.empty(pitch, dtype=torch.int32, device=nbr.device)
     do_sort = block_rows > 0 and kvol <= 32
@@ -368,9 +372,13 @@ def conv_wgrad(x, dy, kmap, kvol, n_out, out=None):
         dw = out
     else:
         dw = torch.empty((kvol, c_in, c_out), dtype=torch.float32, device=x.device)    # overwritten (zero-filled inside if needed)
-    _run("conv_wgrad", 1, lambda: check(lib.b2m_conv_wgrad(
-        ptr(x), x.shape[0], c_in, ptr(dy), c_out, ptr(nbr), ptr(order), ptr(gmask), kvol, n_out, ptr(dw), stream_ptr()),
-        "conv_wgrad"),
+    # partial-sum workspace for the row splits (deterministic reduction instead of atomics); allocated on the current
+    # stream by the caching allocator
+    ws_bytes = int(lib.b2m_conv_wgrad_workspace_bytes(n_out, c_in, c_out, kvol))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+    _run("conv_wgrad", 2 if ws is not None else 1, lambda: check(lib.b2m_conv_wgrad_ex(
+        ptr(x), x.shape[0], c_in, ptr(dy), c_out, ptr(nbr), ptr(order), ptr(gmask), kvol, n_out, ptr(dw), ptr(ws), ws_bytes,
+        stream_ptr()), "conv_wgrad"),
         flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * c_in * c_out,
         nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * (c_in + c_out),
         tag="k%d %d->%d n_in=%d n_out=%d" % (kvol, c_in, c_out, x.shape[0], n_out))

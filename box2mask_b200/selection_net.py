@@ -65,6 +65,9 @@ def default_config(**overrides):
         loss_weight_semantics=1.0, loss_weight_center_scores=None, loss_weight_bb_iou=None,
         loss_weight_per_vox_semantics=1.0, mlp_bb_scores_start_epoch=100, mlp_center_scores_start_epoch=0,
         eval_ths=[0.5, 0.05, 0.3, 0.6], multigpu=False, batch_size=8, voxel_size=0.02,
+        # not a reference field: run the U-Net trunk on the hand-scheduled executor (box2mask_b200/trunk.py) instead of
+        # module by module; numerics are the same (tests/test_gpu_net.py compares the two)
+        trunk_executor=True,
     )
     for k, v in overrides.items():
         setattr(cfg, k, v)

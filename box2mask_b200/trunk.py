@@ -208,6 +208,12 @@ class TrunkExecutor:
         self.on_bucket = None
         self.bucket_after = None
         self.on_done = None
+        # Weight gradients run on a side stream: they are off the critical path of backward (nothing in the pass reads
+        # them), while the dgrad chain through tensor-stride levels >= 2 is a sequence of small launches that leaves
+        # most SMs idle. The wgrads of the full-resolution decoder stages (levels <= DEFER_LEVEL, ~6 ms of full-GPU
+        # work at the start of backward) are held back until the chain enters the deep levels and then fill those SMs.
+        self.overlap_wgrad = True
+        self._wgrad_stream = None
 
     # ---------------------------------------------------------------------------------------------
     def _input(self, feats, unit):
@@ -301,9 +307,38 @@ class TrunkExecutor:
             T[st.dst] = out
         return T[prog.out_id], saved
 
+    DEFER_LEVEL = 1
+
+    def _side_stream(self, device):
+        if not self.overlap_wgrad or device.type != "cuda" or ops.Profile.enabled:
+            return None        # (the instrumented pass of bench.py times every launch alone on one stream)
+        if self._wgrad_stream is None or self._wgrad_stream.device != device:
+            self._wgrad_stream = torch.cuda.Stream(device=device)
+        return self._wgrad_stream
+
+    def _wgrad(self, side, ready, x, dx_bn, km_f, conv, n_out, kview):
+        """dW of one unit into its slice of the flat gradient buffer, on `side` (after event `ready`) when given."""
+        def run():
+            if kview.shape[-2] == x.shape[1]:
+                ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out, out=kview)
+            else:     # the 6-channel input padded to 8: wgrad over the padded width, the real rows are copied out
+                dw = ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out)
+                kview.copy_(dw[:, :kview.shape[-2], :].reshape(kview.shape))
+        if side is None:
+            run()
+            return
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            run()
+        x.record_stream(side)
+        dx_bn.record_stream(side)
+
     # ---------------------------------------------------------------------------------------------
     def backward(self, saved, cm, dout):
         prog, maps, grads = self.program, _Maps(cm), self.grads
+        side = self._side_stream(dout.device)
+        main = torch.cuda.current_stream(dout.device) if side is not None else None
+        deferred, deep_seen = [], False
         # gradients are WRITTEN into the flat buffer; anything already accumulated on the parameters (a caller that does
         # not zero the gradients between backward passes) is carried over and added back at the end
         carry = None
@@ -339,19 +374,36 @@ class TrunkExecutor:
             if st.res is not None:
                 self._acc(G, st.res, dres)
             kview = grads.view(conv.kernel)
-            if kview.shape[-2] == x.shape[1]:
-                ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out, out=kview)
-            else:     # the 6-channel input padded to 8: wgrad over the padded width, the real rows are copied out
-                dw = ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out)
-                kview.copy_(dw[:, :kview.shape[-2], :].reshape(kview.shape))
+            ready = None
+            if side is not None:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                if st.level > self.DEFER_LEVEL and not deep_seen:
+                    deep_seen = True            # the chain enters the deep levels: release the held-back wgrads
+                    for job in deferred:
+                        self._wgrad(side, *job)
+                    deferred = []
+            if side is not None and not deep_seen:
+                deferred.append((ready, x, dx_bn, km_f, conv, n_out, kview))
+            elif side is None or not st.need_dx:
+                self._wgrad(side, ready, x, dx_bn, km_f, conv, n_out, kview)
             if st.need_dx:
                 # the gradient already pending for this unit's input (residual branch / skip connection) is added in
                 # the dgrad epilogue instead of by a separate elementwise pass
                 pending = G.get(st.src)
                 G[st.src] = ops.conv_forward(dx_bn, km_b, _packed(conv)[1], conv.kernel_volume, x.shape[0], x.shape[1],
                                              residual=pending)
+                if side is not None and deep_seen:
+                    # enqueued after the dgrad: the critical path gets the SMs first, the wgrad fills in behind it
+                    self._wgrad(side, ready, x, dx_bn, km_f, conv, n_out, kview)
             if self.on_bucket is not None and st.name == self.bucket_after:
+                if side is not None:
+                    main.wait_stream(side)      # the bucket's gradients include wgrads still running on the side stream
                 self.on_bucket()
+        for job in deferred:
+            self._wgrad(side, *job)
+        if side is not None:
+            main.wait_stream(side)
         if carry is not None:
             grads.flat.add_(carry)
         for p, v in zip(grads.params, grads.views):

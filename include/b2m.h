@@ -48,10 +48,17 @@ const char* b2m_error_string(int code);
  *  B2M_OPT_MAX_CTAS          cap on the CTAs of the persistent convolution kernels (0 = one per SM); lowered by
  *                            the data-parallel host while a gradient all-reduce overlaps the backward pass
  *  B2M_OPT_CHUNKS_PER_STAGE  force 1 or 2 reduction chunks per pipeline stage of the forward kernel (0 = auto)
- *  B2M_OPT_SPLIT_OFFSETS     1 = never split the kernel offsets of a convolution over CTAs (0 = automatic) */
+ *  B2M_OPT_SPLIT_OFFSETS     1 = never split the kernel offsets of a convolution over CTAs (0 = automatic)
+ *  B2M_OPT_GATHER_MODE       0 = feature rows gathered with cp.async (default), 1 = with TMA gather4, 2 = cp.async
+ *                            with the generic->async proxy fence on the producer side (forward kernel)
+ *  B2M_OPT_ISSUER            1 = general MMA issue loop of the forward kernel (0 = lean loop where it applies)
+ *  B2M_OPT_WGRAD_ROWS        64 = 64 reduction rows per wgrad pipeline stage always (0 = 128 on large levels) */
 #define B2M_OPT_MAX_CTAS 1
 #define B2M_OPT_CHUNKS_PER_STAGE 2
 #define B2M_OPT_SPLIT_OFFSETS 3
+#define B2M_OPT_GATHER_MODE 4
+#define B2M_OPT_WGRAD_ROWS 5
+#define B2M_OPT_ISSUER 6
 int b2m_set_option(int32_t option, int64_t value);
 
 /* ------------------------------------------------------------------------------------------------
@@ -187,6 +194,13 @@ int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_red, const in
 int b2m_conv_wgrad(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t* dy, int32_t c_out,
                    const int32_t* nbr, const int32_t* order, const uint32_t* group_mask, int32_t kvol,
                    int64_t n_out, float* dw, b2m_stream_t stream);
+/* The same with a caller-provided workspace (b2m_conv_wgrad_workspace_bytes; 0 = none needed): the row splits then write
+ * partial sums with plain stores and a second kernel adds them in a fixed order - deterministic, and no contended
+ * atomics. Without (or with too small) a workspace it behaves like b2m_conv_wgrad. */
+size_t b2m_conv_wgrad_workspace_bytes(int64_t n_out, int32_t c_in, int32_t c_out, int32_t kvol);
+int b2m_conv_wgrad_ex(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16_t* dy, int32_t c_out,
+                      const int32_t* nbr, const int32_t* order, const uint32_t* group_mask, int32_t kvol,
+                      int64_t n_out, float* dw, void* workspace, size_t workspace_bytes, b2m_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm (+ residual, + ReLU) over rows          reference: MinkowskiBatchNorm -> BatchNorm1d

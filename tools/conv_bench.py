@@ -25,6 +25,9 @@ ap.add_argument("--ksize", type=int, default=3)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--block-rows", type=int, default=None)
 ap.add_argument("--which", default="fwd,wgrad")
+ap.add_argument("--gather", default="both", help="comma list of cpasync | tma | cpasync2 (b2m_set_option B2M_OPT_GATHER_MODE); both = cpasync,tma")
+ap.add_argument("--issuer", default="lean", help="comma list of lean | general (B2M_OPT_ISSUER)")
+ap.add_argument("--wgrows", default="0", help="comma list of 0 | 64 (B2M_OPT_WGRAD_ROWS)")
 args = ap.parse_args()
 
 dev = "cuda"
@@ -64,11 +67,21 @@ def bench(fn, name):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
-    print("%-6s k%d %d->%d rows %d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (name, kvol, args.cin, args.cout, n, ms, flops / ms / 1e9))
+    print("%-24s k%d %d->%d rows %d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (name, kvol, args.cin, args.cout, n, ms, flops / ms / 1e9))
 
 
-if "fwd" in args.which:
-    colsum = torch.zeros(2 * args.cout, dtype=torch.float64, device=dev)
-    bench(lambda: ops.conv_forward(x, km, packed, kvol, n, args.cout, colsum), "fwd")
-if "wgrad" in args.which:
-    bench(lambda: ops.conv_wgrad(x, dy, km, kvol, n), "wgrad")
+from box2mask_b200 import _lib as L  # noqa: E402
+GM = {"cpasync": 0, "tma": 1, "cpasync2": 2}
+for mode in (["cpasync", "tma"] if args.gather == "both" else args.gather.split(",")):
+    L.set_option(L.OPT_GATHER_MODE, GM[mode])
+    if "fwd" in args.which:
+        for iss in args.issuer.split(","):
+            L.set_option(L.OPT_ISSUER, 1 if iss == "general" else 0)
+            colsum = torch.zeros(2 * args.cout, dtype=torch.float64, device=dev)
+            bench(lambda: ops.conv_forward(x, km, packed, kvol, n, args.cout, colsum), "fwd[%s,%s]" % (mode, iss))
+        L.set_option(L.OPT_ISSUER, 0)
+    if "wgrad" in args.which:
+        for r in args.wgrows.split(","):
+            L.set_option(L.OPT_WGRAD_ROWS, int(r))
+            bench(lambda: ops.conv_wgrad(x, dy, km, kvol, n), "wgrad[%s,rows%s]" % (mode, r))
+        L.set_option(L.OPT_WGRAD_ROWS, 0)
