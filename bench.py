@@ -184,6 +184,172 @@ def run_reference(args):
     }))
 
 
+EVAL_METRIC = "scenes/sec Res16UNet34C eval: forward + box-vote decode + 3D IoU-NMS + superpoint pooling (2cm ScanNet-shape)"
+
+
+def run_eval(args):
+    """--workload eval (BASELINE configs 1 and 3): models/evaluation.py:70-98 - forward in eval mode (BatchNorm folded into
+    the convolution epilogues), superpoint pooling, heads, then detection2mask per scene (vote boxes -> 3-D IoU-NMS
+    clustering with heat-maps -> voxel masks -> mask-NMS -> label vote). Scenes are sharded over the ranks with no
+    communication. One step = one batch of --scenes scenes per GPU."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    from box2mask_b200 import ops
+    ops._lib.load()
+    args.warmup = max(args.warmup, 3)
+    scenes = make_scenes(args.scenes, seed=10 + rank, scale=args.scale)
+    rng = np.random.default_rng(rank)
+    model, _, cfg = build_model(dev, multigpu=False)
+    model.eval()
+    host_batches = [jitter_batch(scenes, rng) for _ in range(min(args.warmup + args.steps, 4))]
+    for b in host_batches:
+        for k in TENSOR_KEYS:
+            b[k] = b[k].pin_memory()
+        # Random-initialised heads do not vote coherently (every superpoint would become its own cluster), so the decode
+        # stage is fed votes of the shape a trained network produces: 24 synthetic instances per scene, every superpoint
+        # votes for the box of the nearest instance centre (+ 2 cm noise), score logits in (-1, 3), the instance's class.
+        # The network's own head outputs are still computed inside the timed region.
+        g = torch.Generator().manual_seed(0)
+        loc, bid = b["input_location"], b["batch_ids"]
+        off, bnd = torch.zeros_like(loc), torch.zeros_like(loc)
+        sem = torch.zeros(loc.shape[0], dtype=torch.long)
+        for sc in range(int(bid.max()) + 1):
+            m = bid == sc
+            lo, hi = loc[m].min(0)[0], loc[m].max(0)[0]
+            ctr = lo + (hi - lo) * torch.rand((24, 3), generator=g)
+            half = 0.2 + 0.6 * torch.rand((24, 3), generator=g)
+            cls = torch.randint(0, 20, (24,), generator=g)
+            near = torch.cdist(loc[m], ctr).argmin(1)
+            off[m] = ctr[near] - loc[m]
+            bnd[m] = half[near]
+            sem[m] = cls[near]
+        b["_votes"] = {
+            cfg.mlp_offsets: off + 0.02 * torch.randn(off.shape, generator=g),
+            cfg.mlp_bounds: (bnd + 0.02 * torch.randn(bnd.shape, generator=g)).clamp(min=0.04),
+            cfg.mlp_bb_scores: 4.0 * torch.rand((loc.shape[0], 1), generator=g) - 1.0,
+            cfg.mlp_semantics: torch.nn.functional.one_hot(sem, 20).float() * 8.0,
+        }
+    dev_batches = []
+    for b in host_batches:
+        d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items() if k != "_votes"}
+        d["_votes"] = {k: v.to(dev) for k, v in b["_votes"].items()}
+        dev_batches.append(d)
+    voxels = float(np.mean([b["vox_coords"].shape[0] for b in host_batches]))
+    stage_ms = {"forward": 0.0, "decode": 0.0, "n": 0}
+
+    def step(b, e2e):
+        if e2e:
+            votes = {k: v.to(dev, non_blocking=True) for k, v in b["_votes"].items()}
+            b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in b.items() if k != "_votes"}
+        else:
+            votes = b["_votes"]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        pred = model.get_prediction(b, with_grad=False, to_cpu=False)
+        e[1].record()
+        res = model.pred2mask(b, dict(pred, **votes), "train")          # masks per scene (device work + the result copy)
+        e[2].record()
+        return res, e
+
+    def timed(batches, steps, e2e):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = []
+        e0.record()
+        n_inst = 0
+        for i in range(steps):
+            res, e = step(batches[i % len(batches)], e2e)
+            evs.append(e)
+            n_inst += sum(len(r["conf"]) for r in res.values())
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for e in evs:
+            stage_ms["forward"] += e[0].elapsed_time(e[1]); stage_ms["decode"] += e[1].elapsed_time(e[2]); stage_ms["n"] += 1
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, n_inst / steps
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for i in range(max(args.warmup, len(dev_batches))):
+        step(dev_batches[i % len(dev_batches)], False)
+    REGIONS = max(1, args.regions)
+    ops.Profile.reset()
+    runs = [timed(dev_batches, args.steps, False) for _ in range(REGIONS)]
+    launches = ops.Profile.launches
+    ms_all = [r[0] for r in runs]
+    ms_step = float(np.median(ms_all))
+    fwd_ms, dec_ms = stage_ms["forward"] / stage_ms["n"], stage_ms["decode"] / stage_ms["n"]
+    clocks = sampler.stop() if sampler else None
+    ms_e2e_all = [timed(host_batches, args.steps, True)[0] for _ in range(REGIONS)]
+    ms_e2e = float(np.median(ms_e2e_all))
+    h2d = int(np.mean([sum(b[k].numel() * b[k].element_size() for k in TENSOR_KEYS) +
+                       sum(v.numel() * v.element_size() for v in b["_votes"].values()) for b in host_batches]))
+    # roofline of the forward convolutions: instrumented pass, CUDA events around every launch
+    ops.Profile.reset()
+    ops.Profile.enabled = True
+    for i in range(2):
+        step(dev_batches[i % len(dev_batches)], False)
+    torch.cuda.synchronize()
+    ops.Profile.enabled = False
+    agg = {}
+    for kind, fl, by, a, b_, _tag in ops.Profile.records:
+        d = agg.setdefault(kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        d["ms"] += a.elapsed_time(b_); d["flops"] += fl; d["bytes"] += by; d["launches"] += 1
+    pk = peaks()
+    conv = agg.get("conv_forward", {"ms": 0.0, "flops": 0.0, "launches": 0})
+    achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] else 0.0
+    traffic, traffic_src = conv_traffic()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total = args.scenes * world
+    d2h = int(runs[0][1] * voxels / args.scenes) if runs else 0      # bool voxel masks of the instances (+ scores, labels)
+    print(json.dumps({
+        "metric": EVAL_METRIC, "value": total / (ms_step * 1e-3), "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs/scannet.txt evaluation (BASELINE configs 1/3): %d ScanNet-shape scenes/GPU (%.0f "
+                               "voxels/GPU at 2 cm): hash + 16 kernel maps + eval forward (BatchNorm folded) + pooling + heads "
+                               "+ detection2mask per scene; no communication" % (args.scenes, voxels),
+                   "scenes_per_gpu": args.scenes, "voxels_per_gpu": voxels, "parallelism": "dp%d (scene-sharded)" % world,
+                   "stage_ms": {"forward": fwd_ms, "decode": dec_ms},
+                   "instances_per_step": runs[0][1],
+                   "votes": "decode fed coherent synthetic votes (24 instances/scene, nearest-centre assignment, 2 cm noise; "
+                            "random-init heads do not vote coherently); the network's own head outputs are computed inside "
+                            "the timed region",
+                   "timing": "median of %d regions of %d steps each, ms/step: value %s, e2e %s" % (
+                       REGIONS, args.steps, ["%.2f" % m for m in ms_all], ["%.2f" % m for m in ms_e2e_all]),
+                   "cache": "inputs larger than L2 (full-resolution activations >= 235 MB), freshly translated coordinates "
+                            "every step"},
+        "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": "conv_fwd_kernel (%d launches/step)" % (conv["launches"] // 2),
+                     "kernel_ms_per_step": conv["ms"] / 2, "algorithmic_flops_per_step": conv["flops"] / 2},
+        "cpu_baseline": None,
+        "kernels": {k: {"ms_per_step": v["ms"] / 2, "launches_per_step": v["launches"] / 2} for k, v in
+                    sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,6 +367,8 @@ def main():
     ap.add_argument("--prefetch", action="store_true",
                     help="build the coordinate maps one step ahead on a side stream (Model.prefetch_coordinates); measured "
                          "slower than building them inside the step: the persistent conv kernels leave the side stream no SMs")
+    ap.add_argument("--workload", default="train", choices=["train", "eval"],
+                    help="train: configs/scannet.txt training step (the headline metric); eval: forward + decode")
     ap.add_argument("--no-trunk-executor", action="store_true", help="run the trunk module by module through autograd")
     ap.add_argument("--no-wgrad-overlap", action="store_true", help="weight gradients on the main stream")
     ap.add_argument("--gather-mode", default="cpasync", choices=["cpasync", "tma"],
@@ -208,6 +376,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "eval":
+        return run_eval(args)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist

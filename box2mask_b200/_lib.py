@@ -23,7 +23,8 @@ SIGNATURES = {
     "b2m_downsample_workspace_bytes": (c_size_t, [c_int64]),
     "b2m_downsample_coords": (c_int32, [_P, c_int64, c_int32, _P, _P, _P, _P, c_size_t, _P]),
     "b2m_kernel_map_submanifold": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, c_int64, _P, _P]),
-    "b2m_kernel_map_from_coarse": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P, _P]),
+    "b2m_kernel_map_from_coarse_workspace_bytes": (c_size_t, [c_int64]),
+    "b2m_kernel_map_from_coarse": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P, _P, c_size_t, _P]),
     "b2m_kernel_map_stride2": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, _P, _P]),
     "b2m_kernel_map_count": (c_int32, [_P, c_int32, c_int64, _P, _P]),
     "b2m_cast_pad_bf16": (c_int32, [_P, c_int64, c_int32, c_int32, _P, _P]),

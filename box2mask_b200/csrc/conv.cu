@@ -161,7 +161,14 @@ constexpr int kEpiWarps = 4;
 // scales linearly with the number of warps, so the TMA engine is fed by many warps.
 constexpr int kFwdProd = 12;
 constexpr int kFwdMma = 2;                                     // one MMA issuer warp per tile of a work item
-constexpr int kFwdThreads = (kEpiWarps + kFwdMma + 1 + kFwdProd) * 32;  // 608
+// Warp w runs on scheduler sub-partition w % 4, and tcgen05.mma / tcgen05.commit queue up in that sub-partition's
+// memory-instruction (MIO) queue behind the cp.async of any gather warp living there (ncu: a third of the issuers' time
+// was `mio` stall on UTCHMMA / UTCBAR). So sub-partition 0 holds no gather warp: warps 0-3 epilogue (TMEM lane quarter =
+// warp % 4), warps 4 and 8 the MMA issuers, warp 12 the weight loader, warp 16 idle, every other warp >= 5 a gather warp.
+constexpr int kFwdWarps = 20;
+constexpr int kFwdThreads = kFwdWarps * 32;                     // 640
+constexpr int kFwdIssuer0 = 4, kFwdIssuer1 = 8, kFwdLoader = 12, kFwdIdle = 16;
+__device__ __forceinline__ int fwd_gather_index(int warp) { return ((warp >> 2) - 1) * 3 + (warp & 3) - 1; }   // 0 .. 11
 constexpr int kTileM = 128;
 constexpr int kStagePitch = 33;
 constexpr int kASlotBytes = kTileM * 128;
@@ -500,12 +507,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       }
     }
     if (warp == 0) B2M_TRACE(33);
-  } else if (warp < kEpiWarps + kFwdMma) {
+  } else if (warp == kFwdIssuer0 || warp == kFwdIssuer1) {
     // ================= MMA issuers: warp 4 owns tile 0 of every work item, warp 5 tile 1 (T == 2) =================
     // The single-thread issue loop is the critical path of this kernel (~90 instructions per stage), so the two
     // tiles of a work item, which accumulate into different TMEM columns, get an issuer each. The whole warp runs
     // the loop (warp-uniform values live in uniform registers); one elected lane issues MMAs and commits.
-    const int me = warp - kEpiWarps;
+    const int me = (warp == kFwdIssuer1) ? 1 : 0;
     if (me < a.T) {
       const bool lead = elect_one_sync();
       const uint32_t idesc = umma_idesc_bf16(kTileM, a.ntile, 0, 0);
@@ -727,7 +734,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       }
     }
     __syncwarp();
-  } else if (warp == kEpiWarps + kFwdMma) {
+  } else if (warp == kFwdLoader) {
     // ================= B loader: bulk copies of pre-swizzled weight slices (warp-uniform, elected lane issues) ====
     const bool lead = elect_one_sync();
     Ring rb;
@@ -761,7 +768,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp != kFwdIdle) {
     // ================= gather warps: A stage s is produced by warp s % kFwdProd =================
     // Stage s is produced by warp s % np with np <= SA: a warp then never runs more than one use of a slot ahead
     // of the consumer, which is what waiting on an mbarrier phase PARITY requires.
@@ -771,8 +778,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     // KPACK == 1: the a.cps chunks of a stage are gathered by a.cps warps (a producer group), one chunk each, so that
     // the ~1.2 us a warp needs to issue its 32 gather4s does not grow with the stage.
     const int NS = (KPACK == 1) ? a.cps : 1;
-    const int pw = (warp - (kEpiWarps + kFwdMma + 1)) / NS;     // producer group
-    const int part = (warp - (kEpiWarps + kFwdMma + 1)) % NS;   // the chunk of the stage this warp gathers
+    const int gi = fwd_gather_index(warp);
+    const int pw = gi / NS;                                     // producer group
+    const int part = gi % NS;                                   // the chunk of the stage this warp gathers
     const int groups = (kFwdProd / NS) / a.T;                   // producer groups per ring
     const int t = (a.T > 1 && pw >= groups) ? 1 : 0;            // the tile (ring) this warp feeds
     const int p = pw - t * groups;
@@ -1133,6 +1141,7 @@ struct WgArgs {
   int a_slots, b_slots, b_bytes, off_b, off_bars, tmem_cols;
   int store;      // 1: one CTA owns each dW element (no row splits): plain stores, zeros for offsets without pairs
   int lda, ldb;   // X / dY rows fetched by cp.async from every lane of the gather warps instead of TMA gather4
+  int nwa, nwb;   // warps per producer group of the X / dY operand (2 in cp.async mode when the stage has >= 2 blocks)
   int ncols;      // gridDim.x: accumulator q of column `col` holds offset slot col + ncols * q (interleaved assignment)
   float* part;    // != nullptr: row split y writes its partial dW to part[y][kvol * c_in * c_out] with plain stores
                   // (summed in a fixed order by wgrad_reduce_kernel: deterministic, no contended atomics)
@@ -1164,19 +1173,60 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const int64_t g_begin = (int64_t)blockIdx.y;
   const int64_t g_end = total_groups;
   const int64_t g_step = (int64_t)gridDim.y;
-  // Accumulator q of this CTA holds offset slot col + ncols * q (slot = pk consecutive kernel offsets). Interleaved, not
-  // contiguous: contiguous runs of offsets are whole dz planes of the kernel, whose pair counts differ systematically
-  // (the plane through the centre holds the offsets that almost every voxel has), so the CTAs of different columns
-  // swept the rows at different speeds, drifted apart and pulled several regions of X / dY through L2 at once
-  // (ncu: L2 hit rate 51 %, 1.66 GB of DRAM reads for 0.47 GB of operands).
+  // Which offset slots (slot = pk consecutive kernel offsets) this CTA's accumulators hold. The work of a slot is the
+  // number of row groups in which it occurs, and that differs a lot between offsets (the centre offset occurs in every
+  // group, a corner offset in 16-40 % of them; the sorted order even breaks the k <-> 26 - k symmetry): with contiguous
+  // runs of 5 offsets per column the busiest column of a ScanNet-shape 3^3 map had 1.51x the mean work (interleaved
+  // assignment: 1.32x), i.e. a third of the launch was CTAs waiting for the slowest column, and the columns drifted
+  // apart while sweeping the rows (ncu: L2 hit rate 51 %, 1.66 GB of DRAM reads for 0.47 GB of operands). So every CTA
+  // counts the groups per slot from the map's group masks (a 76 KB read for 1.2 M rows) and runs the same deterministic
+  // longest-processing-time assignment of slots to columns (<= G per column): 1.06x on that map.
   const int kslots_all = (a.kvol + a.pk - 1) / a.pk;
-  const int nq = (kslots_all - col + a.ncols - 1) / a.ncols;   // accumulators of this CTA that hold real offsets (<= G)
-  auto k_first = [&](int q) -> int { return (col + a.ncols * q) * a.pk; };   // first kernel offset of accumulator q
+  __shared__ int s_cnt[128];
+  __shared__ int s_koff[16];
+  __shared__ int s_nq;
+  for (int i = tid; i < 128; i += kWgThreads) s_cnt[i] = 0;
+  __syncthreads();
+  if (a.gmask != nullptr && a.ncols > 1) {
+    const int64_t ng = (a.n_out + 63) / 64;
+    const uint32_t pkb = (a.pk >= 32) ? 0xFFFFFFFFu : ((1u << a.pk) - 1u);
+    for (int64_t g = tid; g < ng; g += kWgThreads) {
+      const MaskBits m = mask_load(a.gmask, g, a.mwords);
+      for (int sl = 0; sl < kslots_all; ++sl) {
+        const int k0 = sl * a.pk;
+        if ((mask_word(m, k0 >> 5) >> (k0 & 31)) & pkb) atomicAdd(&s_cnt[sl], 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int load[128], fill[128];                // ncols <= kslots_all <= 128
+    for (int c2 = 0; c2 < a.ncols; ++c2) { load[c2] = 0; fill[c2] = 0; }
+    int nq_mine = 0;
+    unsigned long long done_lo = 0ull, done_hi = 0ull;
+    for (int it = 0; it < kslots_all; ++it) {
+      int best = -1, bc = -1;
+      for (int sl = 0; sl < kslots_all; ++sl) {            // heaviest slot not placed yet (ties: lowest index)
+        const bool dn = sl < 64 ? ((done_lo >> sl) & 1ull) : ((done_hi >> (sl - 64)) & 1ull);
+        if (!dn && s_cnt[sl] > bc) { bc = s_cnt[sl]; best = sl; }
+      }
+      if (best < 64) done_lo |= 1ull << best; else done_hi |= 1ull << (best - 64);
+      int tgt = -1;
+      for (int c2 = 0; c2 < a.ncols; ++c2)                 // least loaded column with a free accumulator (ties: lowest)
+        if (fill[c2] < a.G && (tgt < 0 || load[c2] < load[tgt])) tgt = c2;
+      load[tgt] += bc; fill[tgt] += 1;
+      if (tgt == col) s_koff[nq_mine++] = best;
+    }
+    s_nq = nq_mine;
+  }
+  __syncthreads();
+  const int nq = s_nq;                       // accumulators of this CTA that hold real offsets (<= G)
+  auto k_first = [&](int q) -> int { return s_koff[q] * a.pk; };   // first kernel offset of accumulator q
   if (warp == 0) B2M_TRACE(0);
 
   if (warp == kWgEpi && lane == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, a.lda ? 32 : 1); mbar_init(a_empty + 8 * s, 1); }
-    for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, a.ldb ? 32 : 1); mbar_init(b_empty + 8 * s, 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, a.lda ? 32 * a.nwa : 1); mbar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, a.ldb ? 32 * a.nwb : 1); mbar_init(b_empty + 8 * s, 1); }
     mbar_init(accum_bar, 1);
     mbar_fence_init();
   }
@@ -1324,8 +1374,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     __syncwarp();
   } else if (warp <= kWgEpi + kWgBProd) {
     // ================= dY producers (B operand, MN-major): gather rows order[g*64 ..]; stage s by warp s % kWgBProd ====
-    const int pb = warp - (kWgEpi + 1);
-    const int npb = min(kWgBProd, SB);   // <= SB, see conv_fwd_kernel
+    // cp.async mode with several column blocks: a stage is gathered by a GROUP of a.nwb warps, warp `partb` of the
+    // group taking the blocks b % nwb == partb, so that the ~8 instructions per 512 bytes a warp spends do not
+    // serialise a whole 32 KB stage on one warp (the stage barrier counts 32 arrivals per warp of the group)
+    const int pb = (warp - (kWgEpi + 1)) / a.nwb, partb = (warp - (kWgEpi + 1)) % a.nwb;
+    const int npb = min(kWgBProd / a.nwb, SB);   // <= SB, see conv_fwd_kernel
     Ring rb;
     rb.init(SB);
     int turn = 0;
@@ -1352,7 +1405,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u, 23);
         const uint8_t* dyb = reinterpret_cast<const uint8_t*>(a.dy);
         const uint32_t row_bytes = (uint32_t)a.c_out * 2u;
-        for (int blk = 0; blk < a.nbb; ++blk) {
+        for (int blk = partb; blk < a.nbb; blk += a.nwb) {
           if (a.wb == 128) {
             const int left = (a.c_out - blk * 64) >> 3;
             ldgsts_rows_sw128<ROWS>(b_s + blk * (ROWS * 128), dyb + blk * 128, row_bytes, R, lane, left < 8 ? left : 8);
@@ -1388,8 +1441,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     }
   } else {
     // ================= gather warps (A operand = X rows, MN-major): A stage s is produced by warp s % kWgAProd ====
-    const int p = warp - (kWgEpi + 1 + kWgBProd);
-    const int np = min(kWgAProd, SA);   // <= SA, see conv_fwd_kernel
+    const int p = (warp - (kWgEpi + 1 + kWgBProd)) / a.nwa, part = (warp - (kWgEpi + 1 + kWgBProd)) % a.nwa;   // group, warp in it
+    const int np = min(kWgAProd / a.nwa, SA);   // <= SA, see conv_fwd_kernel
     Ring ra;
     ra.init(SA);
     int turn = 0;
@@ -1475,7 +1528,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u, 24);
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
-            if (b < a.nab && !(a.pk > 1 && b >= nslots)) {
+            if (b < a.nab && !(a.pk > 1 && b >= nslots) && (b % a.nwa) == part) {
               if (a.wa == 128) {
                 const int col0 = (a.pk > 1) ? 0 : mt * 128 + b * 64;         // first channel of the block
                 const int left = (a.c_in - col0) >> 3;
@@ -1919,6 +1972,8 @@ static int wgrad_run(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16
   a.nbb = (c_out * 2 + a.wb - 1) / a.wb;
   a.lda = (g_opt_gather != 1 && (a.cpad >= 64 || c_in == 32)) ? 1 : 0;      // SW128 blocks, or SW64 for exactly 32 channels
   a.ldb = (g_opt_gather != 1 && a.wb >= 64) ? 1 : 0;
+  a.nwa = (a.lda && a.nab >= 2) ? 2 : 1;
+  a.nwb = (a.ldb && a.nbb >= 2) ? 2 : 1;
   const int mtiles = (c_in + 127) / 128;
   a.colstride = (c_out + 31) / 32 * 32;
   int G = 512 / a.colstride;
@@ -1973,20 +2028,21 @@ static int wgrad_run(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16
   if (a.b_bytes < 1024) a.b_bytes = 1024;
   a.b_bytes = (a.b_bytes + 1023) / 1024 * 1024;
   a.b_slots = a.b_bytes >= 65536 ? 2 : (a.b_bytes >= 32768 ? 3 : 4);
-  a.a_slots = (227 * 1024 - 1024 - 256 - a.b_slots * a.b_bytes) / a_slot_bytes;
+  a.a_slots = (227 * 1024 - 2048 - 256 - a.b_slots * a.b_bytes) / a_slot_bytes;   // (1 KB of static shared memory)
   if (a.a_slots > 10) a.a_slots = 10;
   if (a.a_slots < 2) return B2M_ERR_UNSUPPORTED_SHAPE;
   a.off_b = a.a_slots * a_slot_bytes;
   a.off_bars = a.off_b + a.b_slots * a.b_bytes;
   const int smem_bytes = a.off_bars + 16 * a.a_slots + 16 * a.b_slots + 64 + 1024;
-  if (smem_bytes > 227 * 1024) return B2M_ERR_UNSUPPORTED_SHAPE;
+  if (smem_bytes > 226 * 1024) return B2M_ERR_UNSUPPORTED_SHAPE;
   CUtensorMap tm_x, tm_dy;
   if (!make_row_map(&tm_x, x, n_in, c_in, a.cpad == 8 ? 8 : a.wa / 2)) return B2M_ERR_CUDA_LAUNCH;   // unused when cpad == 8
   if (!make_row_map(&tm_dy, dy, n_out, c_out, a.wb / 2)) return B2M_ERR_CUDA_LAUNCH;
   DeviceCache* dc = device_cache();
   if (!dc->wg_attr) {
-    if (cudaFuncSetAttribute(conv_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    // (the kernel also has ~0.6 KB of static shared memory: the two together must stay within the 227 KB per block)
+    if (cudaFuncSetAttribute(conv_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
       return B2M_ERR_CUDA_LAUNCH;
     dc->wg_attr = true;
   }

@@ -187,6 +187,79 @@ __global__ void kmap_from_coarse_kernel(const int4* __restrict__ coords, int64_t
   }
 }
 
+// ---- the same table, one thread per ROW (used when the caller provides a workspace for the transposed child table) ----
+// The kernel above spends two dependent 4-byte reads of L2-resident tables per ENTRY (250 per row for a 5^3 map): 306 M
+// sector requests for the 125 x 1.22 M table of a ScanNet-shape batch, which is what its 1.6 ms were. Per row there are
+// only 27 coarse cells (8 for a 3^3 map) and the 8 children of a cell are one 32-byte sector of the TRANSPOSED child table
+// child8[coarse row][slot]: 27 + 27 reads per row. A thread collects its K^3 entries in shared memory ([k][thread], bank =
+// thread) and the block then writes the table rows k = 0 .. K^3 - 1 fully coalesced.
+__global__ void child_table_kernel(const int32_t* __restrict__ nbr_down, int64_t coarse_pitch, int32_t* __restrict__ child8) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= coarse_pitch) return;
+  int4 lo, hi;
+  lo.x = __ldg(nbr_down + 0 * coarse_pitch + c); lo.y = __ldg(nbr_down + 1 * coarse_pitch + c);
+  lo.z = __ldg(nbr_down + 2 * coarse_pitch + c); lo.w = __ldg(nbr_down + 3 * coarse_pitch + c);
+  hi.x = __ldg(nbr_down + 4 * coarse_pitch + c); hi.y = __ldg(nbr_down + 5 * coarse_pitch + c);
+  hi.z = __ldg(nbr_down + 6 * coarse_pitch + c); hi.w = __ldg(nbr_down + 7 * coarse_pitch + c);
+  reinterpret_cast<int4*>(child8)[2 * c] = lo;
+  reinterpret_cast<int4*>(child8)[2 * c + 1] = hi;
+}
+
+constexpr int kFromCoarseThreads = 128;
+template <int KS>
+__global__ void __launch_bounds__(kFromCoarseThreads)
+kmap_from_coarse_rows_kernel(const int4* __restrict__ coords, int64_t n, int ts, const int32_t* __restrict__ parent,
+                             const int32_t* __restrict__ nbr3_coarse, int64_t coarse_pitch, const int4* __restrict__ child8,
+                             int32_t* __restrict__ nbr, int64_t pitch, uint32_t* __restrict__ group_mask, int words) {
+  constexpr int KV = KS * KS * KS, H = KS / 2;
+  extern __shared__ int32_t sh_tab[];                       // [KV][kFromCoarseThreads]
+  const int t = threadIdx.x;
+  const int64_t row = (int64_t)blockIdx.x * kFromCoarseThreads + t;
+  const bool valid = row < n;
+  for (int k = 0; k < KV; ++k) sh_tab[k * kFromCoarseThreads + t] = -1;
+  if (valid) {
+    const int4 c = __ldg(coords + row);
+    const int cs = 2 * ts;
+    const int sx = (c.y - floor_to_multiple(c.y, cs)) / ts, sy = (c.z - floor_to_multiple(c.z, cs)) / ts,
+              sz = (c.w - floor_to_multiple(c.w, cs)) / ts;       // child slot of this row inside its parent, 0/1 per axis
+    const int32_t p = __ldg(parent + row);
+#pragma unroll 1
+    for (int cell = 0; cell < 27; ++cell) {
+      const int qx = cell % 3 - 1, qy = (cell / 3) % 3 - 1, qz = cell / 9 - 1;
+      // fine offsets that land in this coarse cell: d = 2 q + b - s with b in {0, 1}, |d| <= H, per axis
+      const int dx0 = 2 * qx - sx, dy0 = 2 * qy - sy, dz0 = 2 * qz - sz;
+      if (dx0 + 1 < -H || dx0 > H || dy0 + 1 < -H || dy0 > H || dz0 + 1 < -H || dz0 > H) continue;
+      const int32_t pc = (cell == 13) ? p : __ldg(nbr3_coarse + (int64_t)cell * coarse_pitch + p);
+      if (pc < 0) continue;
+      const int4 lo = __ldg(child8 + 2 * (int64_t)pc), hi = __ldg(child8 + 2 * (int64_t)pc + 1);
+      const int32_t ch[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const int dx = dx0 + (b & 1), dy = dy0 + ((b >> 1) & 1), dz = dz0 + (b >> 2);
+        if (dx < -H || dx > H || dy < -H || dy > H || dz < -H || dz > H) continue;
+        sh_tab[((dx + H) + KS * (dy + H) + KS * KS * (dz + H)) * kFromCoarseThreads + t] = ch[b];
+      }
+    }
+  }
+  __syncthreads();                                            // (only orders this thread's own writes for the compiler)
+  uint32_t m[4] = {0u, 0u, 0u, 0u};
+  if (row < pitch) {
+#pragma unroll 5
+    for (int k = 0; k < KV; ++k) {
+      const int32_t r = sh_tab[k * kFromCoarseThreads + t];
+      nbr[(int64_t)k * pitch + row] = r;
+      if (r >= 0) m[k >> 5] |= 1u << (k & 31);
+    }
+  }
+  if (group_mask != nullptr) {
+    // 64-row group = 2 warps of this block: OR the lanes' masks, one atomicOr per (warp, word)
+    for (int wd = 0; wd < words; ++wd) {
+      const uint32_t any = __reduce_or_sync(0xffffffffu, m[wd]);
+      if ((t & 31) == 0 && any && row < n) atomicOr(group_mask + (row >> 6) * words + wd, any);
+    }
+  }
+}
+
 __global__ void kmap_count_kernel(const int32_t* __restrict__ nbr, int64_t n_out, int64_t pitch, int32_t* __restrict__ counts) {
   const int k = blockIdx.y;
   int local = 0;
@@ -377,9 +450,14 @@ extern "C" int b2m_kernel_map_submanifold(const int32_t* coords, int64_t n, int3
   return B2M_OK;
 }
 
+extern "C" size_t b2m_kernel_map_from_coarse_workspace_bytes(int64_t n_coarse) {
+  return n_coarse > 0 ? (size_t)b2m_map_pitch(n_coarse) * 32 : 0;
+}
+
 extern "C" int b2m_kernel_map_from_coarse(const int32_t* coords, int64_t n, int32_t tensor_stride, int32_t kernel_size,
                                           const int32_t* parent_row, const int32_t* nbr3_coarse, const int32_t* nbr_down,
-                                          int64_t n_coarse, int32_t* nbr, uint32_t* group_mask, b2m_stream_t stream) {
+                                          int64_t n_coarse, int32_t* nbr, uint32_t* group_mask, void* workspace,
+                                          size_t workspace_bytes, b2m_stream_t stream) {
   if (kernel_size != 3 && kernel_size != 5) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n == 0) return B2M_OK;
   if (!coords || !parent_row || !nbr3_coarse || !nbr_down || !nbr || n < 0 || n_coarse <= 0 || tensor_stride <= 0)
@@ -387,12 +465,39 @@ extern "C" int b2m_kernel_map_from_coarse(const int32_t* coords, int64_t n, int3
   cudaStream_t st = (cudaStream_t)stream;
   const int kvol = kernel_size * kernel_size * kernel_size;
   const int words = (kvol + 31) / 32;
-  const int64_t pitch = b2m_map_pitch(n);
+  const int64_t pitch = b2m_map_pitch(n), coarse_pitch = b2m_map_pitch(n_coarse);
   if (group_mask)
     if (cudaMemsetAsync(group_mask, 0, (size_t)((n + 63) / 64) * words * 4, st) != cudaSuccess) return B2M_ERR_CUDA_LAUNCH;
+  if (workspace && workspace_bytes >= (size_t)coarse_pitch * 32 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+    // one thread per row over the transposed child table (27 + 27 table reads per row instead of 2 per entry)
+    int32_t* child8 = reinterpret_cast<int32_t*>(workspace);
+    child_table_kernel<<<cdiv(coarse_pitch, 256), 256, 0, st>>>(nbr_down, coarse_pitch, child8);
+    B2M_CHECK_LAUNCH();
+    const unsigned blocks = (unsigned)(pitch / kFromCoarseThreads);
+    const size_t sh = (size_t)kvol * kFromCoarseThreads * 4;
+    if (kernel_size == 5) {
+      static bool attr5[64];
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev >= 0 && dev < 64 && !attr5[dev]) {
+        if (cudaFuncSetAttribute(kmap_from_coarse_rows_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh) != cudaSuccess)
+          return B2M_ERR_CUDA_LAUNCH;
+        attr5[dev] = true;
+      }
+      kmap_from_coarse_rows_kernel<5><<<blocks, kFromCoarseThreads, sh, st>>>(
+          reinterpret_cast<const int4*>(coords), n, tensor_stride, parent_row, nbr3_coarse, coarse_pitch,
+          reinterpret_cast<const int4*>(child8), nbr, pitch, group_mask, words);
+    } else {
+      kmap_from_coarse_rows_kernel<3><<<blocks, kFromCoarseThreads, sh, st>>>(
+          reinterpret_cast<const int4*>(coords), n, tensor_stride, parent_row, nbr3_coarse, coarse_pitch,
+          reinterpret_cast<const int4*>(child8), nbr, pitch, group_mask, words);
+    }
+    B2M_CHECK_LAUNCH();
+    return B2M_OK;
+  }
   kmap_from_coarse_kernel<<<cdiv(pitch * kvol, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, tensor_stride,
                                                                   kernel_size, parent_row, nbr3_coarse, nbr_down,
-                                                                  b2m_map_pitch(n_coarse), nbr, pitch, group_mask, words);
+                                                                  coarse_pitch, nbr, pitch, group_mask, words);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }

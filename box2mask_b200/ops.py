@@ -169,9 +169,11 @@ def kernel_map_from_coarse(coords, tensor_stride, kernel_size, parent_row, nbr3_
     kvol = kernel_size ** 3
     nbr = torch.empty((kvol, map_pitch(n)), dtype=torch.int32, device=coords.device)
     gmask = torch.empty(((n + 63) // 64, (kvol + 31) // 32), dtype=torch.int32, device=coords.device) if want_gmask else None
-    _run("kernel_map_from_coarse", 1, lambda: check(lib.b2m_kernel_map_from_coarse(
+    ws_bytes = int(lib.b2m_kernel_map_from_coarse_workspace_bytes(int(n_coarse)))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=coords.device)       # transposed child table
+    _run("kernel_map_from_coarse", 2, lambda: check(lib.b2m_kernel_map_from_coarse(
         ptr(coords), n, int(tensor_stride), int(kernel_size), ptr(parent_row), ptr(nbr3_coarse), ptr(nbr_down), int(n_coarse),
-        ptr(nbr), ptr(gmask), stream_ptr()), "kernel_map_from_coarse"), nbytes=20 * n + 4 * n * kvol)
+        ptr(nbr), ptr(gmask), ptr(ws), ws_bytes, stream_ptr()), "kernel_map_from_coarse"), nbytes=20 * n + 4 * n * kvol)
     return (nbr, gmask) if want_gmask else nbr
 
 

@@ -183,7 +183,9 @@ class SelectionNet(nn.Module):
         ME.prepack_conv_weights(self)      # every conv's forward and dgrad weight image, one launch per step
         x.coordinate_manager.wait_ready()  # maps prefetched on a side stream (Model.prefetch_coordinates), if any
         x.coordinate_manager.prepare(*self.coordinate_plan())   # no-op for levels / maps that already exist
-        if self.use_trunk_executor:
+        # the executor covers training (forward + backward) and inference; a backward pass through eval-mode BatchNorm
+        # (fine-tuning with frozen statistics, the gradient parity tests) goes module by module through autograd
+        if self.use_trunk_executor and (self.training or not torch.is_grad_enabled()):
             out = x._like(self.trunk_executor().run(x), 1)
         else:
             out = self.forward_trunk_modules(x)

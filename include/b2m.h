@@ -106,10 +106,15 @@ int b2m_kernel_map_submanifold(const int32_t* coords, int64_t n, int32_t tensor_
  * b2m_kernel_map_stride2 (unsorted), nbr3_coarse int32[27, pitch(n_coarse)] = the coarse level's own 3^3 table
  * (unsorted). nbr[k][o] = nbr_down[slot][nbr3_coarse[kP][parent_row[o]]]: two reads of small dense tables per entry.
  * group_mask (optional, uint32[ceil(n/64), ceil(K/32)], zeroed inside) receives the offsets present in each 64-row group
- * of the UNSORTED table (what a map that is consumed in its original row order needs, e.g. the 125-offset map). */
+ * of the UNSORTED table (what a map that is consumed in its original row order needs, e.g. the 125-offset map).
+ * workspace (optional, b2m_kernel_map_from_coarse_workspace_bytes(n_coarse) bytes, 16-byte aligned): room for the child
+ * table transposed to [coarse row][8]; with it the table is built one thread per row (27 + 27 table reads per row and
+ * coalesced writes) instead of one thread per entry; the result is identical. */
+size_t b2m_kernel_map_from_coarse_workspace_bytes(int64_t n_coarse);
 int b2m_kernel_map_from_coarse(const int32_t* coords, int64_t n, int32_t tensor_stride, int32_t kernel_size,
                                const int32_t* parent_row, const int32_t* nbr3_coarse, const int32_t* nbr_down,
-                               int64_t n_coarse, int32_t* nbr, uint32_t* group_mask, b2m_stream_t stream);
+                               int64_t n_coarse, int32_t* nbr, uint32_t* group_mask, void* workspace,
+                               size_t workspace_bytes, b2m_stream_t stream);
 /* kernel 2 / stride 2 maps from the parent relation of b2m_downsample_coords.
  * nbr_down int32[8, pitch(n_coarse)]: child row of coarse row o at offset k (strided conv, coarse output).
  * nbr_up   int32[8, pitch(n_fine)]  : parent row if offset(f)==k else -1 (transposed conv, fine output).
