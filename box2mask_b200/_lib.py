@@ -60,6 +60,11 @@ SIGNATURES = {
     "b2m_mask_nms_workspace_bytes": (c_size_t, [c_int64]),
     "b2m_mask_nms": (c_int32, [_P, c_int64, c_int64, c_float, _P, _P, _P, c_size_t, _P]),
     "b2m_unpack_masks": (c_int32, [_P, c_int64, c_int64, c_int64, _P, _P]),
+    "b2m_point_box_occupancy": (c_int32, [_P, c_int64, _P, _P, _P, c_int32, _P, _P, _P, _P]),
+    "b2m_point_instances": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P, _P]),
+    "b2m_segment_association_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "b2m_segment_association": (c_int32, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P,
+                                          c_size_t, _P]),
     "b2m_voxel_coords": (c_int32, [_P, c_int64, _P, c_double, _P, _P, _P]),
     "b2m_nearest_point": (c_int32, [_P, _P, c_double, _P, c_int64, _P, _P, _P, _P, _P]),
 }
@@ -102,7 +107,7 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
-OPT_MAX_CTAS, OPT_CHUNKS_PER_STAGE, OPT_SPLIT_OFFSETS, OPT_GATHER_MODE, OPT_WGRAD_ROWS, OPT_ISSUER = 1, 2, 3, 4, 5, 6
+OPT_MAX_CTAS, OPT_CHUNKS_PER_STAGE, OPT_SPLIT_OFFSETS, OPT_GATHER_MODE, OPT_WGRAD_ROWS, OPT_ISSUER, OPT_WGRAD_GROUP, OPT_WGRAD_BSLOTS = 1, 2, 3, 4, 5, 6, 8, 9
 
 
 def set_option(option, value):

@@ -204,6 +204,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// L2 prefetch of a contiguous global range through the TMA engine (no shared-memory destination, nothing to wait for)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // TMA row gather (sm_100a): 4 rows (r0..r3, any order, out-of-range rows are zero-filled) x one box of columns
 // starting at `col` of a 2-D tensor map whose box is {columns, 1}; the rows land back to back in shared memory

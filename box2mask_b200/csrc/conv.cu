@@ -296,6 +296,9 @@ __device__ __forceinline__ void ldgsts_rows_sw128(uint32_t dst, const uint8_t* _
   const uint32_t d_even = dst + (uint32_t)(s * 128 + ((j ^ s) << 4));
   const uint32_t d_odd = dst + (uint32_t)((4 + s) * 128 + ((j ^ (4 + s)) << 4));
   const uint8_t* src_lane = src + j * 16;
+#ifdef B2M_LDGSTS_LEAN_ADDR
+  asm volatile("" : "+l"(src_lane));     // one opaque 64-bit base: the row address is a single IMAD.WIDE
+#endif
   const bool colok = j < pieces;
 #pragma unroll
   for (int i = 0; i < NROWS / 4; ++i) {
@@ -313,10 +316,56 @@ __device__ __forceinline__ void ldgsts_rows_sw64(uint32_t dst, const uint8_t* __
   const int j = lane & 3, s = lane >> 2;
   const uint32_t d0 = dst + (uint32_t)(s * 64 + ((j ^ ((lane >> 3) & 3)) << 4));
   const uint8_t* src_lane = src + j * 16;
+#ifdef B2M_LDGSTS_LEAN_ADDR
+  asm volatile("" : "+l"(src_lane));
+#endif
 #pragma unroll
   for (int i = 0; i < NROWS / 8; ++i) {
     const int r = __shfl_sync(0xFFFFFFFFu, R[i >> 2], ((8 * i) & 31) + s);
     cp_async16_zfill(d0 + (uint32_t)(i * 512), src_lane + (uint64_t)(uint32_t)max(r, 0) * (uint64_t)row_bytes, r < 0);
+  }
+}
+
+// Rolled variants (one loop per index register, ~1 KB of SASS per instance instead of ~3.7 KB) for the wgrad kernel's
+// optional cp.async mode. NOT for the forward kernel: how fast a gather warp gets its requests out sets the turnaround of
+// a ring slot, and with these loops (shuffle -> address -> copy serialised per iteration, ~1300 cycles per chunk) the
+// forward kernel measured 0.61 ms on k27 96->96 against 0.48 ms with the unrolled bursts above (TMA gather4: 0.59 ms).
+template <int NROWS>
+__device__ __forceinline__ void ldgsts_rows_sw128_rolled(uint32_t dst, const uint8_t* __restrict__ src, uint32_t row_bytes,
+                                                  const int (&R)[NROWS / 32], int lane, int pieces) {
+  const int j = lane & 7, s = lane >> 3;
+  const uint32_t d_even = dst + (uint32_t)(s * 128 + ((j ^ s) << 4));
+  const uint32_t d_odd = dst + (uint32_t)((4 + s) * 128 + ((j ^ (4 + s)) << 4));
+  const uint8_t* src_lane = src + j * 16;
+  const bool colok = j < pieces;
+#pragma unroll
+  for (int u = 0; u < NROWS / 32; ++u) {
+    const int Ru = R[u];
+#pragma unroll 2
+    for (int ii = 0; ii < 8; ++ii) {                 // rows 32 u + 4 ii + s
+      const int r = __shfl_sync(0xFFFFFFFFu, Ru, 4 * ii + s);
+      const bool ok = colok && r >= 0;
+      // (a row without a neighbour reads nothing: the address only has to be well formed)
+      cp_async16_zfill(((ii & 1) ? d_odd : d_even) + (uint32_t)((4 * u + (ii >> 1)) * 1024),
+                       src_lane + (uint64_t)(uint32_t)max(r, 0) * (uint64_t)row_bytes, !ok);
+    }
+  }
+}
+// NROWS rows x 32 channels -> SW64 tile (row r at r * 64, 16-byte piece j at (j ^ ((r >> 1) & 3)) * 16)
+template <int NROWS>
+__device__ __forceinline__ void ldgsts_rows_sw64_rolled(uint32_t dst, const uint8_t* __restrict__ src, uint32_t row_bytes,
+                                                 const int (&R)[NROWS / 32], int lane) {
+  const int j = lane & 3, s = lane >> 2;
+  const uint32_t d0 = dst + (uint32_t)(s * 64 + ((j ^ ((lane >> 3) & 3)) << 4));
+  const uint8_t* src_lane = src + j * 16;
+#pragma unroll
+  for (int u = 0; u < NROWS / 32; ++u) {
+    const int Ru = R[u];
+#pragma unroll 2
+    for (int ii = 0; ii < 4; ++ii) {                 // rows 32 u + 8 ii + s
+      const int r = __shfl_sync(0xFFFFFFFFu, Ru, 8 * ii + s);
+      cp_async16_zfill(d0 + (uint32_t)((4 * u + ii) * 512), src_lane + (uint64_t)(uint32_t)max(r, 0) * (uint64_t)row_bytes, r < 0);
+    }
   }
 }
 
@@ -1185,9 +1234,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   __shared__ int s_cnt[128];
   __shared__ int s_koff[16];
   __shared__ int s_nq;
-  for (int i = tid; i < 128; i += kWgThreads) s_cnt[i] = 0;
-  __syncthreads();
-  if (a.gmask != nullptr && a.ncols > 1) {
+  // (small launches are latency bound, not balance bound, and the serial assignment below costs tens of microseconds
+  // for 27 slots in 14 columns: they take the interleaved assignment slot = col + ncols * q)
+  const bool balance = a.gmask != nullptr && a.ncols > 1 && a.n_out >= 32768 && kslots_all <= 32 && a.ncols <= 32;
+  if (balance) {
+    for (int i = tid; i < 128; i += kWgThreads) s_cnt[i] = 0;
+    __syncthreads();
     const int64_t ng = (a.n_out + 63) / 64;
     const uint32_t pkb = (a.pk >= 32) ? 0xFFFFFFFFu : ((1u << a.pk) - 1u);
     for (int64_t g = tid; g < ng; g += kWgThreads) {
@@ -1197,26 +1249,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if ((mask_word(m, k0 >> 5) >> (k0 & 31)) & pkb) atomicAdd(&s_cnt[sl], 1);
       }
     }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int load[128], fill[128];                // ncols <= kslots_all <= 128
-    for (int c2 = 0; c2 < a.ncols; ++c2) { load[c2] = 0; fill[c2] = 0; }
-    int nq_mine = 0;
-    unsigned long long done_lo = 0ull, done_hi = 0ull;
-    for (int it = 0; it < kslots_all; ++it) {
-      int best = -1, bc = -1;
-      for (int sl = 0; sl < kslots_all; ++sl) {            // heaviest slot not placed yet (ties: lowest index)
-        const bool dn = sl < 64 ? ((done_lo >> sl) & 1ull) : ((done_hi >> (sl - 64)) & 1ull);
-        if (!dn && s_cnt[sl] > bc) { bc = s_cnt[sl]; best = sl; }
+    __syncthreads();
+    if (warp == 0) {
+      // longest-processing-time assignment by one warp: lane = slot for the arg-max, lane = column for the arg-min
+      int cnt = lane < kslots_all ? s_cnt[lane] : -1;
+      int load = 0, fill = 0, nq_mine = 0;
+      for (int it = 0; it < kslots_all; ++it) {
+        const int best = __reduce_max_sync(0xFFFFFFFFu, cnt < 0 ? -1 : ((cnt << 5) | (31 - lane)));   // ties: lowest slot
+        const int slot = 31 - (best & 31), bc = best >> 5;
+        if (lane == slot) cnt = -1;
+        const int tgt = __reduce_min_sync(0xFFFFFFFFu, (lane < a.ncols && fill < a.G) ? ((load << 5) | lane) : 0x7FFFFFFF) & 31;
+        if (lane == tgt) { load += bc; fill += 1; }
+        if (tgt == col) { if (lane == 0) s_koff[nq_mine] = slot; ++nq_mine; }
       }
-      if (best < 64) done_lo |= 1ull << best; else done_hi |= 1ull << (best - 64);
-      int tgt = -1;
-      for (int c2 = 0; c2 < a.ncols; ++c2)                 // least loaded column with a free accumulator (ties: lowest)
-        if (fill[c2] < a.G && (tgt < 0 || load[c2] < load[tgt])) tgt = c2;
-      load[tgt] += bc; fill[tgt] += 1;
-      if (tgt == col) s_koff[nq_mine++] = best;
+      if (lane == 0) s_nq = nq_mine;
     }
+  } else if (tid == 0) {
+    int nq_mine = 0;
+    for (int sl = col; sl < kslots_all; sl += a.ncols) s_koff[nq_mine++] = sl;
     s_nq = nq_mine;
   }
   __syncthreads();
@@ -1382,6 +1432,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     Ring rb;
     rb.init(SB);
     int turn = 0;
+    int Rb_next[ROWS / 32];
+    bool rb_have = false;
+    int64_t rb_g = -1;
+    (void)rb_g;
+    auto load_order = [&](int64_t gq, int (&R)[ROWS / 32]) {
+      const int64_t p0 = gq * ROWS + lane;
+#pragma unroll
+      for (int u = 0; u < ROWS / 32; ++u) {
+        if (a.order) R[u] = (p0 + 32 * u < a.n_pitch) ? __ldg(a.order + p0 + 32 * u) : -1;
+        else R[u] = p0 + 32 * u < a.n_out ? (int)(p0 + 32 * u) : -1;
+      }
+    };
     const int items = a.nbb * 16;   // (column block, 4-row quad)
     MaskBits m_next = group_mask(g_begin < g_end ? g_begin : 0);
     for (int64_t g = g_begin; g < g_end; g += g_step) {
@@ -1394,13 +1456,27 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const uint32_t b_s = smem_base + a.off_b + rb.slot * a.b_bytes;
       const uint32_t full = b_full + 8 * rb.slot;
       if (a.ldb) {
-        // cp.async mode: lane l holds the rows at positions l and 32 + l of the group
+        // cp.async mode: lane l holds the rows at positions l, 32 + l, ... of the group; the indices of this warp's NEXT
+        // group were loaded one stage ago (Rb_next below)
         int R[ROWS / 32];
-        const int64_t p0 = g * ROWS + lane;
+        if (rb_have) {
 #pragma unroll
-        for (int u = 0; u < ROWS / 32; ++u) {
-          if (a.order) R[u] = (p0 + 32 * u < a.n_pitch) ? __ldg(a.order + p0 + 32 * u) : -1;
-          else R[u] = p0 + 32 * u < a.n_out ? (int)(p0 + 32 * u) : -1;
+          for (int u = 0; u < ROWS / 32; ++u) R[u] = Rb_next[u];
+        } else {
+          load_order(g, R);
+        }
+        // look ahead: the next group this warp gathers
+        {
+          int64_t g2 = g + g_step;
+          int t2 = turn;                      // turn already advanced past this stage
+          rb_have = false;
+          while (g2 < g_end) {
+            if (acc_mask(group_mask(g2))) {
+              if (t2 == pb) { load_order(g2, Rb_next); rb_have = true; rb_g = g2; break; }
+              t2 = (t2 + 1 == npb) ? 0 : t2 + 1;
+            }
+            g2 += g_step;
+          }
         }
         mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u, 23);
         const uint8_t* dyb = reinterpret_cast<const uint8_t*>(a.dy);
@@ -1408,9 +1484,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int blk = partb; blk < a.nbb; blk += a.nwb) {
           if (a.wb == 128) {
             const int left = (a.c_out - blk * 64) >> 3;
-            ldgsts_rows_sw128<ROWS>(b_s + blk * (ROWS * 128), dyb + blk * 128, row_bytes, R, lane, left < 8 ? left : 8);
+            ldgsts_rows_sw128_rolled<ROWS>(b_s + blk * (ROWS * 128), dyb + blk * 128, row_bytes, R, lane, left < 8 ? left : 8);
           } else {
-            ldgsts_rows_sw64<ROWS>(b_s + blk * (ROWS * 64), dyb + blk * 64, row_bytes, R, lane);
+            ldgsts_rows_sw64_rolled<ROWS>(b_s + blk * (ROWS * 64), dyb + blk * 64, row_bytes, R, lane);
           }
         }
         cp_async_mbar_arrive_noinc(full);
@@ -1447,6 +1523,94 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     ra.init(SA);
     int turn = 0;
     const int items = a.nab * 16;   // (block, 4-row quad); pk > 1: block == packed offset slot, else channel block
+    if (a.lda && a.cpad != 8) {
+      // ---- cp.async mode, software-pipelined: the row indices of this warp's NEXT stage are loaded (streamed from
+      // DRAM: ~1-2 us) before the current stage waits for its slot, like the forward kernel's gather warps. Stages are
+      // enumerated in the order every role uses: row groups ascending, within a group the set bits of acc_mask
+      // ascending; stage n lives in ring slot n % SA and belongs to producer group n % np.
+      struct St { bool valid; int64_t g; int q; int slot; uint32_t phase; };
+      int64_t ge = g_begin - g_step;
+      uint32_t rem = 0;
+      int n_mod = 0;
+      Ring ring;
+      ring.init(SA);
+      auto next = [&]() -> St {
+        St st; st.valid = false; st.g = 0; st.q = 0; st.slot = 0; st.phase = 0;
+        if (p >= np) return st;
+        while (true) {
+          if (rem == 0) {
+            ge += g_step;
+            if (ge >= g_end) return st;
+            rem = acc_mask(group_mask(ge));
+            continue;
+          }
+          const int q = __ffs(rem) - 1;
+          rem &= rem - 1;
+          const bool mine = (n_mod == p);
+          n_mod = (n_mod + 1 == np) ? 0 : n_mod + 1;
+          if (mine) { st.valid = true; st.g = ge; st.q = q; st.slot = ring.slot; st.phase = ring.phase; ring.next(); return st; }
+          ring.next();
+        }
+      };
+      auto load_rows = [&](const St& st, int (&R)[4][ROWS / 32]) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int u = 0; u < ROWS / 32; ++u) R[b][u] = -1;
+        if (!st.valid) return;
+        const int k0 = k_first(st.q);
+        const int nslots = min(a.pk, a.kvol - k0);
+        const int64_t p0 = st.g * ROWS + lane;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+#pragma unroll
+          for (int u = 0; u < ROWS / 32; ++u) {
+            if (b < (a.pk > 1 ? nslots : 1) && p0 + 32 * u < a.n_pitch) {
+              if (a.nbr) R[b][u] = __ldg(a.nbr + (int64_t)(k0 + b) * a.n_pitch + p0 + 32 * u);
+              else R[b][u] = p0 + 32 * u < a.n_out ? (int)(p0 + 32 * u) : -1;
+            }
+          }
+        }
+        if (a.pk == 1) {                 // the column blocks of one offset share its rows
+#pragma unroll
+          for (int b = 1; b < 4; ++b)
+#pragma unroll
+            for (int u = 0; u < ROWS / 32; ++u) R[b][u] = R[0][u];
+        }
+      };
+      const uint8_t* xb = reinterpret_cast<const uint8_t*>(a.x);
+      const uint32_t row_bytes = (uint32_t)a.c_in * 2u;
+      St cur = next();
+      int R[4][ROWS / 32];
+      load_rows(cur, R);
+      while (cur.valid) {
+        const St nxt = next();
+        int Rn[4][ROWS / 32];
+        load_rows(nxt, Rn);                                   // in flight while this stage waits for its slot
+        const uint32_t a_s = smem_base + cur.slot * kSlotA;
+        const int nslots = min(a.pk, a.kvol - k_first(cur.q));
+        mbar_wait(a_empty + 8 * cur.slot, cur.phase ^ 1u, 24);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (b < a.nab && !(a.pk > 1 && b >= nslots) && (b % a.nwa) == part) {
+            if (a.wa == 128) {
+              const int col0 = (a.pk > 1) ? 0 : mt * 128 + b * 64;         // first channel of the block
+              const int left = (a.c_in - col0) >> 3;
+              ldgsts_rows_sw128_rolled<ROWS>(a_s + b * (ROWS * 128), xb + col0 * 2, row_bytes, R[b], lane,
+                                         left < 8 ? (left > 0 ? left : 0) : 8);
+            } else {
+              ldgsts_rows_sw64_rolled<ROWS>(a_s + b * (ROWS * 64), xb, row_bytes, R[b], lane);
+            }
+          }
+        }
+        cp_async_mbar_arrive_noinc(a_full + 8 * cur.slot);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int u = 0; u < ROWS / 32; ++u) R[b][u] = Rn[b][u];
+        cur = nxt;
+      }
+    } else {
     MaskBits m_next = group_mask(g_begin < g_end ? g_begin : 0);
     for (int64_t g = g_begin; g < g_end; g += g_step) {
       const MaskBits m = m_next;
@@ -1497,49 +1661,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full + 8 * ra.slot);
-        } else if (mine && a.lda) {
-          // cp.async mode (wa 128 or 64): block = 64 gathered rows x wa bytes; pk > 1: block b holds offset k0 + b,
-          // else the blocks are the 64-channel column blocks of one offset
-          const uint32_t a_s = smem_base + ra.slot * kSlotA;
-          const uint32_t full = a_full + 8 * ra.slot;
-          const int k0 = k_first(q);
-          const int nslots = min(a.pk, a.kvol - k0);
-          const int64_t p0 = g * ROWS + lane;
-          const uint8_t* xb = reinterpret_cast<const uint8_t*>(a.x);
-          const uint32_t row_bytes = (uint32_t)a.c_in * 2u;
-          int R[4][ROWS / 32];
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-#pragma unroll
-            for (int u = 0; u < ROWS / 32; ++u) {
-              R[b][u] = -1;
-              if (b < (a.pk > 1 ? nslots : 1) && p0 + 32 * u < a.n_pitch) {
-                if (a.nbr) R[b][u] = __ldg(a.nbr + (int64_t)(k0 + b) * a.n_pitch + p0 + 32 * u);
-                else R[b][u] = p0 + 32 * u < a.n_out ? (int)(p0 + 32 * u) : -1;
-              }
-            }
-          }
-          if (a.pk == 1) {                 // the column blocks of one offset share its rows
-#pragma unroll
-            for (int b = 1; b < 4; ++b)
-#pragma unroll
-              for (int u = 0; u < ROWS / 32; ++u) R[b][u] = R[0][u];
-          }
-          mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u, 24);
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            if (b < a.nab && !(a.pk > 1 && b >= nslots) && (b % a.nwa) == part) {
-              if (a.wa == 128) {
-                const int col0 = (a.pk > 1) ? 0 : mt * 128 + b * 64;         // first channel of the block
-                const int left = (a.c_in - col0) >> 3;
-                ldgsts_rows_sw128<ROWS>(a_s + b * (ROWS * 128), xb + col0 * 2, row_bytes, R[b], lane,
-                                           left < 8 ? (left > 0 ? left : 0) : 8);
-              } else {
-                ldgsts_rows_sw64<ROWS>(a_s + b * (ROWS * 64), xb, row_bytes, R[b], lane);
-              }
-            }
-          }
-          cp_async_mbar_arrive_noinc(full);
         } else if (mine) {
           const uint32_t a_s = smem_base + ra.slot * kSlotA;
           const uint32_t full = a_full + 8 * ra.slot;
@@ -1586,6 +1707,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       ra = ra0.at(n_g);
       turn += n_g;
       while (turn >= np) turn -= np;
+    }
     }
   }
 
@@ -1674,10 +1796,12 @@ static DeviceCache* device_cache() {
 //   B2M_OPT_CHUNKS_PER_STAGE: force 1 or 2 64-wide chunks per pipeline stage of the forward kernel (0 = automatic).
 //   B2M_OPT_SPLIT_OFFSETS: 0 = automatic offset splitting on levels with few row tiles, 1 = never split (tests).
 //   B2M_OPT_GATHER_MODE: 0 = cp.async row gathers for reductions of >= 48 channels (the MMA issuer fences the proxies),
-//   1 = TMA gather4 (round 1), 2 = cp.async with the proxy fence on the producer side (forward kernel only).
+//   1 = TMA gather4 (round 1), 2 = cp.async with the proxy fence on the producer side (forward kernel only),
+//   3 = cp.async in the wgrad kernel too (its default stays TMA gather4).
 //   B2M_OPT_ISSUER: 1 = general MMA issue loop of the forward kernel everywhere (0 = lean loop where it applies).
 //   B2M_OPT_WGRAD_ROWS: 64 = wgrad pipeline stages of 64 reduction rows always (0 = 128 rows on large levels).
 static int g_opt_max_ctas = 0, g_opt_cps = 0, g_opt_nosplit = 0, g_opt_gather = 0, g_opt_wgrows = 0, g_opt_issuer = 0;
+static int g_opt_wggroup = 0, g_opt_wgbslots = 0;
 static int num_sms() {
   const int sms = device_cache()->sms;
   const int cap = g_opt_max_ctas;
@@ -1688,8 +1812,10 @@ extern "C" int b2m_set_option(int32_t option, int64_t value) {
     case B2M_OPT_MAX_CTAS: g_opt_max_ctas = value > 0 ? (int)value : 0; return B2M_OK;
     case B2M_OPT_CHUNKS_PER_STAGE: g_opt_cps = (value == 1 || value == 2) ? (int)value : 0; return B2M_OK;
     case B2M_OPT_SPLIT_OFFSETS: g_opt_nosplit = value ? 1 : 0; return B2M_OK;
-    case B2M_OPT_GATHER_MODE: g_opt_gather = (value == 1 || value == 2) ? (int)value : 0; return B2M_OK;
+    case B2M_OPT_GATHER_MODE: g_opt_gather = (value >= 1 && value <= 3) ? (int)value : 0; return B2M_OK;
     case B2M_OPT_ISSUER: g_opt_issuer = value ? 1 : 0; return B2M_OK;
+    case B2M_OPT_WGRAD_GROUP: g_opt_wggroup = (value == 2) ? 2 : 0; return B2M_OK;
+    case B2M_OPT_WGRAD_BSLOTS: g_opt_wgbslots = (int)value; return B2M_OK;
     case B2M_OPT_WGRAD_ROWS: g_opt_wgrows = (value == 64) ? 64 : 0; return B2M_OK;
     default: return B2M_ERR_INVALID_ARGUMENT;
   }
@@ -1832,7 +1958,10 @@ extern "C" int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_re
   a.colstride = (a.ntile + 31) / 32 * 32;
   a.n_tiles = (int)((n_out + kTileM - 1) / kTileM);
   const int sms = num_sms();
-  a.T = (a.ntile <= 128 && a.n_tiles >= 4 * sms) ? 2 : 1;
+#ifndef B2M_T2_MIN_ROUNDS
+#define B2M_T2_MIN_ROUNDS 4
+#endif
+  a.T = (a.ntile <= 128 && a.n_tiles >= B2M_T2_MIN_ROUNDS * sms) ? 2 : 1;
   a.n_work = (a.n_tiles + a.T - 1) / a.T;
   // KPACK == 1: an A stage holds one or two 64-wide chunks of one offset (each gathered by its own warp) and a weight
   // slot the matching slices. The MMA issuer pays ~1000 cycles (0.5 us) of dependent barrier / fence / commit latency
@@ -1891,7 +2020,7 @@ extern "C" int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_re
   a.off_bars = (a.off_ep + ep_bytes + 15) / 16 * 16;
   a.tmem_cols = pow2_cols(2 * a.T * a.colstride);
   if (a.tmem_cols > 512) return B2M_ERR_UNSUPPORTED_SHAPE;
-  a.ldgsts = (a.kpack == 1 && g_opt_gather != 1) ? (g_opt_gather == 2 ? 2 : 1) : 0;
+  a.ldgsts = (a.kpack == 1 && g_opt_gather != 1) ? (g_opt_gather == 2 ? 2 : 1) : 0;     // modes 0 and 3: cp.async, issuer-side fence
   // (measured on k27 256->256 over 1.22 M rows: 2.66 ms lean vs 2.45 ms general - with 256-wide tiles the tensor pipe, not
   // the issue loop, paces the kernel, and the straight-line stage block gives the MMAs less slack; lean for tiles <= 128)
   a.lean_off = (g_opt_issuer || a.ntile > 128) ? 1 : 0;
@@ -1970,10 +2099,15 @@ static int wgrad_run(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16
   a.nab = 128 * 2 / a.wa;
   a.wb = (c_out == 16 || c_out == 32) ? c_out * 2 : 128;
   a.nbb = (c_out * 2 + a.wb - 1) / a.wb;
-  a.lda = (g_opt_gather != 1 && (a.cpad >= 64 || c_in == 32)) ? 1 : 0;      // SW128 blocks, or SW64 for exactly 32 channels
-  a.ldb = (g_opt_gather != 1 && a.wb >= 64) ? 1 : 0;
-  a.nwa = (a.lda && a.nab >= 2) ? 2 : 1;
-  a.nwb = (a.ldb && a.nbb >= 2) ? 2 : 1;
+  // wgrad keeps the TMA gather4 row gathers by default: measured on k27 96->96 over 1.22 M rows 1.06-1.09 ms in every
+  // build, against 1.12-1.46 ms for the cp.async variants (B2M_OPT_GATHER_MODE = 3 selects them)
+  // Exception: 32-channel operands. A gather4 then moves only 4 x 64 bytes per instruction and the kernel is bound by the
+  // TMA request rate: k27 32->32 over 291 k rows 0.213 ms with TMA gathers, 0.082 ms with cp.async.
+  a.lda = ((g_opt_gather == 3 && a.cpad >= 64) || (g_opt_gather != 1 && c_in == 32)) ? 1 : 0;   // SW128 blocks / SW64 for 32 channels
+  a.ldb = ((g_opt_gather == 3 && a.wb >= 64) || (g_opt_gather != 1 && a.wb == 64)) ? 1 : 0;
+  // (measured on k27 96->96 over 1.22 M rows: two-warp producer groups 1.28 ms, one warp per stage 1.12 ms)
+  a.nwa = (g_opt_wggroup == 2 && a.lda && a.nab >= 2) ? 2 : 1;
+  a.nwb = (g_opt_wggroup == 2 && a.ldb && a.nbb >= 2) ? 2 : 1;
   const int mtiles = (c_in + 127) / 128;
   a.colstride = (c_out + 31) / 32 * 32;
   int G = 512 / a.colstride;
@@ -2028,6 +2162,7 @@ static int wgrad_run(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16
   if (a.b_bytes < 1024) a.b_bytes = 1024;
   a.b_bytes = (a.b_bytes + 1023) / 1024 * 1024;
   a.b_slots = a.b_bytes >= 65536 ? 2 : (a.b_bytes >= 32768 ? 3 : 4);
+  if (g_opt_wgbslots >= 2 && g_opt_wgbslots <= 8 && g_opt_wgbslots * a.b_bytes <= 128 * 1024) a.b_slots = g_opt_wgbslots;
   a.a_slots = (227 * 1024 - 2048 - 256 - a.b_slots * a.b_bytes) / a_slot_bytes;   // (1 KB of static shared memory)
   if (a.a_slots > 10) a.a_slots = 10;
   if (a.a_slots < 2) return B2M_ERR_UNSUPPORTED_SHAPE;

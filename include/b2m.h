@@ -49,9 +49,12 @@ const char* b2m_error_string(int code);
  *                            the data-parallel host while a gradient all-reduce overlaps the backward pass
  *  B2M_OPT_CHUNKS_PER_STAGE  force 1 or 2 reduction chunks per pipeline stage of the forward kernel (0 = auto)
  *  B2M_OPT_SPLIT_OFFSETS     1 = never split the kernel offsets of a convolution over CTAs (0 = automatic)
- *  B2M_OPT_GATHER_MODE       0 = feature rows gathered with cp.async (default), 1 = with TMA gather4, 2 = cp.async
- *                            with the generic->async proxy fence on the producer side (forward kernel)
+ *  B2M_OPT_GATHER_MODE       0 = forward / dgrad gather feature rows with cp.async, wgrad with TMA gather4 (default),
+ *                            1 = TMA gather4 everywhere, 2 = cp.async with the generic->async proxy fence on the
+ *                            producer side (forward kernel), 3 = cp.async in wgrad too
  *  B2M_OPT_ISSUER            1 = general MMA issue loop of the forward kernel (0 = lean loop where it applies)
+ *  B2M_OPT_WGRAD_BSLOTS      dY ring depth of the wgrad kernel (0 = automatic)
+ *  B2M_OPT_WGRAD_GROUP       2 = two gather warps per wgrad pipeline stage (0 = one)
  *  B2M_OPT_WGRAD_ROWS        64 = 64 reduction rows per wgrad pipeline stage always (0 = 128 on large levels) */
 #define B2M_OPT_MAX_CTAS 1
 #define B2M_OPT_CHUNKS_PER_STAGE 2
@@ -59,6 +62,8 @@ const char* b2m_error_string(int code);
 #define B2M_OPT_GATHER_MODE 4
 #define B2M_OPT_WGRAD_ROWS 5
 #define B2M_OPT_ISSUER 6
+#define B2M_OPT_WGRAD_GROUP 8
+#define B2M_OPT_WGRAD_BSLOTS 9
 int b2m_set_option(int32_t option, int64_t value);
 
 /* ------------------------------------------------------------------------------------------------
@@ -320,6 +325,33 @@ int b2m_voxel_coords(const double* positions, int64_t n, const double* min_posit
 int b2m_nearest_point(const double* positions, const double* min_position, double voxel_size,
                       const int32_t* vox_coords, int64_t n_vox, const int32_t* nbr, const int64_t* start,
                       const int64_t* point_order, int64_t* nearest, b2m_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weak-supervision label association (next row 2)      reference: ScanNet.approx_association,
+ * models/dataloader.py:203-314 (ARKitScenes :539-621 and S3DIS :805-927 use the same steps)
+ * ---------------------------------------------------------------------------------------------- */
+/* Point-in-box occupancy. positions f64[n,3]; box_min / box_max f64[n_boxes,3] (inclusive on both sides, float64
+ * comparisons like numpy); volume f64[n_boxes]. num[i] = boxes containing point i; first[i] = the lowest such box index
+ * (-1 if none); smallest[i] = the containing box of least volume, lowest index on ties (-1 if none).
+ * reference: dataloader.py:236-242 (`is_within_bb`, `bb_occupancy.sum`, `np.argmin(bb_volume[box_ids])`). */
+int b2m_point_box_occupancy(const double* positions, int64_t n, const double* box_min, const double* box_max,
+                            const double* volume, int32_t n_boxes, int32_t* num, int32_t* first, int32_t* smallest,
+                            b2m_stream_t stream);
+/* inst[i] = -1 (no box), the instance id of the single box, or for several boxes -2 / the smallest box's instance
+ * (smallest_heuristic). reference: dataloader.py:243-259. */
+int b2m_point_instances(const int32_t* num, const int32_t* first, const int32_t* smallest, const int64_t* instance_ids,
+                        int64_t n, int32_t smallest_heuristic, int64_t* inst, b2m_stream_t stream);
+/* Per-superpoint decision pooled back to the points. seg_rank int32[n]: index of the point's superpoint in the caller's
+ * unique-segment list, -1 if it is not in the list (such points get -2). majority_vote = 0: the superpoint follows its
+ * least-covered point (lowest point index on ties): 1 box -> that instance, 0 boxes -> -1, several -> -2 or the smallest
+ * box (dataloader.py:278-312). majority_vote = 1: most common per-point value, smallest value on ties (:264-274); needs
+ * sorted_ids int64[n_boxes] (instance ids ascending) and id_rank int32[n_boxes] (rank of each box's id in that order). */
+size_t b2m_segment_association_workspace_bytes(int64_t n_segs, int32_t n_boxes, int32_t majority_vote);
+int b2m_segment_association(const int32_t* num, const int32_t* first, const int32_t* smallest, const int32_t* seg_rank,
+                            int64_t n, int64_t n_segs, const int64_t* instance_ids, const int64_t* sorted_ids,
+                            const int32_t* id_rank, int32_t n_boxes, int32_t majority_vote, int32_t smallest_heuristic,
+                            int64_t* per_seg, int64_t* per_point, void* workspace, size_t workspace_bytes,
+                            b2m_stream_t stream);
 
 #ifdef __cplusplus
 }

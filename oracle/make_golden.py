@@ -330,12 +330,64 @@ def golden_decode():
     np.savez_compressed(os.path.join(OUT, "decode_small.npz"), **out)
 
 
+def golden_label_assoc():
+    """tests/golden/label_assoc.npz: the reference's own `ScanNet.approx_association` (models/dataloader.py:203-314), called
+    unbound on seeded synthetic scenes for every mode. The module's other imports (open3d, pyviz3d, the dataset readers,
+    MinkowskiEngine) are not needed by that method and are stubbed for the import; `np.int` (removed from numpy) and the
+    old scipy.stats.mode return shape are shimmed, the method itself runs unmodified."""
+    import types
+    import scipy.stats as stats
+    from oracle import me_shim
+    from oracle.label_assoc import synthetic_case
+    me_shim.install()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    for name in ("dataprocessing.scannet", "dataprocessing.arkitscenes", "dataprocessing.s3dis"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    if "dataprocessing" not in sys.modules:
+        pkg = types.ModuleType("dataprocessing")
+        pkg.__path__ = []
+        sys.modules["dataprocessing"] = pkg
+    if not hasattr(np, "int"):
+        np.int = int
+    if "numpy.lib.type_check" not in sys.modules:       # an unused private import at the top of the reference module
+        tc = types.ModuleType("numpy.lib.type_check")
+        tc._is_type_dispatcher = None
+        sys.modules["numpy.lib.type_check"] = tc
+    orig_mode = stats.mode
+
+    def old_mode(a, axis=0, **kw):          # scipy < 1.9 returned 1-element arrays for axis=None
+        r = orig_mode(np.asarray(a), axis=axis, keepdims=False)
+        return np.atleast_1d(r.mode), np.atleast_1d(r.count)
+    stats.mode = old_mode
+    try:
+        import models.dataloader as ref_dl
+        out = {}
+        cases = [("seg", False, False, False, 0.0, 0.0), ("seg_small", False, False, True, 0.0, 0.0),
+                 ("point", True, False, False, 0.0, 0.0), ("point_small", True, False, True, 0.0, 0.0),
+                 ("vote", False, True, False, 0.0, 0.0), ("vote_small", False, True, True, 0.0, 0.0),
+                 ("seg_noise_drop", False, False, True, 0.3, 0.1)]
+        for ci, (tag, pa, mv, small, drop, noise) in enumerate(cases):
+            labels, scene, unique_segs = synthetic_case(seed=40 + ci)
+            cfg = types.SimpleNamespace(dropout_boxes=drop, noisy_boxes=noise, smallest_bb_heuristic=small)
+            fake_self = types.SimpleNamespace(cfg=cfg)
+            per_point, per_seg = ref_dl.ScanNet.approx_association(fake_self, labels, scene, pa, mv, unique_segs, {})
+            out[tag + "_per_point"] = np.asarray(per_point).astype(np.int64)
+            if per_seg is not None:
+                out[tag + "_per_seg"] = np.asarray(per_seg).astype(np.int64)
+            out[tag + "_cfg"] = np.array([40 + ci, int(pa), int(mv), int(small), drop, noise], dtype=np.float64)
+            print("label association golden", tag, "points", len(per_point), "labels", np.unique(per_point)[:8])
+        np.savez_compressed(os.path.join(OUT, "label_assoc.npz"), **out)
+    finally:
+        stats.mode = orig_mode
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("reference not mounted at %s" % REF)
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("nms", golden_nms), ("net", golden_net), ("decode", golden_decode), ("variants", golden_variants),
-                     ("decode_s3dis", golden_decode_s3dis)):
+                     ("decode_s3dis", golden_decode_s3dis), ("label_assoc", golden_label_assoc)):
         if not only or name in only:
             fn()

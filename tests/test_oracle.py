@@ -259,3 +259,24 @@ def test_decode_scene_voxel_semantics_matches_reference(golden_dir):
     assert np.array_equal(r["representatives"].numpy(), g["train_%s_reps" % name])
     ev = np.unpackbits(g["eval_%s_mask" % name], axis=1)[:, :int(g["eval_%s_mask_shape" % name][1])].astype(bool)
     assert np.array_equal(r["mask"][:, batch["vox2point"][0]].numpy(), ev)
+
+
+def test_label_association_oracle_matches_reference_golden(golden_dir):
+    """oracle/label_assoc.py against the outputs of the reference's own ScanNet.approx_association
+    (models/dataloader.py:203-314, run by oracle/make_golden.py:golden_label_assoc) for every mode: exact."""
+    import numpy as np
+    from oracle import label_assoc as la
+    g = np.load(os.path.join(golden_dir, "label_assoc.npz"))
+    tags = sorted(k[:-4] for k in g.files if k.endswith("_cfg"))
+    assert len(tags) == 7
+    for tag in tags:
+        seed, pa, mv, small, drop, noise = g[tag + "_cfg"]
+        labels, scene, unique_segs = la.synthetic_case(int(seed))
+        mn, mx, ids, vol = la.prepare_boxes(labels, scene["name"], dropout_boxes=drop, noisy_boxes=noise)
+        per_point, per_seg = la.approx_association(scene["positions"], scene["segments"], unique_segs, mn, mx, ids, vol,
+                                                   bool(pa), bool(mv), bool(small))
+        assert np.array_equal(per_point, g[tag + "_per_point"]), tag
+        if per_seg is not None:
+            assert np.array_equal(per_seg, g[tag + "_per_seg"]), tag
+        else:
+            assert tag + "_per_seg" not in g.files

@@ -28,6 +28,8 @@ ap.add_argument("--which", default="fwd,wgrad")
 ap.add_argument("--gather", default="both", help="comma list of cpasync | tma | cpasync2 (b2m_set_option B2M_OPT_GATHER_MODE); both = cpasync,tma")
 ap.add_argument("--issuer", default="lean", help="comma list of lean | general (B2M_OPT_ISSUER)")
 ap.add_argument("--wgrows", default="0", help="comma list of 0 | 64 (B2M_OPT_WGRAD_ROWS)")
+ap.add_argument("--bslots", default="0", help="comma list of dY ring depths (B2M_OPT_WGRAD_BSLOTS)")
+ap.add_argument("--wggroup", default="0", help="comma list of 0 | 2 (B2M_OPT_WGRAD_GROUP)")
 args = ap.parse_args()
 
 dev = "cuda"
@@ -67,11 +69,22 @@ def bench(fn, name):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
-    print("%-24s k%d %d->%d rows %d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (name, kvol, args.cin, args.cout, n, ms, flops / ms / 1e9))
+    print("%-30s k%d %d->%d rows %d: %.3f ms  %.1f TFLOP/s (algorithmic)" % (name, kvol, args.cin, args.cout, n, ms, flops / ms / 1e9))
 
 
 from box2mask_b200 import _lib as L  # noqa: E402
-GM = {"cpasync": 0, "tma": 1, "cpasync2": 2}
+_set = L.set_option
+
+
+def _tolerant(opt, val):      # older library variants do not know the newer options
+    try:
+        _set(opt, val)
+    except Exception:
+        pass
+
+
+L.set_option = _tolerant
+GM = {"cpasync": 0, "tma": 1, "cpasync2": 2, "cpasync_all": 3}
 for mode in (["cpasync", "tma"] if args.gather == "both" else args.gather.split(",")):
     L.set_option(L.OPT_GATHER_MODE, GM[mode])
     if "fwd" in args.which:
@@ -83,5 +96,11 @@ for mode in (["cpasync", "tma"] if args.gather == "both" else args.gather.split(
     if "wgrad" in args.which:
         for r in args.wgrows.split(","):
             L.set_option(L.OPT_WGRAD_ROWS, int(r))
-            bench(lambda: ops.conv_wgrad(x, dy, km, kvol, n), "wgrad[%s,rows%s]" % (mode, r))
+            for gsz in args.wggroup.split(","):
+                L.set_option(L.OPT_WGRAD_GROUP, int(gsz))
+                for bs in args.bslots.split(","):
+                    L.set_option(L.OPT_WGRAD_BSLOTS, int(bs))
+                    bench(lambda: ops.conv_wgrad(x, dy, km, kvol, n), "wgrad[%s,rows%s,grp%s,bs%s]" % (mode, r, gsz, bs))
+                L.set_option(L.OPT_WGRAD_BSLOTS, 0)
+            L.set_option(L.OPT_WGRAD_GROUP, 0)
         L.set_option(L.OPT_WGRAD_ROWS, 0)
