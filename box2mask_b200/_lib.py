@@ -43,10 +43,10 @@ SIGNATURES = {
     "b2m_conv_wgrad_ex": (c_int32, [_P, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int32, c_int64, _P, _P, c_size_t, _P]),
     "b2m_colstats": (c_int32, [_P, c_int64, c_int32, _P, _P]),
     "b2m_bn_forward": (c_int32, [_P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, c_float, c_float, c_int32, _P, c_int32,
-                                 _P, _P, _P, _P]),
-    "b2m_bn_backward_reduce": (c_int32, [_P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P, _P]),
+                                 _P, _P, _P, _P, _P]),
+    "b2m_bn_backward_reduce": (c_int32, [_P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P, _P, _P]),
     "b2m_bn_backward_apply": (c_int32, [_P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_int32, c_int32, _P,
-                                        _P, _P, _P, _P]),
+                                        _P, _P, _P, _P, _P]),
     "b2m_segment_mean_forward": (c_int32, [_P, _P, c_int64, c_int32, c_int64, _P, _P, _P]),
     "b2m_segment_mean_backward": (c_int32, [_P, _P, _P, c_int64, c_int32, c_int64, _P, _P]),
     "b2m_segment_max_backward": (c_int32, [_P, _P, c_int64, c_int32, c_int64, _P, _P]),

@@ -1275,8 +1275,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   if (warp == 0) B2M_TRACE(0);
 
   if (warp == kWgEpi && lane == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, a.lda ? 32 * a.nwa : 1); mbar_init(a_empty + 8 * s, 1); }
-    for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, a.ldb ? 32 * a.nwb : 1); mbar_init(b_empty + 8 * s, 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(a_full + 8 * s, a.lda ? 32 * a.nwa : a.nwa); mbar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(b_full + 8 * s, a.ldb ? 32 * a.nwb : a.nwb); mbar_init(b_empty + 8 * s, 1); }
     mbar_init(accum_bar, 1);
     mbar_fence_init();
   }
@@ -1493,6 +1493,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         rb.next();
         continue;
       }
+      if (ROWS == 128) {
+        // TMA gathers of a 128-row stage: one gather4 per lane and column block, blocks dealt to the a.nwb warps of the group
+        const int64_t p128 = g * ROWS + 4 * lane;
+        int4 idx;
+        if (a.order) {
+          idx = ld_nc_int4(a.order + p128);
+        } else {
+          idx.x = p128 < a.n_out ? (int)p128 : -1;
+          idx.y = p128 + 1 < a.n_out ? (int)p128 + 1 : -1;
+          idx.z = p128 + 2 < a.n_out ? (int)p128 + 2 : -1;
+          idx.w = p128 + 3 < a.n_out ? (int)p128 + 3 : -1;
+        }
+        int nmine = 0;
+        for (int blk = partb; blk < a.nbb; blk += a.nwb) ++nmine;
+        mbar_wait(b_empty + 8 * rb.slot, rb.phase ^ 1u, 23);
+        if (lane == 0) {
+          if (nmine) mbar_arrive_expect_tx(full, (uint32_t)(nmine * ROWS * a.wb)); else mbar_arrive(full);
+        }
+        __syncwarp();
+        for (int blk = partb; blk < a.nbb; blk += a.nwb)
+          tma_gather4(b_s + blk * (ROWS * a.wb) + lane * 4 * a.wb, &tm_dy, full, blk * 64, idx.x, idx.y, idx.z, idx.w);
+        __syncwarp();
+        rb.next();
+        continue;
+      }
       const int64_t pos0 = g * ROWS + 4 * (lane & 15);
       int4 idx;
       if (a.order) {
@@ -1661,6 +1686,46 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full + 8 * ra.slot);
+        } else if (mine && ROWS == 128) {
+          // TMA gathers of a 128-row stage: one gather4 per lane and block (32 quads of rows); the blocks of a stage are
+          // dealt to the a.nwa warps of the producer group (block b to warp b % nwa), each of which announces its own
+          // bytes on the stage barrier (count nwa), so that issuing a 32 KB stage does not take one warp ~5000 cycles
+          const uint32_t a_s = smem_base + ra.slot * kSlotA;
+          const uint32_t full = a_full + 8 * ra.slot;
+          const int k0 = k_first(q);
+          const int nslots = min(a.pk, a.kvol - k0);
+          const int64_t pos0 = g * ROWS + 4 * lane;
+          int4 idx[4];
+          int nmine = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int b = part + j * a.nwa;
+            if (b < a.nab && !(a.pk > 1 && b >= nslots)) {
+              ++nmine;
+              if (a.nbr) {
+                idx[j] = ld_nc_int4(a.nbr + (int64_t)((a.pk > 1) ? k0 + b : k0) * a.n_pitch + pos0);
+              } else {
+                idx[j].x = pos0 < a.n_out ? (int)pos0 : -1;
+                idx[j].y = pos0 + 1 < a.n_out ? (int)pos0 + 1 : -1;
+                idx[j].z = pos0 + 2 < a.n_out ? (int)pos0 + 2 : -1;
+                idx[j].w = pos0 + 3 < a.n_out ? (int)pos0 + 3 : -1;
+              }
+            }
+          }
+          mbar_wait(a_empty + 8 * ra.slot, ra.phase ^ 1u, 24);
+          if (lane == 0) {
+            if (nmine) mbar_arrive_expect_tx(full, (uint32_t)(nmine * ROWS * a.wa)); else mbar_arrive(full);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int b = part + j * a.nwa;
+            if (b < a.nab && !(a.pk > 1 && b >= nslots)) {
+              const int colx = (a.pk > 1) ? 0 : mt * 128 + b * 64;
+              tma_gather4(a_s + b * (ROWS * a.wa) + lane * 4 * a.wa, &tm_x, full, colx, idx[j].x, idx[j].y, idx[j].z, idx[j].w);
+            }
+          }
+          __syncwarp();
         } else if (mine) {
           const uint32_t a_s = smem_base + ra.slot * kSlotA;
           const uint32_t full = a_full + 8 * ra.slot;
@@ -2120,7 +2185,13 @@ static int wgrad_run(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16
   // Reduction rows per pipeline stage. The MMA issuer pays ~1000 cycles of dependent barrier / fence / commit latency per
   // stage whatever it holds, and a 64-row stage is only 4 MMAs (~270 cycles of tensor time): with cp.async gathers on
   // both operands and enough rows, a stage is 128 rows (8 MMAs) of the union of the two 64-row groups' offsets.
-  const int rows = (a.lda && a.ldb && n_out >= 64 * 1024 && g_opt_wgrows != 64) ? 128 : 64;
+  // (measured over 1.22 M rows, k27: 96->96 0.91 ms with 128-row stages / 1.03 ms with 64; 64->64, where a stage packs two
+  // offsets of which often only one occurs, 0.66 / 0.57 ms: 128 rows only for one offset per stage or cp.async operands)
+  const int rows = (n_out >= 64 * 1024 && g_opt_wgrows != 64 && (a.pk == 1 || (a.lda && a.ldb))) ? 128 : 64;
+  if (rows == 128) {            // TMA operands: the blocks of a 128-row stage are dealt to two gather warps
+    if (!a.lda && a.nab >= 2) a.nwa = 2;
+    if (!a.ldb && a.nbb >= 2) a.nwb = 2;
+  }
   const int64_t total_groups = (n_out + rows - 1) / rows;
   const int sms = num_sms();
   // Row splits. Plenty of row groups: one CTA per SM, as many row splits as fit (the kernel is throughput bound). Few row

@@ -42,7 +42,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kNormThreads)
 colreduce_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ out, const uint16_t* __restrict__ dout,
                  int64_t n, int c, const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
-                 double* __restrict__ red) {
+                 const uint8_t* __restrict__ relu_mask, double* __restrict__ red) {
   extern __shared__ float sh[];  // [rows_per_pass][c][2]
   const int G = c / 8;
   const int rpp = kNormThreads / G;  // rows per pass
@@ -61,14 +61,19 @@ colreduce_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ ou
     constexpr int U = (MODE == 0) ? 4 : 2;   // rows in flight per thread
     for (int64_t r0 = (int64_t)blockIdx.x * rpp + rl; r0 < n; r0 += U * rstep) {
       uint4 xr[U], gr[U], orr[U];
+      unsigned mk[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t r = r0 + u * rstep;
+        mk[u] = 0xFFu;
         if (r < n) {
           xr[u] = __ldg(reinterpret_cast<const uint4*>(x + r * c) + g);
           if (MODE == 1) {
             gr[u] = __ldg(reinterpret_cast<const uint4*>(dout + r * c) + g);
-            if (relu) orr[u] = __ldg(reinterpret_cast<const uint4*>(out + r * c) + g);
+            if (relu) {
+              if (relu_mask) mk[u] = __ldg(relu_mask + r * G + g);      // one byte instead of 16: bit i = (out[8 g + i] > 0)
+              else orr[u] = __ldg(reinterpret_cast<const uint4*>(out + r * c) + g);
+            }
           }
         }
       }
@@ -84,7 +89,10 @@ colreduce_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ ou
         } else {
           float gv[8];
           bf16x8_to_float(gr[u], gv);
-          if (relu) {
+          if (relu && relu_mask) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (!((mk[u] >> i) & 1u)) gv[i] = 0.f;
+          } else if (relu) {
             float ov[8];
             bf16x8_to_float(orr[u], ov);
 #pragma unroll
@@ -119,7 +127,8 @@ __global__ void __launch_bounds__(kNormThreads)
 bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int64_t n_stat, int c, const double* __restrict__ sums,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
                 float momentum, float eps, int training, const uint16_t* __restrict__ residual, int relu,
-                uint16_t* __restrict__ out, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+                uint16_t* __restrict__ out, float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                uint8_t* __restrict__ relu_mask) {
   const int G = c / 8;
   const int rpp = kNormThreads / G;
   const int g = threadIdx.x % G, rl = threadIdx.x / G;
@@ -184,6 +193,12 @@ bn_apply_kernel(const uint16_t* __restrict__ x, int64_t n, int64_t n_stat, int c
         for (int i = 0; i < 8; ++i) o[i] += rv[i];
       }
       if (relu) {
+        if (relu_mask) {             // the gate of the backward pass as one byte per 8 columns (it re-read `out` before)
+          unsigned m = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m |= (o[i] > 0.f ? 1u : 0u) << i;
+          relu_mask[r * G + g] = (uint8_t)m;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
       }
@@ -198,7 +213,7 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__
                     const float* __restrict__ gamma, const double* __restrict__ red,
                     const double* __restrict__ red_local, const double* __restrict__ n_stat_dev, int relu, int training,
                     uint16_t* __restrict__ dx, uint16_t* __restrict__ dres, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta) {
+                    float* __restrict__ dbeta, const uint8_t* __restrict__ relu_mask) {
   const int G = c / 8;
   // The affine gradients come from THIS rank's reduction (red_local): torch's SyncBatchNorm keeps grad_weight /
   // grad_bias local and lets the gradient all-reduce average them like every other parameter; only dx needs the
@@ -235,13 +250,18 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__
   const int64_t rstep = (int64_t)gridDim.x * rpp;
   for (int64_t r0 = (int64_t)blockIdx.x * rpp + rl; r0 < n; r0 += U * rstep) {
     uint4 xr[U], gr[U], orr[U];
+    unsigned mk[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t r = r0 + u * rstep;
+      mk[u] = 0xFFu;
       if (r < n) {
         xr[u] = __ldg(reinterpret_cast<const uint4*>(x + r * c) + g);
         gr[u] = __ldg(reinterpret_cast<const uint4*>(dout + r * c) + g);
-        if (relu) orr[u] = __ldg(reinterpret_cast<const uint4*>(out + r * c) + g);
+        if (relu) {
+          if (relu_mask) mk[u] = __ldg(relu_mask + r * G + g);
+          else orr[u] = __ldg(reinterpret_cast<const uint4*>(out + r * c) + g);
+        }
       }
     }
 #pragma unroll
@@ -251,7 +271,10 @@ bn_bwd_apply_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__
       float xv[8], gv[8], o[8];
       bf16x8_to_float(xr[u], xv);
       bf16x8_to_float(gr[u], gv);
-      if (relu) {
+      if (relu && relu_mask) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (!((mk[u] >> i) & 1u)) gv[i] = 0.f;
+      } else if (relu) {
         float ov[8];
         bf16x8_to_float(orr[u], ov);
 #pragma unroll
@@ -301,7 +324,7 @@ extern "C" int b2m_colstats(const uint16_t* x, int64_t n, int32_t c, double* sum
   const int rpp = kNormThreads / (c / 8);
   const size_t sh = (size_t)rpp * c * 2 * sizeof(float);
   colreduce_kernel<0><<<reduce_grid(n, c), kNormThreads, sh, (cudaStream_t)stream>>>(x, nullptr, nullptr, n, c, nullptr,
-                                                                                    nullptr, 0, sums);
+                                                                                    nullptr, 0, nullptr, sums);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }
@@ -309,7 +332,7 @@ extern "C" int b2m_colstats(const uint16_t* x, int64_t n, int32_t c, double* sum
 extern "C" int b2m_bn_forward(const uint16_t* x, int64_t n, int64_t n_stat, int32_t c, const double* sums, const float* gamma,
                               const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                               int32_t training, const uint16_t* residual, int32_t relu, uint16_t* out, float* save_mean,
-                              float* save_invstd, b2m_stream_t stream) {
+                              float* save_invstd, uint8_t* relu_mask, b2m_stream_t stream) {
   if (!x || !gamma || !beta || !out || !save_mean || !save_invstd || n < 0) return B2M_ERR_INVALID_ARGUMENT;
   if (training && !sums) return B2M_ERR_INVALID_ARGUMENT;
   if (!training && (!running_mean || !running_var)) return B2M_ERR_INVALID_ARGUMENT;
@@ -320,22 +343,22 @@ extern "C" int b2m_bn_forward(const uint16_t* x, int64_t n, int64_t n_stat, int3
   // are not written; in training mode the normalisation uses the batch sums, so there is no read/write hazard.
   bn_apply_kernel<<<apply_grid(n, c), kNormThreads, 0, st>>>(x, n, n_stat, c, sums, gamma, beta, running_mean, running_var,
                                                             momentum, eps, training, residual, relu, out, save_mean,
-                                                            save_invstd);
+                                                            save_invstd, relu ? relu_mask : nullptr);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }
 
 extern "C" int b2m_bn_backward_reduce(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n, int32_t c,
                                       const float* save_mean, const float* save_invstd, int32_t relu, double* red,
-                                      b2m_stream_t stream) {
+                                      const uint8_t* relu_mask, b2m_stream_t stream) {
   if (!x || !dout || !save_mean || !save_invstd || !red || n < 0) return B2M_ERR_INVALID_ARGUMENT;
-  if (relu && !out) return B2M_ERR_INVALID_ARGUMENT;
+  if (relu && !out && !relu_mask) return B2M_ERR_INVALID_ARGUMENT;
   if (!norm_shape_ok(c)) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n == 0) return B2M_OK;
   const int rpp = kNormThreads / (c / 8);
   const size_t sh = (size_t)rpp * c * 2 * sizeof(float);
   colreduce_kernel<1><<<reduce_grid(n, c), kNormThreads, sh, (cudaStream_t)stream>>>(x, out, dout, n, c, save_mean,
-                                                                                    save_invstd, relu, red);
+                                                                                    save_invstd, relu, relu_mask, red);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }
@@ -345,14 +368,15 @@ extern "C" int b2m_bn_backward_apply(const uint16_t* x, const uint16_t* out, con
                                      const float* save_mean, const float* save_invstd, const float* gamma,
                                      const double* red, const double* red_local, const double* n_stat_dev,
                                      int32_t relu, int32_t training, uint16_t* dx,
-                                     uint16_t* dresidual, float* dgamma, float* dbeta, b2m_stream_t stream) {
+                                     uint16_t* dresidual, float* dgamma, float* dbeta, const uint8_t* relu_mask,
+                                     b2m_stream_t stream) {
   if (!x || !dout || !save_mean || !save_invstd || !gamma || !red || !dx || n < 0) return B2M_ERR_INVALID_ARGUMENT;
-  if (relu && !out) return B2M_ERR_INVALID_ARGUMENT;
+  if (relu && !out && !relu_mask) return B2M_ERR_INVALID_ARGUMENT;
   if (!norm_shape_ok(c)) return B2M_ERR_UNSUPPORTED_SHAPE;
   if (n == 0) return B2M_OK;
   bn_bwd_apply_kernel<<<apply_grid(n, c), kNormThreads, 0, (cudaStream_t)stream>>>(
       x, out, dout, n, n_stat, c, save_mean, save_invstd, gamma, red, red_local, n_stat_dev, relu, training, dx, dresidual,
-      dgamma, dbeta);
+      dgamma, dbeta, relu_mask);
   B2M_CHECK_LAUNCH();
   return B2M_OK;
 }

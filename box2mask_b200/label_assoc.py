@@ -56,7 +56,8 @@ def approx_association(labels, scene, cfg, point_association, majority_vote, uni
     pos = torch.as_tensor(np.ascontiguousarray(scene["positions"], dtype=np.float64), device=dev)
     n, b = pos.shape[0], len(ids)
     t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)     # noqa: E731
-    num, first, smallest = point_box_occupancy(pos, t(mn, torch.float64), t(mx, torch.float64), t(vol, torch.float64))
+    mn_d, mx_d, vol_d = t(mn, torch.float64), t(mx, torch.float64), t(vol, torch.float64)
+    num, first, smallest = point_box_occupancy(pos, mn_d, mx_d, vol_d)
     ids_d = t(ids, torch.int64)
     if point_association:
         inst = torch.empty(n, dtype=torch.int64, device=dev)
@@ -76,7 +77,8 @@ def approx_association(labels, scene, cfg, point_association, majority_vote, uni
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     per_seg = torch.empty(s, dtype=torch.int64, device=dev)
     per_point = torch.empty(n, dtype=torch.int64, device=dev)
+    sorted_ids_d, id_rank_d = t(ids[order], torch.int64), t(id_rank, torch.int32)     # (kept alive across the launch)
     check(lib.b2m_segment_association(ptr(num), ptr(first), ptr(smallest), ptr(seg_rank), n, s, ptr(ids_d),
-                                      ptr(t(ids[order], torch.int64)), ptr(t(id_rank, torch.int32)), b, 1 if majority_vote else 0,
+                                      ptr(sorted_ids_d), ptr(id_rank_d), b, 1 if majority_vote else 0,
                                       heur, ptr(per_seg), ptr(per_point), ptr(ws), ws_bytes, stream_ptr()), "segment_association")
     return per_point.cpu().numpy(), per_seg.cpu().numpy()

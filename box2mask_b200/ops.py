@@ -400,31 +400,35 @@ def colstats(x):
 
 
 def bn_forward(x, sums, gamma, beta, running_mean, running_var, momentum, eps, training, residual=None, relu=False,
-               n_stat=None):
+               n_stat=None, want_mask=False):
+    """want_mask (with relu): also returns the ReLU gate as uint8[n, c/8] bits for bn_backward(relu_mask=...)."""
     lib = _lib_or_raise()
     _cuda(x, torch.bfloat16, "x")
     n, c = x.shape
     out = torch.empty_like(x)
     save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
     save_invstd = torch.empty(c, dtype=torch.float32, device=x.device)
+    mask = torch.empty((n, c // 8), dtype=torch.uint8, device=x.device) if (want_mask and relu) else None
     _run("bn_forward", 1, lambda: check(lib.b2m_bn_forward(
         ptr(x), n, n if n_stat is None else int(n_stat), c, ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean),
         ptr(running_var), float(momentum), float(eps), int(bool(training)), ptr(residual), int(bool(relu)), ptr(out),
-        ptr(save_mean), ptr(save_invstd), stream_ptr()), "bn_forward"),
+        ptr(save_mean), ptr(save_invstd), ptr(mask), stream_ptr()), "bn_forward"),
         nbytes=2 * x.numel() * (3 if residual is not None else 2))
+    if want_mask:
+        return out, save_mean, save_invstd, mask
     return out, save_mean, save_invstd
 
 
 def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, want_dresidual, n_stat=None,
-                reduce_hook=None, n_stat_dev=None, dgamma=None, dbeta=None):
+                reduce_hook=None, n_stat_dev=None, dgamma=None, dbeta=None, relu_mask=None):
     """n_stat_dev: optional f64[1] device tensor with the global row count (SyncBN, no host round trip).
     reduce_hook(red) -> all-reduced copy of red: only dx uses it; dgamma / dbeta stay this rank's own sums."""
     lib = _lib_or_raise()
     n, c = x.shape
     red = ZeroArena.take(2 * c, x.device)
     _run("bn_backward_reduce", 1, lambda: check(lib.b2m_bn_backward_reduce(
-        ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd), int(bool(relu)), ptr(red), stream_ptr()),
-        "bn_backward_reduce"), nbytes=2 * x.numel() * (3 if relu else 2))
+        ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd), int(bool(relu)), ptr(red), ptr(relu_mask),
+        stream_ptr()), "bn_backward_reduce"), nbytes=2 * x.numel() * (3 if (relu and relu_mask is None) else 2))
     red_local = None
     if reduce_hook is not None:
         red_local = red
@@ -438,7 +442,8 @@ def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, wan
     _run("bn_backward_apply", 1, lambda: check(lib.b2m_bn_backward_apply(
         ptr(x), ptr(out), ptr(dout), n, n if n_stat is None else int(n_stat), c, ptr(save_mean), ptr(save_invstd),
         ptr(gamma), ptr(red), ptr(red_local), ptr(n_stat_dev), int(bool(relu)), int(bool(training)), ptr(dx), ptr(dres),
-        ptr(dgamma), ptr(dbeta), stream_ptr()), "bn_backward_apply"), nbytes=2 * x.numel() * ((3 if relu else 2) + (2 if want_dresidual else 1)))
+        ptr(dgamma), ptr(dbeta), ptr(relu_mask), stream_ptr()), "bn_backward_apply"),
+        nbytes=2 * x.numel() * ((3 if (relu and relu_mask is None) else 2) + (2 if want_dresidual else 1)))
     return dx, dres, dgamma, dbeta
 
 

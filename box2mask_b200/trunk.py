@@ -301,9 +301,9 @@ class TrunkExecutor:
                     raise ValueError("Expected more than 1 value per channel when training")
             momentum = b.momentum if b.momentum is not None else 1.0 / float(b.num_batches_tracked)
             res = T[st.res] if st.res is not None else None
-            out, mean, invstd = ops.bn_forward(y, sums, b.weight.detach(), b.bias.detach(), b.running_mean, b.running_var,
-                                               momentum, b.eps, True, res, st.relu, n_stat)
-            saved.append((x, y, out, mean, invstd, count, n_stat))
+            out, mean, invstd, mask = ops.bn_forward(y, sums, b.weight.detach(), b.bias.detach(), b.running_mean,
+                                                     b.running_var, momentum, b.eps, True, res, st.relu, n_stat, want_mask=True)
+            saved.append((x, y, mask, mean, invstd, count, n_stat))
             T[st.dst] = out
         return T[prog.out_id], saved
 
@@ -356,7 +356,7 @@ class TrunkExecutor:
                 self._acc(G, st.b, g[:, st.ca:].contiguous())
                 continue
             si -= 1
-            x, y, out, mean, invstd, count, n_stat = saved[si]
+            x, y, mask, mean, invstd, count, n_stat = saved[si]
             saved[si] = None
             conv, b = st.conv, st.bn.bn
             km_f, km_b, n_out = maps.get(st.map)
@@ -368,9 +368,10 @@ class TrunkExecutor:
                     tot = red.clone()
                     torch.distributed.all_reduce(tot, group=group)
                     return tot
-            dx_bn, dres, _, _ = ops.bn_backward(y, out, g_out, mean, invstd, b.weight.detach(), st.relu, True,
+            # the ReLU gate comes from the 1-bit mask the forward pass wrote, not from re-reading the unit's output
+            dx_bn, dres, _, _ = ops.bn_backward(y, None, g_out, mean, invstd, b.weight.detach(), st.relu, True,
                                                 st.res is not None, n_stat, hook, count,
-                                                dgamma=grads.view(b.weight), dbeta=grads.view(b.bias))
+                                                dgamma=grads.view(b.weight), dbeta=grads.view(b.bias), relu_mask=mask)
             if st.res is not None:
                 self._acc(G, st.res, dres)
             kview = grads.view(conv.kernel)

@@ -223,17 +223,20 @@ int b2m_colstats(const uint16_t* x, int64_t n, int32_t c, double* sums, b2m_stre
  * n_stat <= 0: read it from sums[2c], where the SyncBN all-reduce carries the global row count).
  * training: mean/var from sums (biased var for normalisation), running stats updated with momentum
  * (unbiased var), save_mean/save_invstd float[c] written. eval (training==0): uses running stats.
- * out = act( (x-mean)*invstd*gamma + beta (+ residual) ), act = ReLU if relu else identity. */
+ * out = act( (x-mean)*invstd*gamma + beta (+ residual) ), act = ReLU if relu else identity.
+ * relu_mask (optional, uint8[n, c/8], written when relu): bit i of byte (row, g) = (out[row, 8 g + i] > 0), the gate
+ * the backward passes need - 1/16 of the bytes of `out`, which they re-read otherwise. */
 int b2m_bn_forward(const uint16_t* x, int64_t n, int64_t n_stat, int32_t c, const double* sums, const float* gamma,
                    const float* beta, float* running_mean, float* running_var, float momentum,
                    float eps, int32_t training, const uint16_t* residual, int32_t relu, uint16_t* out,
-                   float* save_mean, float* save_invstd, b2m_stream_t stream);
-/* pass 1: red double[2c] += (sum_g, sum_g*xhat), g = dout masked by (out > 0) when relu.
+                   float* save_mean, float* save_invstd, uint8_t* relu_mask, b2m_stream_t stream);
+/* pass 1: red double[2c] += (sum_g, sum_g*xhat), g = dout masked by (out > 0) when relu (read from relu_mask when
+ *         given - `out` may then be NULL - else from `out`).
  * pass 2: dx = gamma*invstd*(g - sum_g/n - xhat*sum_gxhat/n); dresidual = g (optional);
  *         dgamma = sum_gxhat, dbeta = sum_g. In eval mode dx = gamma*invstd*g. */
 int b2m_bn_backward_reduce(const uint16_t* x, const uint16_t* out, const uint16_t* dout, int64_t n,
                            int32_t c, const float* save_mean, const float* save_invstd, int32_t relu,
-                           double* red, b2m_stream_t stream);
+                           double* red, const uint8_t* relu_mask, b2m_stream_t stream);
 /* SyncBatchNorm (models/model.py:25): `red` is the all-reduced (global) reduction that enters dx; `red_local`
  * (NULL = red) is this rank's own reduction, which becomes dgamma / dbeta (torch's SyncBatchNorm keeps the affine
  * gradients local; the gradient all-reduce averages them like any other parameter); `n_stat_dev` (NULL = use
@@ -243,7 +246,7 @@ int b2m_bn_backward_apply(const uint16_t* x, const uint16_t* out, const uint16_t
                           const float* gamma, const double* red, const double* red_local,
                           const double* n_stat_dev, int32_t relu, int32_t training,
                           uint16_t* dx, uint16_t* dresidual, float* dgamma, float* dbeta,
-                          b2m_stream_t stream);
+                          const uint8_t* relu_mask, b2m_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Superpoint pooling                reference: models/detection_net.py:345-352 (re-keyed

@@ -604,3 +604,22 @@ def test_sparse_tensor_validates_and_deduplicates():
     bad[3, 2] = 40000
     with pytest.raises(RuntimeError):
         ME.SparseTensor(feats, torch.from_numpy(bad), device=DEV)
+
+
+@pytest.mark.parametrize("n,c,res", [(5000, 96, True), (70001, 256, False), (3, 32, True)])
+def test_bn_relu_mask_equals_output_gate(n, c, res):
+    """The 1-bit ReLU gate written by bn_forward (uint8[n, c/8]) against the gate re-read from `out`: the backward
+    passes must give identical bits either way (dx, dresidual, dgamma, dbeta)."""
+    torch.manual_seed(n + c)
+    x = torch.randn(n, c, device=DEV).to(torch.bfloat16)
+    r = torch.randn(n, c, device=DEV).to(torch.bfloat16) if res else None
+    gamma, beta = torch.rand(c, device=DEV) + 0.5, torch.randn(c, device=DEV) * 0.1
+    out, sm, si, mask = ops.bn_forward(x, ops.colstats(x), gamma, beta, torch.zeros(c, device=DEV), torch.ones(c, device=DEV),
+                                       0.1, 1e-5, True, r, True, want_mask=True)
+    bits = (mask[:, :, None] >> torch.arange(8, device=DEV, dtype=torch.uint8)) & 1
+    assert torch.equal(bits.reshape(n, c).bool(), out > 0)
+    dout = torch.randn(n, c, device=DEV).to(torch.bfloat16)
+    a = ops.bn_backward(x, out, dout, sm, si, gamma, True, True, res)
+    b = ops.bn_backward(x, None, dout, sm, si, gamma, True, True, res, relu_mask=mask)
+    for u, v in zip(a, b):
+        assert (u is None and v is None) or torch.equal(u, v)

@@ -133,7 +133,7 @@ def fake_ops(monkeypatch):
         return torch.cat([x.double().sum(0), (x.double() ** 2).sum(0)])
 
     def bn_forward(x, sums, gamma, beta, running_mean, running_var, momentum, eps, training, residual=None, relu=False,
-                   n_stat=None):
+                   n_stat=None, want_mask=False):
         n = x.shape[0] if n_stat is None else n_stat
         c = x.shape[1]
         if training:
@@ -149,14 +149,16 @@ def fake_ops(monkeypatch):
             out = out + residual.double()
         if relu:
             out = torch.relu(out)
+        if want_mask:           # the stand-in keeps the gate as a boolean matrix (the kernels pack it into bits)
+            return out.float(), mean.float(), invstd.float(), (out > 0) if relu else None
         return out.float(), mean.float(), invstd.float()
 
     def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, want_dresidual, n_stat=None,
-                    reduce_hook=None, n_stat_dev=None, dgamma=None, dbeta=None):
+                    reduce_hook=None, n_stat_dev=None, dgamma=None, dbeta=None, relu_mask=None):
         n = x.shape[0] if n_stat is None else n_stat
         g = dout.double()
         if relu:
-            g = g * (out > 0)
+            g = g * (relu_mask if relu_mask is not None else (out > 0))
         xhat = (x.double() - save_mean.double()) * save_invstd.double()
         sg, sgx = g.sum(0), (g * xhat).sum(0)
         scale = gamma.double() * save_invstd.double()

@@ -62,3 +62,41 @@ if args.dump:
     for r in rows[:45]:
         print("%-22s %-44s %8.3f ms  %s" % (r["kind"], r["tag"], r["ms"],
               ("%.1f TF/s" % r["tflops"]) if r["tflops"] else (("%.0f GB/s" % r["gbs"]) if r["gbs"] else "")))
+
+# ---- phase timeline of one step (CUDA events on the main stream): where the 34 ms go ----
+import box2mask_b200 as _pkg  # noqa: E402
+ME = _pkg.install_as_minkowski_engine()
+
+
+def phases():
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+    names = ["zero_grad", "coordinate maps + weight packing", "trunk + heads forward", "losses", "backward", "optimizer"]
+    net = model.net
+    torch.cuda.synchronize()
+    ev[0].record()
+    opt.zero_grad(set_to_none=True)
+    ev[1].record()
+    sin = ME.SparseTensor(batch["vox_features"], batch["vox_coords"], device=dev)
+    ME.prepack_conv_weights(net)
+    sin.coordinate_manager.prepare(*net.coordinate_plan())
+    ev[2].record()
+    b2 = dict(batch)
+    b2["_coordinate_manager"] = sin.coordinate_manager
+    # compute_loss_detection = forward + losses; split it with an event recorded by a forward hook on the network
+    h = net.register_forward_hook(lambda *_: ev[3].record())
+    losses, _ = model.compute_loss_detection(b2, epoch=0)
+    h.remove()
+    ev[4].record()
+    losses["optimization_loss"].backward()
+    ev[5].record()
+    opt.step()
+    ev[6].record()
+    torch.cuda.synchronize()
+    return names, [ev[i].elapsed_time(ev[i + 1]) for i in range(6)]
+
+
+for _ in range(2):
+    names, ms = phases()
+print("phase timeline of one training step (ms, CUDA events on the main stream; total %.2f):" % sum(ms))
+for nm, t in zip(names, ms):
+    print("  %-36s %7.2f" % (nm, t))
