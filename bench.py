@@ -458,8 +458,16 @@ def main():
     # milliseconds, which once landed inside the first timed region and stalled kernel submission (72 instead of 44 ms
     # per step); by the time the warm-up is over it only polls.
     sampler = ClockSampler(local) if rank == 0 else None
-    for i in range(max(args.warmup, len(dev_batches))):
+    # Untimed warm-up: the W steps asked for, and at least three passes over the distinct batches - the caching allocator
+    # keeps growing for a few steps (weight gradients run on a side stream, so blocks are handed back late), and a
+    # region that still contains that growth measured 37-54 ms/step next to 33-34 ms ones.
+    n_warm = max(args.warmup, 3 * len(dev_batches))
+    for i in range(n_warm):
         train_step(model, opt, dev_batches[i % len(dev_batches)])
+    for i in range(len(host_batches)):          # the end-to-end path allocates its own device copies: warm that too
+        hb = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_batches[i].items()}
+        float(train_step(model, opt, hb).item())
+    args.warmup = n_warm + len(host_batches)    # reported as done
     # Each region times exactly `steps` steps between barrier + synchronize; the MEDIAN of REGIONS regions is reported
     # and every region's figure is kept in config.timing.
     REGIONS = max(1, args.regions)
