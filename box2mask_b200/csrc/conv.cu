@@ -1175,9 +1175,20 @@ conv_finalize_kernel(const float* __restrict__ part, int nslices, int64_t n, int
 // wgrad kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgEpi = 4;                                       // warps 0-3: epilogue (TMEM lane quarters)
+#ifdef B2M_WG_REMAP
+// experiment: 20 warps, no gather warp on the issuer's scheduler sub-partition (warps 8, 12, 16 idle), like the forward kernel
+constexpr int kWgAProd = 8;
+constexpr int kWgBProd = 4;
+constexpr int kWgThreads = 640;
+#define B2M_WG_SW128 ldgsts_rows_sw128
+#define B2M_WG_SW64 ldgsts_rows_sw64
+#else
 constexpr int kWgAProd = 10;                                    // gather warps for the X operand
 constexpr int kWgBProd = 4;                                     // gather warps for the dY operand
 constexpr int kWgThreads = (kWgEpi + 1 + kWgBProd + kWgAProd) * 32;   // 608
+#define B2M_WG_SW128 ldgsts_rows_sw128_rolled
+#define B2M_WG_SW64 ldgsts_rows_sw64_rolled
+#endif
 constexpr int kWgRows = 64;
 constexpr int kWgASlotBytes = 128 * kWgRows * 2;                // 16 KB: M = 128 x 64 reduction rows
 
@@ -1288,6 +1299,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
   if (warp == 0) B2M_TRACE(1);
+#ifdef B2M_WG_REMAP
+  const int gidx = (warp >= 5 && (warp & 3)) ? fwd_gather_index(warp) : -1;     // 0 .. 11 over the warps off sub-partition 0
+  const bool is_bprod = gidx >= 0 && gidx < kWgBProd, is_aprod = gidx >= kWgBProd;
+  const int bidx = gidx, aidx = gidx - kWgBProd;
+#else
+  const bool is_bprod = warp > kWgEpi && warp <= kWgEpi + kWgBProd, is_aprod = warp > kWgEpi + kWgBProd;
+  const int bidx = warp - (kWgEpi + 1), aidx = warp - (kWgEpi + 1 + kWgBProd);
+#endif
 
   // offsets present in reduction group g (ROWS rows = ROWS / 64 groups of the sorted map's masks)
   const int64_t ngroups64 = (a.n_out + 63) / 64;
@@ -1422,12 +1441,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     }
     B2M_TRACE(21);
     __syncwarp();
-  } else if (warp <= kWgEpi + kWgBProd) {
+  } else if (is_bprod) {
     // ================= dY producers (B operand, MN-major): gather rows order[g*64 ..]; stage s by warp s % kWgBProd ====
     // cp.async mode with several column blocks: a stage is gathered by a GROUP of a.nwb warps, warp `partb` of the
     // group taking the blocks b % nwb == partb, so that the ~8 instructions per 512 bytes a warp spends do not
     // serialise a whole 32 KB stage on one warp (the stage barrier counts 32 arrivals per warp of the group)
-    const int pb = (warp - (kWgEpi + 1)) / a.nwb, partb = (warp - (kWgEpi + 1)) % a.nwb;
+    const int pb = bidx / a.nwb, partb = bidx % a.nwb;
     const int npb = min(kWgBProd / a.nwb, SB);   // <= SB, see conv_fwd_kernel
     Ring rb;
     rb.init(SB);
@@ -1484,9 +1503,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         for (int blk = partb; blk < a.nbb; blk += a.nwb) {
           if (a.wb == 128) {
             const int left = (a.c_out - blk * 64) >> 3;
-            ldgsts_rows_sw128_rolled<ROWS>(b_s + blk * (ROWS * 128), dyb + blk * 128, row_bytes, R, lane, left < 8 ? left : 8);
+            B2M_WG_SW128<ROWS>(b_s + blk * (ROWS * 128), dyb + blk * 128, row_bytes, R, lane, left < 8 ? left : 8);
           } else {
-            ldgsts_rows_sw64_rolled<ROWS>(b_s + blk * (ROWS * 64), dyb + blk * 64, row_bytes, R, lane);
+            B2M_WG_SW64<ROWS>(b_s + blk * (ROWS * 64), dyb + blk * 64, row_bytes, R, lane);
           }
         }
         cp_async_mbar_arrive_noinc(full);
@@ -1540,9 +1559,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (g == g_begin) B2M_TRACE(11);
       rb.next();
     }
-  } else {
+  } else if (is_aprod) {
     // ================= gather warps (A operand = X rows, MN-major): A stage s is produced by warp s % kWgAProd ====
-    const int p = (warp - (kWgEpi + 1 + kWgBProd)) / a.nwa, part = (warp - (kWgEpi + 1 + kWgBProd)) % a.nwa;   // group, warp in it
+    const int p = aidx / a.nwa, part = aidx % a.nwa;   // group, warp in it
     const int np = min(kWgAProd / a.nwa, SA);   // <= SA, see conv_fwd_kernel
     Ring ra;
     ra.init(SA);
@@ -1621,10 +1640,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             if (a.wa == 128) {
               const int col0 = (a.pk > 1) ? 0 : mt * 128 + b * 64;         // first channel of the block
               const int left = (a.c_in - col0) >> 3;
-              ldgsts_rows_sw128_rolled<ROWS>(a_s + b * (ROWS * 128), xb + col0 * 2, row_bytes, R[b], lane,
+              B2M_WG_SW128<ROWS>(a_s + b * (ROWS * 128), xb + col0 * 2, row_bytes, R[b], lane,
                                          left < 8 ? (left > 0 ? left : 0) : 8);
             } else {
-              ldgsts_rows_sw64_rolled<ROWS>(a_s + b * (ROWS * 64), xb, row_bytes, R[b], lane);
+              B2M_WG_SW64<ROWS>(a_s + b * (ROWS * 64), xb, row_bytes, R[b], lane);
             }
           }
         }
