@@ -57,6 +57,25 @@ def make_scenes(n, seed, scale):
     return [make_scene(1000 * seed + i, scale=scale) for i in range(n)]
 
 
+
+def balanced_scenes(n, seed, scale, world, dev):
+    """Per-rank scenes. On several GPUs every step waits for the rank with the most voxels (the ranks draw different
+    scenes: 144 k - 164 k voxels each), so each rank generates n + 2 candidates and keeps the n whose total voxel count is
+    closest to n x the all-rank mean (what a size-bucketing sampler does for a real data set; no scene is altered and
+    the single-GPU workload is unchanged)."""
+    if world <= 1:
+        return make_scenes(n, seed=seed, scale=scale)
+    import itertools
+    import torch.distributed as dist
+    pool = make_scenes(n + 2, seed=seed, scale=scale)
+    counts = [len(sc["vox_coords"]) for sc in pool]
+    mean = torch.tensor([float(np.mean(counts))], device=dev)
+    dist.all_reduce(mean)
+    target = n * float(mean.item()) / world
+    best = min(itertools.combinations(range(len(pool)), n), key=lambda c: abs(sum(counts[i] for i in c) - target))
+    return [pool[i] for i in best]
+
+
 def jitter_batch(scenes, rng):
     """A fresh batch from cached scenes: random scene order and a random integer translation per scene
     (different coordinates every step, so no coordinate map could be reused)."""
@@ -203,7 +222,7 @@ def run_eval(args):
     from box2mask_b200 import ops
     ops._lib.load()
     args.warmup = max(args.warmup, 3)
-    scenes = make_scenes(args.scenes, seed=10 + rank, scale=args.scale)
+    scenes = balanced_scenes(args.scenes, 10 + rank, args.scale, world, dev)
     rng = np.random.default_rng(rank)
     model, _, cfg = build_model(dev, multigpu=False)
     model.eval()
@@ -397,7 +416,7 @@ def main():
     ops._lib.load()      # fail loudly if the CUDA library is missing
     ops._lib.set_option(ops._lib.OPT_GATHER_MODE, 1 if args.gather_mode == "tma" else 0)
 
-    scenes = make_scenes(args.scenes, seed=10 + rank, scale=args.scale)
+    scenes = balanced_scenes(args.scenes, 10 + rank, args.scale, world, dev)
     rng = np.random.default_rng(rank)
     model, opt, cfg = build_model(dev, multigpu=world > 1, grad_sync=args.grad_sync,
                                   trunk_executor=not args.no_trunk_executor, overlap_wgrad=not args.no_wgrad_overlap)
@@ -533,6 +552,8 @@ def main():
                                "hash + 16 kernel maps + fwd + box-vote losses + bwd + Adam" % (args.scenes, voxels),
                    "scenes_per_gpu": args.scenes, "voxels_per_gpu": voxels, "parallelism": "dp%d" % world,
                    "sync_bn": bool(args.sync_bn and world > 1),
+                   "scene_sampling": ("size-balanced: each rank keeps the %d of %d generated scenes whose total voxel count is "
+                                      "closest to the all-rank mean" % (args.scenes, args.scenes + 2)) if world > 1 else "fixed seeds",
                    "grad_sync": (args.grad_sync if world > 1 else None),
                    "timing": "median of %d regions of %d steps each, ms/step of every region: value %s, e2e %s" % (
                        REGIONS, args.steps, ["%.2f" % m for m in ms_all], ["%.2f" % m for m in ms_e2e_all]),

@@ -199,6 +199,7 @@ class KernelMap:
 
 
 SORT_BLOCK_ROWS = 32768
+SORT_MIN_ROWS = 8192          # maps with fewer output rows keep their row order (masks are still produced)
 
 
 def pad_table(nbr):
@@ -218,6 +219,10 @@ def sort_kernel_map(nbr, n_out=None, block_rows=None, keep_raw=False):
     kvol, pitch = nbr.shape
     if pitch != map_pitch(n_out):
         raise _lib.B2MError("neighbour table must have the padded pitch %d, got %d" % (map_pitch(n_out), pitch))
+    if block_rows is None and n_out < SORT_MIN_ROWS:
+        # a level of a few thousand rows is a few dozen MMA tiles that each contain (almost) every offset whatever the
+        # order: the five launches of a sort buy nothing there (12 of the 22 maps of a ScanNet-shape step)
+        block_rows = 0
     if block_rows is None:
         # blocks of >= 32768 rows (their features stay L2-resident while a block is swept); doubled while that lets the
         # (block, mask) sort key fit 32 bits (one radix pass fewer, half the key bytes)
