@@ -104,7 +104,7 @@ def ptr(t):
     """Device (or host) pointer of a torch tensor as a void*; None -> NULL."""
     if t is None:
         return None
-    return c_void_p(t.data_ptr())
+    return t.data_ptr()          # ctypes converts an int for a c_void_p parameter; no wrapper object per argument
 
 
 OPT_MAX_CTAS, OPT_CHUNKS_PER_STAGE, OPT_SPLIT_OFFSETS, OPT_GATHER_MODE, OPT_WGRAD_ROWS, OPT_ISSUER, OPT_WGRAD_GROUP, OPT_WGRAD_BSLOTS = 1, 2, 3, 4, 5, 6, 8, 9
@@ -116,5 +116,16 @@ def set_option(option, value):
 
 def stream_ptr(device=None):
     """Current CUDA stream of `device` (default: the current device) as a void*."""
+    # the raw handle straight from torch's C layer: `torch.cuda.current_stream()` builds a Stream object and resolves
+    # the device through several Python layers (3 400 calls = 5 ms of host time per training step)
     import torch
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    C = torch._C
+    if device is None:
+        idx = C._cuda_getDevice()
+    elif isinstance(device, int):
+        idx = device
+    else:
+        idx = torch.device(device).index
+        if idx is None:
+            idx = C._cuda_getDevice()
+    return C._cuda_getCurrentRawStream(idx)

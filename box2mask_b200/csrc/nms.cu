@@ -67,28 +67,29 @@ __global__ void nms_mask_kernel(const float* __restrict__ boxes, const int32_t* 
 // l, l + 32, ...), so a cluster costs one ballot to find the first remaining box, one coalesced read of its mask row
 // and an and-not: no block barriers, no shared memory; the dependent chain per cluster is one L2 read (~0.5 us).
 // Outputs the representatives as sorted positions; box indices and memberships follow in nms_assign_kernel.
-constexpr int kScanWords = 64;      // words per lane: up to 32 * 64 * 32 = 65536 boxes
+// Instantiated per words-per-lane count so that the loops over a lane's words are exactly as long as the box count needs
+// (M <= 2048: two words, ~20 instructions + one L2 read per cluster).
+constexpr int kScanWords = 64;      // most words per lane (template parameter WPL = ceil(words / 32) rounded up): up to 32 * 64 * 32 = 65536 boxes
+template <int WPL>
 __global__ void __launch_bounds__(32)
 nms_scan_kernel(const uint32_t* __restrict__ mask, int m, int words, int32_t* __restrict__ n_clusters,
                 int32_t* __restrict__ rep_pos) {
   const int lane = threadIdx.x;
-  const int wpl = (words + 31) / 32;                       // words per lane actually used
-  uint32_t rem[kScanWords];
+  uint32_t rem[WPL];
 #pragma unroll
-  for (int i = 0; i < kScanWords; ++i) {
+  for (int i = 0; i < WPL; ++i) {
     const int w = i * 32 + lane;
     const int lo = w * 32;
-    rem[i] = (i < wpl && w < words) ? ((m - lo >= 32) ? 0xFFFFFFFFu : ((m > lo) ? ((1u << (m - lo)) - 1u) : 0u)) : 0u;
+    rem[i] = (w < words) ? ((m - lo >= 32) ? 0xFFFFFFFFu : ((m > lo) ? ((1u << (m - lo)) - 1u) : 0u)) : 0u;
   }
   // first remaining position at or after nothing: min over lanes of the first set bit
   auto first_remaining = [&]() -> int {
     int best = 0x7FFFFFFF;
 #pragma unroll
-    for (int i = 0; i < kScanWords; ++i) {
-      if (i < wpl && rem[i] && best == 0x7FFFFFFF) best = (i * 32 + lane) * 32 + __ffs(rem[i]) - 1;
+    for (int i = 0; i < WPL; ++i) {
+      if (rem[i] && best == 0x7FFFFFFF) best = (i * 32 + lane) * 32 + __ffs(rem[i]) - 1;
     }
-    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-    return best;
+    return __reduce_min_sync(0xffffffffu, best);
   };
   int nc = 0;
   int p = first_remaining();
@@ -97,11 +98,9 @@ nms_scan_kernel(const uint32_t* __restrict__ mask, int m, int words, int32_t* __
     ++nc;
     const uint32_t* row = mask + (int64_t)p * words;
 #pragma unroll
-    for (int i = 0; i < kScanWords; ++i) {
-      if (i < wpl) {
-        const int w = i * 32 + lane;
-        if (w < words) rem[i] &= ~__ldg(row + w);          // members = remaining & row (incl. p itself: diagonal bit)
-      }
+    for (int i = 0; i < WPL; ++i) {
+      const int w = i * 32 + lane;
+      if (w < words) rem[i] &= ~__ldg(row + w);            // members = remaining & row (incl. p itself: diagonal bit)
     }
     p = first_remaining();
   }
@@ -289,7 +288,13 @@ extern "C" int b2m_aabb_nms(const float* boxes, int64_t m, float cluster_th, int
   B2M_CHECK_LAUNCH();
   int32_t* rep_pos = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + ((size_t)m * 4 + 255) / 256 * 256 +
                                                 ((size_t)m * words * 4 + 255) / 256 * 256);
-  nms_scan_kernel<<<1, 32, 0, st>>>(mask, mi, words, n_clusters, rep_pos);
+  const int wpl = (words + 31) / 32;
+  if (wpl <= 1) nms_scan_kernel<1><<<1, 32, 0, st>>>(mask, mi, words, n_clusters, rep_pos);
+  else if (wpl <= 2) nms_scan_kernel<2><<<1, 32, 0, st>>>(mask, mi, words, n_clusters, rep_pos);
+  else if (wpl <= 4) nms_scan_kernel<4><<<1, 32, 0, st>>>(mask, mi, words, n_clusters, rep_pos);
+  else if (wpl <= 8) nms_scan_kernel<8><<<1, 32, 0, st>>>(mask, mi, words, n_clusters, rep_pos);
+  else if (wpl <= 16) nms_scan_kernel<16><<<1, 32, 0, st>>>(mask, mi, words, n_clusters, rep_pos);
+  else nms_scan_kernel<kScanWords><<<1, 32, 0, st>>>(mask, mi, words, n_clusters, rep_pos);
   B2M_CHECK_LAUNCH();
   nms_assign_kernel<<<cdiv(mi, 128), 128, 0, st>>>(mask, order, mi, words, n_clusters, rep_pos, representatives, cluster_of);
   B2M_CHECK_LAUNCH();

@@ -38,6 +38,8 @@ def _run(kind, n_kernels, call, flops=None, nbytes=None, tag=""):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f = flops() if callable(flops) else flops
     b = nbytes() if callable(nbytes) else nbytes
+    if callable(tag):
+        tag = tag()
     e0.record()
     r = call()
     e1.record()
@@ -78,7 +80,7 @@ class ZeroArena:
 def _cuda(t, dtype=None, name="tensor"):
     if not t.is_cuda:
         raise _lib.B2MError("%s must be a CUDA tensor (no CPU fallback in the product path)" % name)
-    if t.device.index != torch.cuda.current_device():
+    if t.device.index != torch._C._cuda_getDevice():
         # kernels launch on the current device's stream; a tensor of another device would be dereferenced there
         raise _lib.B2MError("%s lives on cuda:%d but the current device is cuda:%d - call torch.cuda.set_device "
                             "(or use `with torch.cuda.device(...)`) first" % (name, t.device.index, torch.cuda.current_device()))
@@ -327,7 +329,8 @@ class Workspace:
 
     @classmethod
     def get(cls, nbytes, device):
-        key = (torch.device(device), torch.cuda.current_stream(device).cuda_stream)
+        device = torch.device(device)
+        key = (device, stream_ptr(device))
         buf = cls._buf.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(int(nbytes), 1 << 22), dtype=torch.uint8, device=device)
@@ -359,7 +362,7 @@ def conv_forward(x, kmap, packed_w, kvol, n_out, c_n, colsum=None, scale=None, s
         int(out_fp32_cols) if out_fp32_cols is not None else 0, ptr(ws), ws_bytes, stream_ptr()), "conv_forward"),
         flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] * c_n,
         nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] + 2.0 * n_out * c_n,
-        tag="k%d %d->%d n_in=%d n_out=%d" % (kvol, x.shape[1], c_n, x.shape[0], n_out))
+        tag=lambda: "k%d %d->%d n_in=%d n_out=%d" % (kvol, x.shape[1], c_n, x.shape[0], n_out))
     return y if y32 is None else y32
 
 
@@ -388,7 +391,7 @@ def conv_wgrad(x, dy, kmap, kvol, n_out, out=None):
         stream_ptr()), "conv_wgrad"),
         flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * c_in * c_out,
         nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * (c_in + c_out),
-        tag="k%d %d->%d n_in=%d n_out=%d" % (kvol, c_in, c_out, x.shape[0], n_out))
+        tag=lambda: "k%d %d->%d n_in=%d n_out=%d" % (kvol, c_in, c_out, x.shape[0], n_out))
     return dw
 
 

@@ -21,6 +21,7 @@ ap.add_argument("--scenes", type=int, default=8)
 ap.add_argument("--scale", type=float, default=0.84)
 ap.add_argument("--dump", default=None)
 ap.add_argument("--warm", type=int, default=2)
+ap.add_argument("--cprofile", type=int, default=0, help="cProfile this many steps (host side) and print the top entries")
 args = ap.parse_args()
 
 dev = "cuda:0"
@@ -40,11 +41,23 @@ for _ in range(3):   # host enqueue time vs end-to-end time of a step (how far t
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     print("step: host returned after %.1f ms, GPU done after %.1f ms" % ((t1 - t0) * 1e3, (t2 - t0) * 1e3))
+if args.cprofile:
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(args.cprofile):
+        bench.train_step(model, opt, batch)
+    pr.disable()
+    torch.cuda.synchronize()
+    for key in ("tottime", "cumulative"):
+        print("---- host profile of %d steps, sorted by %s ----" % (args.cprofile, key))
+        pstats.Stats(pr).sort_stats(key).print_stats(70)
 if args.dump:
     ops.Profile.reset()
     ops.Profile.enabled = True
 torch.cuda.profiler.start()
-bench.train_step(model, opt, batch)
+(bench.instrumented_step if args.dump else bench.train_step)(model, opt, batch)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 if args.dump:
