@@ -91,7 +91,7 @@ def jitter_batch(scenes, rng):
 
 
 TENSOR_KEYS = ("vox_coords", "vox_features", "pooling_ids", "input_location", "gt_bb_offsets", "gt_bb_bounds",
-               "gt_semantics", "fg_instances")
+               "gt_semantics", "fg_instances", "fg_index")
 
 
 class ClockSampler:

@@ -60,6 +60,8 @@ SIGNATURES = {
     "b2m_mask_nms_workspace_bytes": (c_size_t, [c_int64]),
     "b2m_mask_nms": (c_int32, [_P, c_int64, c_int64, c_float, _P, _P, _P, c_size_t, _P]),
     "b2m_unpack_masks": (c_int32, [_P, c_int64, c_int64, c_int64, _P, _P]),
+    "b2m_copy_columns": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int32, _P]),
+    "b2m_run_commands": (c_int32, [_P, c_int64, _P, _P, _P]),
     "b2m_point_box_occupancy": (c_int32, [_P, c_int64, _P, _P, _P, c_int32, _P, _P, _P, _P]),
     "b2m_point_instances": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P, _P]),
     "b2m_segment_association_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),

@@ -1116,6 +1116,7 @@ conv_finalize_kernel(const float* __restrict__ part, int nslices, int64_t n, int
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll 4
       for (int z = 0; z < nslices; ++z) {
         const float4* p = reinterpret_cast<const float4*>(part + ((int64_t)z * n + r) * c + g * 8);
         const float4 a0 = __ldg(p), a1 = __ldg(p + 1);
@@ -1804,17 +1805,38 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   }
 }
 
-// dw[i] = sum over row splits s (ascending: deterministic) of part[s][i]; one float4 per thread
+// dw[i] = sum over row splits of part[s][i] in a FIXED order (deterministic). SL lanes per float4: lane j adds the splits
+// j, j + SL, ... (ascending), then the lanes' sums are added in ascending j. SL = 8 for small dW with many splits (a
+// 32 x 32 x 27 kernel split 140 ways is a chain of 140 dependent-latency loads per thread with SL = 1).
+template <int SL>
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float4* __restrict__ part, int nsplits, int64_t n4, float4* __restrict__ dw) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  float4 acc = __ldg(part + i);
-  for (int s2 = 1; s2 < nsplits; ++s2) {
-    const float4 v = __ldg(part + (int64_t)s2 * n4 + i);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  constexpr int E = 256 / SL;
+  __shared__ float4 sh[SL > 1 ? SL : 1][SL > 1 ? E : 1];
+  const int e = threadIdx.x % E, j = threadIdx.x / E;
+  const int64_t i = (int64_t)blockIdx.x * E + e;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+#pragma unroll 4
+    for (int s2 = j; s2 < nsplits; s2 += SL) {
+      const float4 v = __ldg(part + (int64_t)s2 * n4 + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   }
-  dw[i] = acc;
+  if (SL > 1) {
+    sh[j][e] = acc;
+    __syncthreads();
+    if (j == 0 && i < n4) {
+#pragma unroll
+      for (int jj = 1; jj < SL; ++jj) {
+        const float4 v = sh[jj][e];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      dw[i] = acc;
+    }
+  } else if (i < n4) {
+    dw[i] = acc;
+  }
 }
 
 static int pow2_cols(int need) {
@@ -2279,8 +2301,12 @@ static int wgrad_run(const uint16_t* x, int64_t n_in, int32_t c_in, const uint16
   B2M_CHECK_LAUNCH();
   if (a.part) {
     const int64_t n4 = (int64_t)(dw_bytes / 16);
-    wgrad_reduce_kernel<<<cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(a.part), (int)splits, n4,
-                                                                      reinterpret_cast<float4*>(dw));
+    if (splits >= 16 && n4 <= (int64_t)256 * 2 * sms)
+      wgrad_reduce_kernel<8><<<cdiv(n4, 32), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(a.part),
+                                                                          (int)splits, n4, reinterpret_cast<float4*>(dw));
+    else
+      wgrad_reduce_kernel<1><<<cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(a.part),
+                                                                           (int)splits, n4, reinterpret_cast<float4*>(dw));
     B2M_CHECK_LAUNCH();
   }
   return B2M_OK;

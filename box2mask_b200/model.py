@@ -93,10 +93,19 @@ class Model:
         losses = {"optimization_loss": 0}
         use_fg = cfg.loss_on_fg_instances or cfg.bb_supervision
         fg = batch["fg_instances"].to(dev)
+        # rows of the foreground superpoints as an index list: a boolean-mask gather reads its size back from the device
+        # for every tensor it is applied to (ten per step). The list comes with the batch ("fg_index", from the collate
+        # function), is computed on the host while the mask still lives there, or costs one read-back.
+        fg_index = batch.get("fg_index") if isinstance(batch, dict) else None
+        if fg_index is None and use_fg:
+            src = batch["fg_instances"]
+            fg_index = torch.nonzero(src.reshape(-1)).reshape(-1)
+        if fg_index is not None:
+            fg_index = fg_index.to(dev)
 
         def sel(t):
             t = t.to(dev)
-            return t[fg] if use_fg else t
+            return t.index_select(0, fg_index) if use_fg else t
 
         offset_loss_per_pred = None
         if cfg.mlp_offsets in cfg.network_heads:
@@ -139,7 +148,7 @@ class Model:
         if cfg.mlp_center_scores in cfg.network_heads and epoch >= cfg.mlp_center_scores_start_epoch:
             cs = pred[cfg.mlp_center_scores].reshape(-1)
             if cfg.loss_on_fg_instances:
-                cs = cs[fg]
+                cs = cs.index_select(0, fg_index) if fg_index is not None else cs[fg]
             cs_loss = torch.mean(torch.abs(cs - offset_loss_per_pred.detach()))
             losses["optimization_loss"] = losses["optimization_loss"] + cfg.loss_weight_center_scores * cs_loss
             losses["center_score_loss"] = cs_loss.detach()

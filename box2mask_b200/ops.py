@@ -1,5 +1,8 @@
 """Thin functional wrappers over the C-ABI (include/b2m.h). torch is used only for device memory and
 streams; every computation below happens in libb2m.so. All tensors must live on a CUDA device."""
+import ctypes
+import struct
+
 import torch
 
 from . import _lib
@@ -47,6 +50,111 @@ def _run(kind, n_kernels, call, flops=None, nbytes=None, tag=""):
     return r
 
 
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class LaunchList:
+    """Recorder for b2m_run_commands (include/b2m.h, "Launch lists"): while one is current, conv_forward / conv_wgrad /
+    bn_forward / bn_backward / copy_columns append their C-ABI arguments to a command buffer instead of calling the
+    library, and flush() issues the whole pass in one call - ~5 us of launch cost per kernel instead of ~50 us of
+    Python, ctypes and stream bookkeeping per call (a training step has ~540 of them).
+
+    Rules that keep deferred launches correct with torch's caching allocator:
+      * commands run in recording order on the main stream, so a block that Python frees and torch.empty hands out
+        again during recording is reused in stream order, exactly as with immediate launches - as long as no *eager*
+        torch kernel runs while commands are pending: call flush() before any torch op on tensors the list touches;
+      * tensors read by side-stream commands are kept alive until flush() and then marked with record_stream(side)
+        (the allocator must not reuse them for main-stream work before the side stream is done)."""
+    current = None
+    _S = struct.Struct("<ii22q2d")
+    _PAD = (0,) * 22
+    OP_CONV_FORWARD, OP_CONV_WGRAD, OP_BN_FORWARD, OP_BN_BACKWARD_REDUCE, OP_BN_BACKWARD_APPLY = 1, 2, 3, 4, 5
+    OP_COPY_COLUMNS, OP_RECORD, OP_WAIT = 6, 7, 8
+
+    FLUSH_EVERY = 8      # commands per b2m_run_commands call: the GPU starts on a pass while the host still records it
+
+    def __init__(self, device, side_stream=None, capacity=64):
+        self.device = torch.device(device)
+        self.side = side_stream
+        self.cap = capacity
+        self.buf = bytearray(self._S.size * capacity)
+        self.cbuf = (ctypes.c_char * len(self.buf)).from_buffer(self.buf)
+        self.n = 0
+        self.kinds = []
+        self.stream = 0          # stream selector of the commands being recorded (1 = side)
+        self.keep_side = []      # tensors read or written by side-stream commands
+        self.next_event = 0
+        self.flushes = 0
+
+    @classmethod
+    def begin(cls, device, side_stream=None):
+        """A new current list, or None where launches stay immediate (CPU stand-ins, the instrumented pass)."""
+        device = torch.device(device)
+        if device.type != "cuda" or Profile.enabled or cls.current is not None:
+            return None
+        cls.current = cls(device, side_stream)
+        return cls.current
+
+    def end(self):
+        try:
+            self.flush()
+        finally:
+            if LaunchList.current is self:
+                LaunchList.current = None
+
+    def add(self, kind, op, args, f0=0.0, f1=0.0):
+        if self.n >= self.FLUSH_EVERY:
+            self.flush()
+        self._S.pack_into(self.buf, self.n * self._S.size, op, self.stream, *args, *self._PAD[len(args):], f0, f1)
+        self.kinds.append(kind)
+        self.n += 1
+
+    def target_stream(self):
+        """the torch stream the commands being recorded will run on (None = the current stream)"""
+        return self.side if self.stream else None
+
+    def record_event(self, stream=0):
+        slot = self.next_event
+        self.next_event += 1
+        cur, self.stream = self.stream, stream
+        self.add("record", self.OP_RECORD, (slot,))
+        self.stream = cur
+        return slot
+
+    def wait_event(self, slot, stream):
+        cur, self.stream = self.stream, stream
+        self.add("wait", self.OP_WAIT, (slot,))
+        self.stream = cur
+
+    def join_side(self):
+        """the main stream waits for everything recorded on the side stream so far"""
+        self.wait_event(self.record_event(stream=1), stream=0)
+
+    def flush(self):
+        n, kinds = self.n, self.kinds
+        self.n, self.kinds = 0, []
+        try:
+            if n:
+                self.flushes += 1
+                failed = ctypes.c_int64(-1)
+                side = self.side.cuda_stream if self.side is not None else None
+                code = _lib.load().b2m_run_commands(self.cbuf, n, stream_ptr(self.device), side, ctypes.byref(failed))
+                if code != 0:
+                    i = failed.value
+                    check(code, "launch list command %d of %d (%s)" % (i, n, kinds[i] if 0 <= i < n else "?"))
+        finally:
+            keep, self.keep_side = self.keep_side, []
+            if self.side is not None:
+                for t in keep:
+                    t.record_stream(self.side)
+
+    @classmethod
+    def flush_current(cls):
+        if cls.current is not None:
+            cls.current.flush()
+
+
 class ZeroArena:
     """Zeroed fp64 scratch for the per-layer statistics (conv epilogue column sums, BatchNorm backward reductions):
     slices of one pre-zeroed buffer per device instead of one fill kernel per layer (243 per training step).
@@ -64,6 +172,7 @@ class ZeroArena:
             st = [torch.zeros(cls.SIZE, dtype=torch.float64, device=device), 0, 0]
             cls._state[device] = st
         elif st[1] + n_al > cls.SIZE:
+            LaunchList.flush_current()      # pending commands still read their slices
             st[0].zero_()
             st[1] = 0
             st[2] += 1
@@ -328,12 +437,22 @@ class Workspace:
     _buf = {}
 
     @classmethod
-    def get(cls, nbytes, device):
+    def get(cls, nbytes, device, stream=None):
+        """stream: the torch stream the consuming launches run on (default: the current stream). The buffer is allocated
+        under that stream: a block the caching allocator recycles from another stream's pool may still be in use by
+        launches of that stream."""
         device = torch.device(device)
-        key = (device, stream_ptr(device))
+        key = (device, stream_ptr(device) if stream is None else stream.cuda_stream)
         buf = cls._buf.get(key)
         if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(int(nbytes), 1 << 22), dtype=torch.uint8, device=device)
+            if buf is not None and LaunchList.current is not None:
+                LaunchList.current.keep_side.append(buf)      # pending commands may still use the old buffer
+            size = max(int(nbytes), 1 << 22)
+            if stream is None:
+                buf = torch.empty(size, dtype=torch.uint8, device=device)
+            else:
+                with torch.cuda.stream(stream):
+                    buf = torch.empty(size, dtype=torch.uint8, device=device)
             cls._buf[key] = buf
         return buf
 
@@ -355,6 +474,15 @@ def conv_forward(x, kmap, packed_w, kvol, n_out, c_n, colsum=None, scale=None, s
     else:
         y32 = torch.empty((n_out, int(out_fp32_cols)), dtype=torch.float32, device=x.device)
     ws_bytes = lib.b2m_conv_forward_workspace_bytes(n_out, x.shape[1], kvol, c_n)
+    ll = LaunchList.current
+    if ll is not None:
+        ws = Workspace.get(ws_bytes, x.device, ll.target_stream()) if ws_bytes else None
+        Profile.launches += 2 if ws_bytes else 1
+        ll.add("conv_forward", ll.OP_CONV_FORWARD, (
+            x.data_ptr(), x.shape[0], x.shape[1], _p(nbr), _p(order), _p(gmask), kvol, n_out, packed_w.data_ptr(), c_n,
+            _p(y), _p(colsum), _p(scale), _p(shift), _p(residual), 1 if relu else 0, _p(y32),
+            int(out_fp32_cols) if out_fp32_cols is not None else 0, _p(ws), ws_bytes))
+        return y if y32 is None else y32
     ws = Workspace.get(ws_bytes, x.device) if ws_bytes else None
     _run("conv_forward", 2 if ws_bytes else 1, lambda: check(lib.b2m_conv_forward_ex(
         ptr(x), x.shape[0], x.shape[1], ptr(nbr), ptr(order), ptr(gmask), kvol, n_out, ptr(packed_w), c_n, ptr(y),
@@ -385,6 +513,16 @@ def conv_wgrad(x, dy, kmap, kvol, n_out, out=None):
     # partial-sum workspace for the row splits (deterministic reduction instead of atomics); allocated on the current
     # stream by the caching allocator
     ws_bytes = int(lib.b2m_conv_wgrad_workspace_bytes(n_out, c_in, c_out, kvol))
+    ll = LaunchList.current
+    if ll is not None:
+        # launches of one stream run one after the other: they share that stream's workspace
+        ws = Workspace.get(ws_bytes, x.device, ll.target_stream()) if ws_bytes else None
+        Profile.launches += 2 if ws is not None else 1
+        ll.add("conv_wgrad", ll.OP_CONV_WGRAD, (x.data_ptr(), x.shape[0], c_in, dy.data_ptr(), c_out, _p(nbr), _p(order),
+                                                 _p(gmask), kvol, n_out, dw.data_ptr(), _p(ws), ws_bytes))
+        if ll.stream:
+            ll.keep_side += (x, dy, dw)
+        return dw
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     _run("conv_wgrad", 2 if ws is not None else 1, lambda: check(lib.b2m_conv_wgrad_ex(
         ptr(x), x.shape[0], c_in, ptr(dy), c_out, ptr(nbr), ptr(order), ptr(gmask), kvol, n_out, ptr(dw), ptr(ws), ws_bytes,
@@ -393,6 +531,26 @@ def conv_wgrad(x, dy, kmap, kvol, n_out, out=None):
         nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * (c_in + c_out),
         tag=lambda: "k%d %d->%d n_in=%d n_out=%d" % (kvol, c_in, c_out, x.shape[0], n_out))
     return dw
+
+
+def copy_columns(src, src_col, width, dst, dst_col):
+    """dst[:, dst_col:dst_col+width] = src[:, src_col:src_col+width] for bf16 [n, c] tensors (column offsets and width
+    multiples of 8): ME.cat of the decoder and the split of its gradient, without torch's cat / strided-copy kernels."""
+    lib = _lib_or_raise()
+    n = src.shape[0]
+    if dst.shape[0] != n or src.dtype != torch.bfloat16 or dst.dtype != torch.bfloat16:
+        raise _lib.B2MError("copy_columns: bf16 tensors with the same number of rows expected")
+    if src_col + width > src.shape[1] or dst_col + width > dst.shape[1] or not (src.is_contiguous() and dst.is_contiguous()):
+        raise _lib.B2MError("copy_columns: column range outside the tensors, or tensors not contiguous")
+    args = (src.data_ptr() + 2 * src_col, src.shape[1], dst.data_ptr() + 2 * dst_col, dst.shape[1], n, width)
+    ll = LaunchList.current
+    if ll is not None:
+        Profile.launches += 1
+        ll.add("copy_columns", ll.OP_COPY_COLUMNS, args)
+    else:
+        _run("copy_columns", 1, lambda: check(lib.b2m_copy_columns(*args, stream_ptr()), "copy_columns"),
+             nbytes=4.0 * n * width)
+    return dst
 
 
 # ---------------------------------------------------------------------------------------------
@@ -417,6 +575,14 @@ def bn_forward(x, sums, gamma, beta, running_mean, running_var, momentum, eps, t
     save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
     save_invstd = torch.empty(c, dtype=torch.float32, device=x.device)
     mask = torch.empty((n, c // 8), dtype=torch.uint8, device=x.device) if (want_mask and relu) else None
+    ll = LaunchList.current
+    if ll is not None:
+        Profile.launches += 1
+        ll.add("bn_forward", ll.OP_BN_FORWARD, (
+            x.data_ptr(), n, n if n_stat is None else int(n_stat), c, _p(sums), gamma.data_ptr(), beta.data_ptr(),
+            _p(running_mean), _p(running_var), 1 if training else 0, _p(residual), 1 if relu else 0, out.data_ptr(),
+            save_mean.data_ptr(), save_invstd.data_ptr(), _p(mask)), float(momentum), float(eps))
+        return (out, save_mean, save_invstd, mask) if want_mask else (out, save_mean, save_invstd)
     _run("bn_forward", 1, lambda: check(lib.b2m_bn_forward(
         ptr(x), n, n if n_stat is None else int(n_stat), c, ptr(sums), ptr(gamma), ptr(beta), ptr(running_mean),
         ptr(running_var), float(momentum), float(eps), int(bool(training)), ptr(residual), int(bool(relu)), ptr(out),
@@ -434,6 +600,29 @@ def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, wan
     lib = _lib_or_raise()
     n, c = x.shape
     red = ZeroArena.take(2 * c, x.device)
+    ll = LaunchList.current
+    if ll is not None:
+        Profile.launches += 2
+        rl, tr = 1 if relu else 0, 1 if training else 0
+        ll.add("bn_backward_reduce", ll.OP_BN_BACKWARD_REDUCE, (
+            x.data_ptr(), _p(out), dout.data_ptr(), n, c, save_mean.data_ptr(), save_invstd.data_ptr(), rl, red.data_ptr(),
+            _p(relu_mask)))
+        red_local = None
+        if reduce_hook is not None:
+            ll.flush()                      # the hook is a collective on the reduction
+            red_local = red
+            red = reduce_hook(red)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if want_dresidual else None
+        if dgamma is None:
+            dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+        if dbeta is None:
+            dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+        ll.add("bn_backward_apply", ll.OP_BN_BACKWARD_APPLY, (
+            x.data_ptr(), _p(out), dout.data_ptr(), n, n if n_stat is None else int(n_stat), c, save_mean.data_ptr(),
+            save_invstd.data_ptr(), gamma.data_ptr(), red.data_ptr(), _p(red_local), _p(n_stat_dev), rl, tr, dx.data_ptr(),
+            _p(dres), dgamma.data_ptr(), dbeta.data_ptr(), _p(relu_mask)))
+        return dx, dres, dgamma, dbeta
     _run("bn_backward_reduce", 1, lambda: check(lib.b2m_bn_backward_reduce(
         ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd), int(bool(relu)), ptr(red), ptr(relu_mask),
         stream_ptr()), "bn_backward_reduce"), nbytes=2 * x.numel() * (3 if (relu and relu_mask is None) else 2))

@@ -128,6 +128,9 @@ def collate(scenes):
         "seg2vox": [torch.from_numpy(s["vox_segments"]).long() for s in scenes],
         "scene": [{"name": "synthetic_%d" % b} for b in range(len(scenes))],
     }
+    # optional key (not in the reference's collate_fn): the rows of the foreground superpoints, so that the losses gather
+    # them without reading the size of a boolean-mask selection back from the device (Model.compute_loss_detection)
+    ret["fg_index"] = torch.nonzero(ret["fg_instances"]).reshape(-1)
     return ret
 
 

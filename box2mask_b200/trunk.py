@@ -244,18 +244,36 @@ class TrunkExecutor:
         prog, maps = self.program, _Maps(cm)
         T = {0: self._input(feats, prog.units[0])}
         last_use = self._last_use()
-        for i, st in enumerate(prog.steps):
-            if isinstance(st, Cat):
-                T[st.dst] = torch.cat([T[st.a], T[st.b]], 1)
-            else:
-                km_f, _, n_out = maps.get(st.map)
-                scale, shift = _fold_bn(st.bn)
-                res = T[st.res] if st.res is not None else None
-                T[st.dst] = ops.conv_forward(T[st.src], km_f, _packed(st.conv)[0], st.conv.kernel_volume, n_out,
-                                             st.conv.out_channels, None, scale, shift, res, st.relu)
-            for tid in last_use.get(i, ()):
-                T.pop(tid, None)
+        folded = [_fold_bn(st.bn) for st in prog.units]      # (eager torch ops when stale: before any launch is recorded)
+        ll = ops.LaunchList.begin(T[0].device)               # the whole pass is issued by one C call (ops.LaunchList)
+        try:
+            ui = 0
+            for i, st in enumerate(prog.steps):
+                if isinstance(st, Cat):
+                    T[st.dst] = self._cat(ll, T[st.a], T[st.b])
+                else:
+                    km_f, _, n_out = maps.get(st.map)
+                    scale, shift = folded[ui]
+                    ui += 1
+                    res = T[st.res] if st.res is not None else None
+                    T[st.dst] = ops.conv_forward(T[st.src], km_f, _packed(st.conv)[0], st.conv.kernel_volume, n_out,
+                                                 st.conv.out_channels, None, scale, shift, res, st.relu)
+                for tid in last_use.get(i, ()):
+                    T.pop(tid, None)
+        finally:
+            if ll is not None:
+                ll.end()
         return T[prog.out_id]
+
+    @staticmethod
+    def _cat(ll, a, b):
+        """channel concatenation: two column copies recorded in the launch list, torch.cat otherwise"""
+        if ll is None:
+            return torch.cat([a, b], 1)
+        out = torch.empty((a.shape[0], a.shape[1] + b.shape[1]), dtype=a.dtype, device=a.device)
+        ops.copy_columns(a, 0, a.shape[1], out, 0)
+        ops.copy_columns(b, 0, b.shape[1], out, a.shape[1])
+        return out
 
     def _last_use(self):
         lu = self.__dict__.get("_lu")
@@ -277,9 +295,18 @@ class TrunkExecutor:
         T = {0: self._input(feats, prog.units[0])}
         saved = []
         torch._foreach_add_([u.bn.bn.num_batches_tracked for u in prog.units], 1)     # one launch for all 81 counters
+        ll = ops.LaunchList.begin(T[0].device)
+        try:
+            self._forward_train_steps(prog, maps, T, saved, ll)
+        finally:
+            if ll is not None:
+                ll.end()
+        return T[prog.out_id], saved
+
+    def _forward_train_steps(self, prog, maps, T, saved, ll):
         for st in prog.steps:
             if isinstance(st, Cat):
-                T[st.dst] = torch.cat([T[st.a], T[st.b]], 1)
+                T[st.dst] = self._cat(ll, T[st.a], T[st.b])
                 continue
             conv, b = st.conv, st.bn.bn
             km_f, _, n_out = maps.get(st.map)
@@ -291,6 +318,8 @@ class TrunkExecutor:
             y = ops.conv_forward(x, km_f, _packed(conv)[0], conv.kernel_volume, n_out, c_out, colsum[:2 * c_out])
             n_stat, count = n_out, None
             if group is not None:
+                if ll is not None:
+                    ll.flush()                  # the statistics are all-reduced by torch: the convolution must be enqueued
                 sums = colsum.clone()
                 sums[-1] = float(n_out)
                 torch.distributed.all_reduce(sums, group=group)
@@ -305,7 +334,6 @@ class TrunkExecutor:
                                                      b.running_var, momentum, b.eps, True, res, st.relu, n_stat, want_mask=True)
             saved.append((x, y, mask, mean, invstd, count, n_stat))
             T[st.dst] = out
-        return T[prog.out_id], saved
 
     DEFER_LEVEL = 1
 
@@ -316,29 +344,37 @@ class TrunkExecutor:
             self._wgrad_stream = torch.cuda.Stream(device=device)
         return self._wgrad_stream
 
-    def _wgrad(self, side, ready, x, dx_bn, km_f, conv, n_out, kview):
-        """dW of one unit into its slice of the flat gradient buffer, on `side` (after event `ready`) when given."""
-        def run():
-            if kview.shape[-2] == x.shape[1]:
-                ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out, out=kview)
-            else:     # the 6-channel input padded to 8: wgrad over the padded width, the real rows are copied out
-                dw = ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out)
-                kview.copy_(dw[:, :kview.shape[-2], :].reshape(kview.shape))
-        if side is None:
-            run()
+    def _wgrad(self, ll, side, ready, x, dx_bn, km_f, conv, n_out, kview):
+        """dW of one unit into its slice of the flat gradient buffer, on `side` (after event `ready`) when given.
+        With a launch list `ready` is an event slot of the list, otherwise a torch event."""
+        padded = kview.shape[-2] != x.shape[1]
+        if padded:
+            # the 6-channel input padded to 8: wgrad over the padded width, the real rows are copied out by torch - on
+            # the main stream (it is the last unit of the pass, nothing is left to overlap with)
+            dw = ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out)
+            if ll is not None:
+                ll.flush()
+            kview.copy_(dw[:, :kview.shape[-2], :].reshape(kview.shape))
             return
-        side.wait_event(ready)
-        with torch.cuda.stream(side):
-            run()
-        x.record_stream(side)
-        dx_bn.record_stream(side)
+        if side is None:
+            ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out, out=kview)
+        elif ll is not None:
+            ll.wait_event(ready, stream=1)
+            ll.stream = 1
+            ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out, out=kview)     # keeps x / dx_bn alive until the flush
+            ll.stream = 0
+        else:
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                ops.conv_wgrad(x, dx_bn, km_f, conv.kernel_volume, n_out, out=kview)
+            x.record_stream(side)
+            dx_bn.record_stream(side)
 
     # ---------------------------------------------------------------------------------------------
     def backward(self, saved, cm, dout):
-        prog, maps, grads = self.program, _Maps(cm), self.grads
+        prog, grads = self.program, self.grads
         side = self._side_stream(dout.device)
         main = torch.cuda.current_stream(dout.device) if side is not None else None
-        deferred, deep_seen = [], False
         # gradients are WRITTEN into the flat buffer; anything already accumulated on the parameters (a caller that does
         # not zero the gradients between backward passes) is carried over and added back at the end
         carry = None
@@ -347,13 +383,44 @@ class TrunkExecutor:
             for p, v in zip(grads.params, torch.split(carry, [q.numel() for q in grads.params])):
                 if p.grad is not None:
                     v.view_as(p).copy_(p.grad)
+        ll = ops.LaunchList.begin(dout.device, side)      # the pass is issued by one C call per bucket (ops.LaunchList)
+        try:
+            self._backward_steps(prog, _Maps(cm), grads, saved, dout, ll, side, main)
+        finally:
+            if ll is not None:
+                ll.end()
+        if carry is not None:
+            grads.flat.add_(carry)
+        for p, v in zip(grads.params, grads.views):
+            p.grad = v
+        if self.on_done is not None:
+            self.on_done()
+
+    def _backward_steps(self, prog, maps, grads, saved, dout, ll, side, main):
+        deferred, deep_seen = [], False
         G = {prog.out_id: dout}
         si = len(saved)
+
+        def join():
+            if side is None:
+                return
+            if ll is not None:
+                ll.join_side()
+            else:
+                main.wait_stream(side)
+
         for st in reversed(prog.steps):
             if isinstance(st, Cat):
                 g = G.pop(st.dst)
-                self._acc(G, st.a, g[:, :st.ca].contiguous())
-                self._acc(G, st.b, g[:, st.ca:].contiguous())
+                if ll is not None:
+                    ga = torch.empty((g.shape[0], st.ca), dtype=g.dtype, device=g.device)
+                    gb = torch.empty((g.shape[0], g.shape[1] - st.ca), dtype=g.dtype, device=g.device)
+                    ops.copy_columns(g, 0, st.ca, ga, 0)
+                    ops.copy_columns(g, st.ca, g.shape[1] - st.ca, gb, 0)
+                else:
+                    ga, gb = g[:, :st.ca].contiguous(), g[:, st.ca:].contiguous()
+                self._acc(G, st.a, ga, ll)
+                self._acc(G, st.b, gb, ll)
                 continue
             si -= 1
             x, y, mask, mean, invstd, count, n_stat = saved[si]
@@ -373,21 +440,24 @@ class TrunkExecutor:
                                                 st.res is not None, n_stat, hook, count,
                                                 dgamma=grads.view(b.weight), dbeta=grads.view(b.bias), relu_mask=mask)
             if st.res is not None:
-                self._acc(G, st.res, dres)
+                self._acc(G, st.res, dres, ll)
             kview = grads.view(conv.kernel)
             ready = None
             if side is not None:
-                ready = torch.cuda.Event()
-                ready.record(main)
+                if ll is not None:
+                    ready = ll.record_event()
+                else:
+                    ready = torch.cuda.Event()
+                    ready.record(main)
                 if st.level > self.DEFER_LEVEL and not deep_seen:
                     deep_seen = True            # the chain enters the deep levels: release the held-back wgrads
                     for job in deferred:
-                        self._wgrad(side, *job)
+                        self._wgrad(ll, side, *job)
                     deferred = []
             if side is not None and not deep_seen:
                 deferred.append((ready, x, dx_bn, km_f, conv, n_out, kview))
             elif side is None or not st.need_dx:
-                self._wgrad(side, ready, x, dx_bn, km_f, conv, n_out, kview)
+                self._wgrad(ll, side, ready, x, dx_bn, km_f, conv, n_out, kview)
             if st.need_dx:
                 # the gradient already pending for this unit's input (residual branch / skip connection) is added in
                 # the dgrad epilogue instead of by a separate elementwise pass
@@ -396,23 +466,19 @@ class TrunkExecutor:
                                              residual=pending)
                 if side is not None and deep_seen:
                     # enqueued after the dgrad: the critical path gets the SMs first, the wgrad fills in behind it
-                    self._wgrad(side, ready, x, dx_bn, km_f, conv, n_out, kview)
+                    self._wgrad(ll, side, ready, x, dx_bn, km_f, conv, n_out, kview)
             if self.on_bucket is not None and st.name == self.bucket_after:
-                if side is not None:
-                    main.wait_stream(side)      # the bucket's gradients include wgrads still running on the side stream
+                join()                          # the bucket's gradients include wgrads still running on the side stream
+                if ll is not None:
+                    ll.flush()
                 self.on_bucket()
         for job in deferred:
-            self._wgrad(side, *job)
-        if side is not None:
-            main.wait_stream(side)
-        if carry is not None:
-            grads.flat.add_(carry)
-        for p, v in zip(grads.params, grads.views):
-            p.grad = v
-        if self.on_done is not None:
-            self.on_done()
+            self._wgrad(ll, side, *job)
+        join()
 
     @staticmethod
-    def _acc(G, tid, g):
+    def _acc(G, tid, g, ll=None):
         cur = G.get(tid)
+        if cur is not None and ll is not None:
+            ll.flush()                          # an eager torch add on tensors that pending launches produce
         G[tid] = g if cur is None else cur.add_(g)

@@ -356,6 +356,37 @@ int b2m_segment_association(const int32_t* num, const int32_t* first, const int3
                             int64_t* per_seg, int64_t* per_point, void* workspace, size_t workspace_bytes,
                             b2m_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Launch lists: a whole pass of the U-Net trunk (models/detection_net.py:235-337 - ~250 modules, ~540 calls per training
+ * step when bound call by call) in ONE call. A command carries the arguments of one of the entry points above in their
+ * declared order (pointers and integers in a[], floating-point arguments in f[]), without the stream; `stream` selects
+ * the main (0) or the side (1) stream passed to b2m_run_commands. RECORD / WAIT order the two streams through events
+ * of a per-device pool owned by the library (a[0] = event slot): weight gradients run on the side stream beside the
+ * dgrad chain.
+ * ---------------------------------------------------------------------------------------------- */
+#define B2M_CMD_CONV_FORWARD 1       /* b2m_conv_forward_ex: a[0..19] */
+#define B2M_CMD_CONV_WGRAD 2         /* b2m_conv_wgrad_ex: a[0..12] */
+#define B2M_CMD_BN_FORWARD 3         /* b2m_bn_forward: a[0..8] = x..running_var, f[0] = momentum, f[1] = eps, a[9..15] = training..relu_mask */
+#define B2M_CMD_BN_BACKWARD_REDUCE 4 /* b2m_bn_backward_reduce: a[0..9] */
+#define B2M_CMD_BN_BACKWARD_APPLY 5  /* b2m_bn_backward_apply: a[0..18] */
+#define B2M_CMD_COPY_COLUMNS 6       /* b2m_copy_columns: a[0..5] */
+#define B2M_CMD_RECORD 7             /* record event slot a[0] on the selected stream */
+#define B2M_CMD_WAIT 8               /* the selected stream waits for event slot a[0] */
+typedef struct b2m_command {
+  int32_t op;
+  int32_t stream;
+  int64_t a[22];
+  double f[2];
+} b2m_command_t;
+/* dst[r, 0:width] = src[r, 0:width] for bf16 rows of pitch src_ld / dst_ld elements (width, pitches multiples of 8,
+ * 16-byte aligned pointers): the channel concatenation `ME.cat` of the decoder (models/detection_net.py:286-336) and
+ * the split of its gradient. */
+int b2m_copy_columns(const uint16_t* src, int64_t src_ld, uint16_t* dst, int64_t dst_ld, int64_t n, int32_t width,
+                     b2m_stream_t stream);
+/* Issues cmds[0..n) in order. On an error returns its code and, if `failed` is given, the index of the command. */
+int b2m_run_commands(const b2m_command_t* cmds, int64_t n, b2m_stream_t main_stream, b2m_stream_t side_stream,
+                     int64_t* failed);
+
 #ifdef __cplusplus
 }
 #endif

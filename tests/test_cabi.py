@@ -35,3 +35,33 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_launch_list_command_layout():
+    """The packed command records of ops.LaunchList match b2m_command_t: argument validation (which happens before any
+    CUDA call) must see the values where the header says they are."""
+    import ctypes
+
+    from box2mask_b200.ops import LaunchList
+    build.build()
+    lib = _lib.load()
+    assert LaunchList._S.size == 8 + 22 * 8 + 2 * 8           # int32 op, int32 stream, int64 a[22], double f[2]
+    ll = LaunchList("cpu")
+
+    def run():
+        failed = ctypes.c_int64(-7)
+        n, ll.n, ll.kinds = ll.n, 0, []
+        return lib.b2m_run_commands(ll.cbuf, n, None, None, ctypes.byref(failed)), failed.value
+
+    ll.add("bogus", 99, ())
+    assert run() == (-1, 0)                                    # unknown op: invalid argument at command 0
+    # b2m_copy_columns(src, src_ld, dst, dst_ld, n, width): n = 0 is a no-op, width 4 (not a multiple of 8) unsupported
+    ll.add("copy_columns", LaunchList.OP_COPY_COLUMNS, (64, 8, 128, 8, 0, 8))
+    ll.add("copy_columns", LaunchList.OP_COPY_COLUMNS, (64, 8, 128, 8, 5, 4))
+    assert run() == (-4, 1)
+    ll.add("copy_columns", LaunchList.OP_COPY_COLUMNS, (64, 8, 128, 8, -5, 8))
+    assert run() == (-1, 0)                                    # negative row count
+    ll.stream = 1
+    ll.add("copy_columns", LaunchList.OP_COPY_COLUMNS, (64, 8, 128, 8, 0, 8))
+    assert run() == (-1, 0)                                    # side-stream command without a side stream
+    assert run() == (0, -1)                                    # empty list
