@@ -38,6 +38,8 @@ SIGNATURES = {
     "b2m_conv_forward_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "b2m_conv_forward_ex": (c_int32, [_P, c_int64, c_int32, _P, _P, _P, c_int32, c_int64, _P, c_int32, _P, _P, _P, _P, _P,
                                       c_int32, _P, c_int32, _P, c_size_t, _P]),
+    "b2m_conv_dgrad_bn_reduce": (c_int32, [_P, c_int64, c_int32, _P, _P, _P, c_int32, c_int64, _P, c_int32, _P, _P, _P, _P,
+                                           _P, c_int32, _P, c_int32, _P, c_size_t, _P, _P, _P, _P, _P, _P]),
     "b2m_conv_wgrad": (c_int32, [_P, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int32, c_int64, _P, _P]),
     "b2m_conv_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "b2m_conv_wgrad_ex": (c_int32, [_P, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int32, c_int64, _P, _P, c_size_t, _P]),

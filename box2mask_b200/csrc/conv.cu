@@ -199,6 +199,10 @@ struct FwdArgs {
   int off_ep;
   int lean_off; // 1 = general MMA issue loop even where the lean one applies (b2m_set_option B2M_OPT_ISSUER, tests)
   int ldgsts;   // KPACK == 1: A rows fetched by cp.async (LDGSTS) from every lane of the gather warps instead of TMA gather4
+  // dgrad with the BatchNorm-backward reduction of the PRODUCER of this gradient fused into the epilogue (bnr_x != nullptr):
+  // the statistics written to `colsum` are then (sum g, sum g * xhat) with g = bf16(v) gated by the producer's ReLU mask and
+  // xhat = (bnr_x - mean) * invstd - what b2m_bn_backward_reduce computes in a pass of its own over v, x and the mask.
+  const uint16_t* bnr_x; const uint8_t* bnr_mask; const float* bnr_mean; const float* bnr_invstd;
 };
 
 // bits [lo, hi) of a 128-bit mask
@@ -371,7 +375,9 @@ __device__ __forceinline__ void ldgsts_rows_sw64_rolled(uint32_t dst, const uint
 
 // KPACK = offsets per A stage: 1 (c_red >= 48: 64-wide chunks), 2 / 4 (c_red 32 / 16: SW64 / SW32 sub-tiles),
 // 8 (c_red 8: cp.async path). A template parameter so that the single-thread MMA issue loop has no mode branches.
-template <int KPACK>
+// BNR: the dgrad instantiation whose epilogue also takes the BatchNorm-backward reduction of the producer layer (a.bnr_*);
+// a template parameter so that the plain instantiations keep exactly the code (and registers) they had.
+template <int KPACK, bool BNR = false>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_rem, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -406,6 +412,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
       for (int i = tid; i < a.ntile; i += kEpiWarps * 32) {
         ep[i] = a.ep_scale ? __ldg(a.ep_scale + n0 + i) : 1.f;
         ep[a.ntile + i] = a.ep_shift ? __ldg(a.ep_shift + n0 + i) : 0.f;
+      }
+    } else if (BNR) {
+      float* ep = reinterpret_cast<float*>(smem + a.off_ep);
+      for (int i = tid; i < a.ntile; i += kEpiWarps * 32) {
+        ep[i] = __ldg(a.bnr_mean + n0 + i);
+        ep[a.ntile + i] = __ldg(a.bnr_invstd + n0 + i);
       }
     }
   }
@@ -448,6 +460,27 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
         for (int cc = 0; cc < nchunk32; ++cc) {
           const int cw = min(32, a.ntile - cc * 32);   // 32 or 16
           uint32_t v[32];
+          // fused BatchNorm-backward reduction: the producer's rows and ReLU gate are requested before anything else of
+          // the chunk, so that their latency overlaps the accumulator load and the residual add
+          uint4 xr[4];
+          uint32_t gate = 0xFFFFFFFFu;
+          if (BNR) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              xr[q] = (orow >= 0 && q * 8 < cw) ? __ldg(reinterpret_cast<const uint4*>(a.bnr_x + rbase + cc * 32 + q * 8))
+                                                : make_uint4(0u, 0u, 0u, 0u);
+            if (a.bnr_mask != nullptr && orow >= 0) {
+              const uint8_t* mp = a.bnr_mask + ((int64_t)orow * a.c_n + n0 + cc * 32) / 8;
+              if (((a.c_n | n0) & 31) == 0) {
+                gate = __ldg(reinterpret_cast<const uint32_t*>(mp));
+              } else {
+                gate = 0u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (q * 8 < cw) gate |= (uint32_t)__ldg(mp + q) << (8 * q);
+              }
+            }
+          }
           if (has_acc) {
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) +
                                    (uint32_t)((par * a.T + t) * a.colstride + cc * 32);
@@ -497,23 +530,6 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0u;
           }
-          if (a.colsum != nullptr && !B2M_ABLATE(a, 2)) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < cw) st_shared_f32(stage_a + (lane * kStagePitch + j) * 4, __uint_as_float(v[j]));
-            __syncwarp();
-            if (lane < cw) {
-              float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-              for (int r = 0; r < 32; ++r) {
-                const float f = ld_shared_f32(stage_a + (r * kStagePitch + lane) * 4);
-                s1 += f;
-                s2 = fmaf(f, f, s2);
-              }
-              red_shared_f64(csum_a + (cc * 32 + lane) * 8, (double)s1);
-              red_shared_f64(csum_a + (a.ntile + cc * 32 + lane) * 8, (double)s2);
-            }
-          }
           if (orow >= 0 && !B2M_ABLATE(a, 2)) {
             if (a.y32 != nullptr) {
               // fp32 rows of c_store real columns (class logits): scalar stores, the row pitch is not 16-byte aligned
@@ -538,6 +554,64 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
               }
             }
           }
+          if (a.colsum != nullptr && !B2M_ABLATE(a, 2)) {
+            if (BNR) {
+              // BatchNorm-backward reduction of the tensor this gradient belongs to: g = the bf16 value just stored, gated
+              // by the producer's ReLU mask; first quantity g, second g * xhat (two staging rounds through the same tile)
+              // g = the bf16 value just stored, gated; the column sums of g and of g * x go through the staging tile one
+              // after the other (xhat = (x - mean) * invstd is applied to the SUMS when they leave the CTA)
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                v[j] = (orow >= 0 && ((gate >> j) & 1u))
+                           ? __float_as_uint(__bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j])))) : 0u;
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < cw) st_shared_f32(stage_a + (lane * kStagePitch + j) * 4, __uint_as_float(v[j]));
+              __syncwarp();
+              if (lane < cw) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) s1 += ld_shared_f32(stage_a + (r * kStagePitch + lane) * 4);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (q * 8 < cw) {
+                  const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&xr[q]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(rb[e]);
+                    st_shared_f32(stage_a + (lane * kStagePitch + q * 8 + 2 * e) * 4, __uint_as_float(v[q * 8 + 2 * e]) * f.x);
+                    st_shared_f32(stage_a + (lane * kStagePitch + q * 8 + 2 * e + 1) * 4,
+                                  __uint_as_float(v[q * 8 + 2 * e + 1]) * f.y);
+                  }
+                }
+              }
+              __syncwarp();
+              if (lane < cw) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) s2 += ld_shared_f32(stage_a + (r * kStagePitch + lane) * 4);
+                red_shared_f64(csum_a + (cc * 32 + lane) * 8, (double)s1);
+                red_shared_f64(csum_a + (a.ntile + cc * 32 + lane) * 8, (double)s2);
+              }
+            } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < cw) st_shared_f32(stage_a + (lane * kStagePitch + j) * 4, __uint_as_float(v[j]));
+            __syncwarp();
+            if (lane < cw) {
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const float f = ld_shared_f32(stage_a + (r * kStagePitch + lane) * 4);
+                s1 += f;
+                s2 = fmaf(f, f, s2);
+              }
+              red_shared_f64(csum_a + (cc * 32 + lane) * 8, (double)s1);
+              red_shared_f64(csum_a + (a.ntile + cc * 32 + lane) * 8, (double)s2);
+            }
+            }
+          }
           __syncwarp();
         }
       }
@@ -550,9 +624,18 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_consta
     if (a.colsum != nullptr && !split) {
       named_bar_sync(1, kEpiWarps * 32);   // all four epilogue warps have added their last tile
       const double* cs = reinterpret_cast<const double*>(smem + a.off_csum);
+      if (BNR) {
+        // (sum g, sum g * x) -> (sum g, sum g * xhat): xhat = (x - mean) * invstd
+        const float* ep = reinterpret_cast<const float*>(smem + a.off_ep);
+        for (int i = tid; i < a.ntile; i += kEpiWarps * 32) {
+          atomicAdd(a.colsum + n0 + i, cs[i]);
+          atomicAdd(a.colsum + a.c_n + n0 + i, (double)ep[a.ntile + i] * (cs[a.ntile + i] - (double)ep[i] * cs[i]));
+        }
+      } else {
       for (int i = tid; i < 2 * a.ntile; i += kEpiWarps * 32) {
         const int col = (i < a.ntile) ? (n0 + i) : (a.c_n + n0 + i - a.ntile);
         atomicAdd(a.colsum + col, cs[i]);
+      }
       }
     }
     if (warp == 0) B2M_TRACE(33);
@@ -1098,7 +1181,9 @@ constexpr int kFinThreads = 256;
 __global__ void __launch_bounds__(kFinThreads)
 conv_finalize_kernel(const float* __restrict__ part, int nslices, int64_t n, int c, const float* __restrict__ scale,
                      const float* __restrict__ shift, const uint16_t* __restrict__ residual, int relu,
-                     uint16_t* __restrict__ y, float* __restrict__ y32, int c_store, double* __restrict__ colsum) {
+                     uint16_t* __restrict__ y, float* __restrict__ y32, int c_store, double* __restrict__ colsum,
+                     const uint16_t* __restrict__ bnr_x, const uint8_t* __restrict__ bnr_mask,
+                     const float* __restrict__ bnr_mean, const float* __restrict__ bnr_invstd) {
   extern __shared__ float fin_sh[];   // [rows per pass][c][2]
   const int G = c / 8;
   const int rpp = kFinThreads / G;
@@ -1107,10 +1192,11 @@ conv_finalize_kernel(const float* __restrict__ part, int nslices, int64_t n, int
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     s1[i] = 0.f; s2[i] = 0.f;
-    sc[i] = scale ? scale[g * 8 + i] : 1.f;
-    sh[i] = shift ? shift[g * 8 + i] : 0.f;
+    // (with bnr_x - the fused BatchNorm-backward reduction, see conv_fwd_kernel - they hold mean / invstd instead)
+    sc[i] = bnr_x ? bnr_mean[g * 8 + i] : (scale ? scale[g * 8 + i] : 1.f);
+    sh[i] = bnr_x ? bnr_invstd[g * 8 + i] : (shift ? shift[g * 8 + i] : 0.f);
   }
-  const bool affine = scale != nullptr || shift != nullptr;
+  const bool affine = !bnr_x && (scale != nullptr || shift != nullptr);
   if (rl < rpp) {
     for (int64_t r = (int64_t)blockIdx.x * rpp + rl; r < n; r += (int64_t)gridDim.x * rpp) {
       float v[8];
@@ -1140,8 +1226,25 @@ conv_finalize_kernel(const float* __restrict__ part, int nslices, int64_t n, int
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
       }
+      if (bnr_x) {
+        const uint4 xx = __ldg(reinterpret_cast<const uint4*>(bnr_x + r * c) + g);
+        const unsigned gate = bnr_mask ? __ldg(bnr_mask + r * G + g) : 0xFFu;
+        const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xx);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(xb[e]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int i = 2 * e + h;
+            const float gq = ((gate >> i) & 1u) ? __bfloat162float(__float2bfloat16_rn(v[i])) : 0.f;
+            s1[i] += gq;
+            s2[i] = fmaf(gq, ((h ? f.y : f.x) - sc[i]) * sh[i], s2[i]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1[i] += v[i]; s2[i] = fmaf(v[i], v[i], s2[i]); }
+      }
       if (y32) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -2023,6 +2126,24 @@ extern "C" int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_re
                                    int32_t c_n, uint16_t* y, double* colsum, const float* scale, const float* shift,
                                    const uint16_t* residual, int32_t relu, float* y32, int32_t c_store, void* workspace,
                                    size_t workspace_bytes, b2m_stream_t stream) {
+  return b2m_conv_dgrad_bn_reduce(x, n_in, c_red, nbr, order, group_mask, kvol, n_out, packed_w, c_n, y, colsum, scale, shift,
+                                  residual, relu, y32, c_store, workspace, workspace_bytes, nullptr, nullptr, nullptr, nullptr,
+                                  nullptr, stream);
+}
+
+extern "C" int b2m_conv_dgrad_bn_reduce(const uint16_t* x, int64_t n_in, int32_t c_red, const int32_t* nbr,
+                                        const int32_t* order, const uint32_t* group_mask, int32_t kvol, int64_t n_out,
+                                        const uint16_t* packed_w, int32_t c_n, uint16_t* y, double* colsum, const float* scale,
+                                        const float* shift, const uint16_t* residual, int32_t relu, float* y32,
+                                        int32_t c_store, void* workspace, size_t workspace_bytes, const uint16_t* bn_x,
+                                        const uint8_t* bn_relu_mask, const float* bn_mean, const float* bn_invstd,
+                                        double* bn_red, b2m_stream_t stream) {
+  if (bn_red && (!bn_x || !bn_mean || !bn_invstd || colsum || scale || shift || relu || y32 || !y))
+    return B2M_ERR_INVALID_ARGUMENT;
+  if (bn_red && (reinterpret_cast<uintptr_t>(bn_x) & 15) != 0) return B2M_ERR_INVALID_ARGUMENT;
+  if (bn_red && conv_kpack(c_red) > 2) return B2M_ERR_UNSUPPORTED_SHAPE;      // no fused instantiation for c_red < 32
+  if (!bn_red) bn_x = nullptr;
+  double* stat_out = bn_red ? bn_red : colsum;
   if (!x || !packed_w || (!y && !y32) || kvol <= 0 || n_out < 0 || n_in < 0) return B2M_ERR_INVALID_ARGUMENT;
   if (!nbr && kvol != 1) return B2M_ERR_INVALID_ARGUMENT;
   if (nbr && !group_mask) return B2M_ERR_INVALID_ARGUMENT;
@@ -2044,7 +2165,7 @@ extern "C" int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_re
   FwdArgs a;
   a.x = x; a.nbr = nbr; a.order = nbr ? order : nullptr; a.gmask = nbr ? group_mask : nullptr;
   a.w = reinterpret_cast<const uint8_t*>(packed_w); a.y = y;
-  a.colsum = colsum; a.n_out = n_out; a.n_pitch = b2m_map_pitch(n_out); a.c_red = c_red; a.kvol = kvol; a.c_n = c_n;
+  a.colsum = stat_out; a.n_out = n_out; a.n_pitch = b2m_map_pitch(n_out); a.c_red = c_red; a.kvol = kvol; a.c_n = c_n;
   a.ntile = c_n / ntiles_n;
   a.kpack = conv_kpack(c_red);
   a.nkg = (kvol + a.kpack - 1) / a.kpack;
@@ -2056,6 +2177,8 @@ extern "C" int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_re
   a.ep_res = slices > 1 ? nullptr : residual; a.ep_relu = slices > 1 ? 0 : (relu ? 1 : 0);
   a.y32 = slices > 1 ? nullptr : y32; a.c_store = c_store;
   if (slices > 1) a.colsum = nullptr;
+  // the fused BatchNorm-backward reduction runs wherever the epilogue runs: here, or in conv_finalize_kernel when split
+  a.bnr_x = slices > 1 ? nullptr : bn_x; a.bnr_mask = bn_relu_mask; a.bnr_mean = bn_mean; a.bnr_invstd = bn_invstd;
   a.nfull = conv_nfull(c_red);
   a.rem = conv_rem(c_red);
   a.wa = (a.kpack > 1 && a.kpack < 8) ? c_red * 2 : 128;
@@ -2145,7 +2268,9 @@ extern "C" int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_re
     if (cudaFuncSetAttribute(conv_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(conv_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(conv_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        cudaFuncSetAttribute(conv_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return B2M_ERR_CUDA_LAUNCH;
     dc->fwd_attr = true;
   }
@@ -2159,7 +2284,9 @@ extern "C" int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_re
   }
   dim3 grid((unsigned)gx, (unsigned)ntiles_n, (unsigned)slices);
   const cudaStream_t st = (cudaStream_t)stream;
-  switch (a.kpack) {
+  if (a.bnr_x != nullptr && a.kpack == 1) conv_fwd_kernel<1, true><<<grid, kFwdThreads, smem_bytes, st>>>(tm_main, tm_rem, a);
+  else if (a.bnr_x != nullptr && a.kpack == 2) conv_fwd_kernel<2, true><<<grid, kFwdThreads, smem_bytes, st>>>(tm_main, tm_rem, a);
+  else switch (a.kpack) {
     case 1: conv_fwd_kernel<1><<<grid, kFwdThreads, smem_bytes, st>>>(tm_main, tm_rem, a); break;
     case 2: conv_fwd_kernel<2><<<grid, kFwdThreads, smem_bytes, st>>>(tm_main, tm_rem, a); break;
     case 4: conv_fwd_kernel<4><<<grid, kFwdThreads, smem_bytes, st>>>(tm_main, tm_rem, a); break;
@@ -2170,9 +2297,10 @@ extern "C" int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_re
     const int rpp = kFinThreads / (c_n / 8);
     int64_t blocks = (n_out + rpp - 1) / rpp;
     if (blocks > 148 * 4) blocks = 148 * 4;
-    const size_t sh = colsum ? (size_t)rpp * c_n * 2 * sizeof(float) : 0;
+    const size_t sh = stat_out ? (size_t)rpp * c_n * 2 * sizeof(float) : 0;
     conv_finalize_kernel<<<(unsigned)blocks, kFinThreads, sh, st>>>(a.part, slices, n_out, c_n, scale, shift, residual,
-                                                                  relu ? 1 : 0, y, y32, c_store, colsum);
+                                                                  relu ? 1 : 0, y, y32, c_store, stat_out, bn_x, bn_relu_mask,
+                                                                  bn_mean, bn_invstd);
     B2M_CHECK_LAUNCH();
   }
   return B2M_OK;

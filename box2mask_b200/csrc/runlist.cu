@@ -77,11 +77,12 @@ extern "C" int b2m_run_commands(const b2m_command_t* cmds, int64_t n, b2m_stream
     if (c.stream && !side_stream) rc = B2M_ERR_INVALID_ARGUMENT;
     else switch (c.op) {
       case B2M_CMD_CONV_FORWARD:
-        rc = b2m_conv_forward_ex((const uint16_t*)P(a[0]), a[1], (int32_t)a[2], (const int32_t*)P(a[3]), (const int32_t*)P(a[4]),
+        rc = b2m_conv_dgrad_bn_reduce((const uint16_t*)P(a[0]), a[1], (int32_t)a[2], (const int32_t*)P(a[3]), (const int32_t*)P(a[4]),
                                  (const uint32_t*)P(a[5]), (int32_t)a[6], a[7], (const uint16_t*)P(a[8]), (int32_t)a[9],
                                  (uint16_t*)P(a[10]), (double*)P(a[11]), (const float*)P(a[12]), (const float*)P(a[13]),
                                  (const uint16_t*)P(a[14]), (int32_t)a[15], (float*)P(a[16]), (int32_t)a[17], P(a[18]),
-                                 (size_t)a[19], st);
+                                 (size_t)a[19], (const uint16_t*)P(a[20]), (const uint8_t*)P(a[21]), (const float*)P(a[22]),
+                                 (const float*)P(a[23]), (double*)P(a[24]), st);
         break;
       case B2M_CMD_CONV_WGRAD:
         rc = b2m_conv_wgrad_ex((const uint16_t*)P(a[0]), a[1], (int32_t)a[2], (const uint16_t*)P(a[3]), (int32_t)a[4],

@@ -67,8 +67,8 @@ class LaunchList:
       * tensors read by side-stream commands are kept alive until flush() and then marked with record_stream(side)
         (the allocator must not reuse them for main-stream work before the side stream is done)."""
     current = None
-    _S = struct.Struct("<ii22q2d")
-    _PAD = (0,) * 22
+    _S = struct.Struct("<ii28q2d")
+    _PAD = (0,) * 28
     OP_CONV_FORWARD, OP_CONV_WGRAD, OP_BN_FORWARD, OP_BN_BACKWARD_REDUCE, OP_BN_BACKWARD_APPLY = 1, 2, 3, 4, 5
     OP_COPY_COLUMNS, OP_RECORD, OP_WAIT = 6, 7, 8
 
@@ -158,8 +158,8 @@ class LaunchList:
 class ZeroArena:
     """Zeroed fp64 scratch for the per-layer statistics (conv epilogue column sums, BatchNorm backward reductions):
     slices of one pre-zeroed buffer per device instead of one fill kernel per layer (243 per training step).
-    A slice is consumed by the kernels launched right after it is taken; when the buffer is used up it is zeroed
-    again in stream order and `generation` advances, which invalidates column sums still attached to a tensor."""
+    When the buffer is used up a fresh zeroed one replaces it (slices still in use keep the old one alive) and
+    `generation` advances, which makes holders of cached column sums recompute them."""
     SIZE = 1 << 19      # doubles (4 MB)
     _state = {}         # device -> [buffer, next offset, generation]
 
@@ -172,8 +172,11 @@ class ZeroArena:
             st = [torch.zeros(cls.SIZE, dtype=torch.float64, device=device), 0, 0]
             cls._state[device] = st
         elif st[1] + n_al > cls.SIZE:
-            LaunchList.flush_current()      # pending commands still read their slices
-            st[0].zero_()
+            # a fresh zeroed buffer, not zero_() in place: slices handed out earlier may still be waiting for their
+            # consumer (a reduction produced by a dgrad epilogue is read several layers later); they keep the old
+            # buffer alive. (An eager fill: commands still pending in a launch list go first.)
+            LaunchList.flush_current()
+            st[0] = torch.zeros(cls.SIZE, dtype=torch.float64, device=device)
             st[1] = 0
             st[2] += 1
         out = st[0][st[1]:st[1] + n]
@@ -457,14 +460,25 @@ class Workspace:
         return buf
 
 
+def conv_forward_is_split(n_out, c_red, kvol, c_n):
+    """True when b2m_conv_forward runs this shape offset-split (few row tiles: the kernel offsets are dealt to several
+    CTAs per tile and conv_finalize_kernel sums the slices and runs the epilogue)."""
+    return _lib_or_raise().b2m_conv_forward_workspace_bytes(n_out, c_red, kvol, c_n) > 0
+
+
 def conv_forward(x, kmap, packed_w, kvol, n_out, c_n, colsum=None, scale=None, shift=None, residual=None, relu=False,
-                 out_fp32_cols=None):
+                 out_fp32_cols=None, bn_reduce=None):
     """y bf16[n_out, c_n] = epilogue(sum_k x[nbr[k]] @ B[k]) over a sorted KernelMap (None = identity, kvol 1).
     Epilogue (optional): * scale[c_n] + shift[c_n] (+ residual bf16[n_out, c_n]) (ReLU). colsum f64[2*c_n] (zeroed by
     the caller) accumulates the statistics of the result. out_fp32_cols = c: return fp32 [n_out, c] (the first c
-    columns) instead of bf16."""
+    columns) instead of bf16.
+    bn_reduce = (x_prod bf16[n_out, c_n], relu_mask uint8[n_out, c_n/8] or None, mean f32[c_n], invstd f32[c_n],
+    red f64[2*c_n] zeroed): the call is a dgrad and its result the complete gradient of a BatchNorm layer's output; the
+    epilogue also accumulates that layer's backward reduction (sum g, sum g*xhat) into red (b2m_conv_dgrad_bn_reduce), which
+    bn_backward(red=...) then takes instead of running its reduction pass."""
     lib = _lib_or_raise()
     _cuda(x, torch.bfloat16, "x")
+    bx, bmask, bmean, binv, bred = bn_reduce if bn_reduce is not None else (None, None, None, None, None)
     nbr = kmap.nbr if kmap is not None else None
     order = kmap.order if kmap is not None else None
     gmask = kmap.gmask if kmap is not None else None
@@ -481,13 +495,15 @@ def conv_forward(x, kmap, packed_w, kvol, n_out, c_n, colsum=None, scale=None, s
         ll.add("conv_forward", ll.OP_CONV_FORWARD, (
             x.data_ptr(), x.shape[0], x.shape[1], _p(nbr), _p(order), _p(gmask), kvol, n_out, packed_w.data_ptr(), c_n,
             _p(y), _p(colsum), _p(scale), _p(shift), _p(residual), 1 if relu else 0, _p(y32),
-            int(out_fp32_cols) if out_fp32_cols is not None else 0, _p(ws), ws_bytes))
+            int(out_fp32_cols) if out_fp32_cols is not None else 0, _p(ws), ws_bytes,
+            _p(bx), _p(bmask), _p(bmean), _p(binv), _p(bred)))
         return y if y32 is None else y32
     ws = Workspace.get(ws_bytes, x.device) if ws_bytes else None
-    _run("conv_forward", 2 if ws_bytes else 1, lambda: check(lib.b2m_conv_forward_ex(
+    _run("conv_forward", 2 if ws_bytes else 1, lambda: check(lib.b2m_conv_dgrad_bn_reduce(
         ptr(x), x.shape[0], x.shape[1], ptr(nbr), ptr(order), ptr(gmask), kvol, n_out, ptr(packed_w), c_n, ptr(y),
         ptr(colsum), ptr(scale), ptr(shift), ptr(residual), int(bool(relu)), ptr(y32),
-        int(out_fp32_cols) if out_fp32_cols is not None else 0, ptr(ws), ws_bytes, stream_ptr()), "conv_forward"),
+        int(out_fp32_cols) if out_fp32_cols is not None else 0, ptr(ws), ws_bytes, ptr(bx), ptr(bmask), ptr(bmean),
+        ptr(binv), ptr(bred), stream_ptr()), "conv_forward"),
         flops=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] * c_n,
         nbytes=lambda: 2.0 * Profile.pairs(nbr, n_out) * x.shape[1] + 2.0 * n_out * c_n,
         tag=lambda: "k%d %d->%d n_in=%d n_out=%d" % (kvol, x.shape[1], c_n, x.shape[0], n_out))
@@ -594,19 +610,23 @@ def bn_forward(x, sums, gamma, beta, running_mean, running_var, momentum, eps, t
 
 
 def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, want_dresidual, n_stat=None,
-                reduce_hook=None, n_stat_dev=None, dgamma=None, dbeta=None, relu_mask=None):
+                reduce_hook=None, n_stat_dev=None, dgamma=None, dbeta=None, relu_mask=None, red=None):
     """n_stat_dev: optional f64[1] device tensor with the global row count (SyncBN, no host round trip).
-    reduce_hook(red) -> all-reduced copy of red: only dx uses it; dgamma / dbeta stay this rank's own sums."""
+    reduce_hook(red) -> all-reduced copy of red: only dx uses it; dgamma / dbeta stay this rank's own sums.
+    red: the reduction (sum g, sum g*xhat) f64[2c] if a dgrad epilogue already produced it (conv_forward(bn_reduce=...))."""
     lib = _lib_or_raise()
     n, c = x.shape
-    red = ZeroArena.take(2 * c, x.device)
+    have_red = red is not None
+    if not have_red:
+        red = ZeroArena.take(2 * c, x.device)
     ll = LaunchList.current
     if ll is not None:
-        Profile.launches += 2
+        Profile.launches += 1 if have_red else 2
         rl, tr = 1 if relu else 0, 1 if training else 0
-        ll.add("bn_backward_reduce", ll.OP_BN_BACKWARD_REDUCE, (
-            x.data_ptr(), _p(out), dout.data_ptr(), n, c, save_mean.data_ptr(), save_invstd.data_ptr(), rl, red.data_ptr(),
-            _p(relu_mask)))
+        if not have_red:
+            ll.add("bn_backward_reduce", ll.OP_BN_BACKWARD_REDUCE, (
+                x.data_ptr(), _p(out), dout.data_ptr(), n, c, save_mean.data_ptr(), save_invstd.data_ptr(), rl,
+                red.data_ptr(), _p(relu_mask)))
         red_local = None
         if reduce_hook is not None:
             ll.flush()                      # the hook is a collective on the reduction
@@ -623,9 +643,10 @@ def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, wan
             save_invstd.data_ptr(), gamma.data_ptr(), red.data_ptr(), _p(red_local), _p(n_stat_dev), rl, tr, dx.data_ptr(),
             _p(dres), dgamma.data_ptr(), dbeta.data_ptr(), _p(relu_mask)))
         return dx, dres, dgamma, dbeta
-    _run("bn_backward_reduce", 1, lambda: check(lib.b2m_bn_backward_reduce(
-        ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd), int(bool(relu)), ptr(red), ptr(relu_mask),
-        stream_ptr()), "bn_backward_reduce"), nbytes=2 * x.numel() * (3 if (relu and relu_mask is None) else 2))
+    if not have_red:
+        _run("bn_backward_reduce", 1, lambda: check(lib.b2m_bn_backward_reduce(
+            ptr(x), ptr(out), ptr(dout), n, c, ptr(save_mean), ptr(save_invstd), int(bool(relu)), ptr(red), ptr(relu_mask),
+            stream_ptr()), "bn_backward_reduce"), nbytes=2 * x.numel() * (3 if (relu and relu_mask is None) else 2))
     red_local = None
     if reduce_hook is not None:
         red_local = red

@@ -29,11 +29,12 @@ from .me.nn import _dgrad_mode, _round16
 
 class Unit:
     """conv -> BatchNorm (+ residual) (+ ReLU). src / dst / res are tensor ids of the program."""
-    __slots__ = ("name", "conv", "bn", "src", "dst", "res", "relu", "map", "need_dx", "level")
+    __slots__ = ("name", "conv", "bn", "src", "dst", "res", "relu", "map", "need_dx", "level", "fuse_for")
 
     def __init__(self, name, conv, bn, src, dst, res, relu, map_key, need_dx, level):
         self.name, self.conv, self.bn, self.src, self.dst, self.res, self.relu = name, conv, bn, src, dst, res, relu
         self.map, self.need_dx, self.level = map_key, need_dx, level
+        self.fuse_for = None      # index of the unit whose BatchNorm-backward reduction this unit's dgrad epilogue takes
 
 
 class Cat:
@@ -94,6 +95,28 @@ class TrunkProgram:
         self.param_order = []
         for u in reversed(self.units):
             self.param_order += [u.conv.kernel, u.bn.bn.weight, u.bn.bn.bias]
+        self._plan_fused_reductions()
+
+    def _plan_fused_reductions(self):
+        """BatchNorm backward needs (sum g, sum g * xhat) over the complete gradient g of the layer's output. Where the
+        LAST contribution to that gradient in backward order is a dgrad (its epilogue adds whatever is already pending:
+        residual branch, skip connection), that dgrad's epilogue takes the reduction too and the layer's own reduction
+        pass - a full read of g and x - is dropped. Not fusable: tensors whose last contribution is a concatenation
+        split (the transposed convolutions of the decoder) and the trunk output (its gradient comes from the heads)."""
+        producer = {u.dst: i for i, u in enumerate(self.units)}
+        index = {id(u): i for i, u in enumerate(self.units)}
+        last = {}                                     # tensor id -> (kind, unit index) of the last contribution
+        for st in reversed(self.steps):
+            if isinstance(st, Cat):
+                last[st.a] = last[st.b] = ("cat", None)
+                continue
+            if st.res is not None:
+                last[st.res] = ("res", None)
+            if st.need_dx:
+                last[st.src] = ("dgrad", index[id(st)])
+        for tid, (kind, ui) in last.items():
+            if kind == "dgrad" and tid in producer and _round16(self.units[ui].conv.out_channels) >= 32:
+                self.units[ui].fuse_for = producer[tid]
 
     def parameters(self):
         return self.param_order
@@ -214,6 +237,9 @@ class TrunkExecutor:
         # work at the start of backward) are held back until the chain enters the deep levels and then fill those SMs.
         self.overlap_wgrad = True
         self._wgrad_stream = None
+        # BatchNorm-backward reductions taken by the dgrad that completes the gradient: True = where that dgrad runs
+        # offset-split (deep levels), "all" = everywhere (slower, kept for the tests), False = never
+        self.fuse_bn_reduce = True
 
     # ---------------------------------------------------------------------------------------------
     def _input(self, feats, unit):
@@ -399,6 +425,7 @@ class TrunkExecutor:
     def _backward_steps(self, prog, maps, grads, saved, dout, ll, side, main):
         deferred, deep_seen = [], False
         G = {prog.out_id: dout}
+        R = {}                                  # unit index -> its BatchNorm reduction, taken by a dgrad epilogue
         si = len(saved)
 
         def join():
@@ -438,7 +465,8 @@ class TrunkExecutor:
             # the ReLU gate comes from the 1-bit mask the forward pass wrote, not from re-reading the unit's output
             dx_bn, dres, _, _ = ops.bn_backward(y, None, g_out, mean, invstd, b.weight.detach(), st.relu, True,
                                                 st.res is not None, n_stat, hook, count,
-                                                dgamma=grads.view(b.weight), dbeta=grads.view(b.bias), relu_mask=mask)
+                                                dgamma=grads.view(b.weight), dbeta=grads.view(b.bias), relu_mask=mask,
+                                                red=R.pop(si, None))
             if st.res is not None:
                 self._acc(G, st.res, dres, ll)
             kview = grads.view(conv.kernel)
@@ -462,8 +490,21 @@ class TrunkExecutor:
                 # the gradient already pending for this unit's input (residual branch / skip connection) is added in
                 # the dgrad epilogue instead of by a separate elementwise pass
                 pending = G.get(st.src)
+                fused = None
+                if st.fuse_for is not None and self.fuse_bn_reduce and (
+                        self.fuse_bn_reduce == "all" or
+                        ops.conv_forward_is_split(x.shape[0], dx_bn.shape[1], conv.kernel_volume, x.shape[1])):
+                    # this dgrad completes the gradient of unit `fuse_for`'s output: its epilogue also takes that unit's
+                    # BatchNorm-backward reduction (TrunkProgram._plan_fused_reductions). Only on the offset-split path
+                    # of the deep levels, where conv_finalize_kernel owns 8 columns of a row per thread and the sums cost
+                    # a few FMAs - and save a launch. In conv_fwd_kernel's epilogue (a lane = a row) the column sums need
+                    # two more trips through shared memory per 32-column chunk, and the epilogue warps set the pace:
+                    # measured on 1.22 M rows, 96 -> 96: 0.51 -> 0.97 ms, against 0.12 ms for the reduction pass alone.
+                    _, py, pmask, pmean, pinvstd, _, _ = saved[st.fuse_for]
+                    R[st.fuse_for] = ops.ZeroArena.take(2 * py.shape[1], py.device)
+                    fused = (py, pmask, pmean, pinvstd, R[st.fuse_for])
                 G[st.src] = ops.conv_forward(dx_bn, km_b, _packed(conv)[1], conv.kernel_volume, x.shape[0], x.shape[1],
-                                             residual=pending)
+                                             residual=pending, bn_reduce=fused)
                 if side is not None and deep_seen:
                     # enqueued after the dgrad: the critical path gets the SMs first, the wgrad fills in behind it
                     self._wgrad(ll, side, ready, x, dx_bn, km_f, conv, n_out, kview)

@@ -197,6 +197,19 @@ int b2m_conv_forward_ex(const uint16_t* x, int64_t n_in, int32_t c_red, const in
                         int32_t c_n, uint16_t* y, double* colsum, const float* scale, const float* shift,
                         const uint16_t* residual, int32_t relu, float* y32, int32_t c_store, void* workspace,
                         size_t workspace_bytes, b2m_stream_t stream);
+/* b2m_conv_forward_ex used as the dgrad of a unit (x = dL/d(conv output), packed_w = the mirrored / transposed weights,
+ * residual = the gradient already pending for the unit's input) with the BatchNorm-backward reduction of the layer that
+ * PRODUCED that input fused into its epilogue: bn_red double[2 * c_n] (zeroed by the caller) += (sum g, sum g * xhat), g =
+ * the bf16 result row gated by bn_relu_mask (uint8[n_out, c_n / 8], NULL = no ReLU), xhat = (bn_x - bn_mean) * bn_invstd
+ * with bn_x bf16[n_out, c_n] the producer's pre-BatchNorm rows - exactly what b2m_bn_backward_reduce computes in a pass of
+ * its own (models/resnet.py:63-67 backward). bn_red == NULL: plain b2m_conv_forward_ex. With bn_red: no colsum, scale,
+ * shift, relu, y32. */
+int b2m_conv_dgrad_bn_reduce(const uint16_t* x, int64_t n_in, int32_t c_red, const int32_t* nbr, const int32_t* order,
+                             const uint32_t* group_mask, int32_t kvol, int64_t n_out, const uint16_t* packed_w,
+                             int32_t c_n, uint16_t* y, double* colsum, const float* scale, const float* shift,
+                             const uint16_t* residual, int32_t relu, float* y32, int32_t c_store, void* workspace,
+                             size_t workspace_bytes, const uint16_t* bn_x, const uint8_t* bn_relu_mask,
+                             const float* bn_mean, const float* bn_invstd, double* bn_red, b2m_stream_t stream);
 /* dw[k, ci, co] = sum_j x[nbr[k][j], ci] * dy[order[j], co]   (fp32; dw is OVERWRITTEN: with one CTA per element
  * - few row groups - by plain stores, otherwise zero-filled inside and accumulated with fp32 vector reductions)
  * over a sorted kernel map. x bf16[n_in, c_in], dy bf16[n_out, c_out]; c_in % 8 == 0, c_out % 16 == 0,
@@ -364,7 +377,7 @@ int b2m_segment_association(const int32_t* num, const int32_t* first, const int3
  * of a per-device pool owned by the library (a[0] = event slot): weight gradients run on the side stream beside the
  * dgrad chain.
  * ---------------------------------------------------------------------------------------------- */
-#define B2M_CMD_CONV_FORWARD 1       /* b2m_conv_forward_ex: a[0..19] */
+#define B2M_CMD_CONV_FORWARD 1       /* b2m_conv_dgrad_bn_reduce: a[0..24] (a[20..24] = bn_x .. bn_red, 0 = plain b2m_conv_forward_ex) */
 #define B2M_CMD_CONV_WGRAD 2         /* b2m_conv_wgrad_ex: a[0..12] */
 #define B2M_CMD_BN_FORWARD 3         /* b2m_bn_forward: a[0..8] = x..running_var, f[0] = momentum, f[1] = eps, a[9..15] = training..relu_mask */
 #define B2M_CMD_BN_BACKWARD_REDUCE 4 /* b2m_bn_backward_reduce: a[0..9] */
@@ -375,7 +388,7 @@ int b2m_segment_association(const int32_t* num, const int32_t* first, const int3
 typedef struct b2m_command {
   int32_t op;
   int32_t stream;
-  int64_t a[22];
+  int64_t a[28];
   double f[2];
 } b2m_command_t;
 /* dst[r, 0:width] = src[r, 0:width] for bf16 rows of pitch src_ld / dst_ld elements (width, pitches multiples of 8,

@@ -45,7 +45,7 @@ def test_launch_list_command_layout():
     from box2mask_b200.ops import LaunchList
     build.build()
     lib = _lib.load()
-    assert LaunchList._S.size == 8 + 22 * 8 + 2 * 8           # int32 op, int32 stream, int64 a[22], double f[2]
+    assert LaunchList._S.size == 8 + 28 * 8 + 2 * 8           # int32 op, int32 stream, int64 a[28], double f[2]
     ll = LaunchList("cpu")
 
     def run():

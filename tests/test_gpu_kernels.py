@@ -237,6 +237,42 @@ def test_conv_forward_offset_split_equals_unsplit(kvol, c_in, c_out, n):
     assert torch.allclose(cs1, cs0, rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("kvol,c_in,c_out,n,relu", [(27, 96, 96, 515, True), (27, 96, 128, 40000, True), (1, 96, 96, 30000, False),
+                                                    (27, 256, 256, 700, True), (27, 32, 32, 5000, True), (8, 128, 96, 3000, False)])
+def test_dgrad_epilogue_takes_batchnorm_reduction(kvol, c_in, c_out, n, relu):
+    """b2m_conv_dgrad_bn_reduce: the dgrad whose result completes the gradient of a BatchNorm layer's output also
+    accumulates that layer's backward reduction (sum g, sum g * xhat), g gated by the layer's ReLU bit mask - on the
+    unsplit path (epilogue of conv_fwd_kernel) and on the offset-split path (conv_finalize_kernel). Must equal what
+    b2m_bn_backward_reduce computes from the stored bf16 gradient, and the gradient itself must not change."""
+    nbr_np, x, w, n = _conv_case(kvol, c_in, c_out, n, seed=21)
+    torch.manual_seed(2)
+    nbr = ops.sort_kernel_map(torch.from_numpy(nbr_np).to(DEV)) if nbr_np is not None else None
+    xd, wp = x.to(DEV).to(torch.bfloat16), ops.pack_weights(w.to(DEV), 0)
+    pending = torch.randn(n, c_out, device=DEV).to(torch.bfloat16)
+    px = (torch.randn(n, c_out, device=DEV) * 2 + 0.3).to(torch.bfloat16)          # the producer's pre-BatchNorm rows
+    mean, invstd = torch.randn(c_out, device=DEV) * 0.2, torch.rand(c_out, device=DEV) + 0.5
+    mask = torch.randint(0, 256, (n, c_out // 8), dtype=torch.uint8, device=DEV) if relu else None
+    g0 = ops.conv_forward(xd, nbr, wp, kvol, n, c_out, residual=pending)
+    red = torch.zeros(2 * c_out, dtype=torch.float64, device=DEV)
+    g1 = ops.conv_forward(xd, nbr, wp, kvol, n, c_out, residual=pending, bn_reduce=(px, mask, mean, invstd, red))
+    assert torch.equal(g0, g1)
+    ref = torch.zeros(2 * c_out, dtype=torch.float64, device=DEV)
+    from box2mask_b200 import _lib
+    _lib.check(_lib.load().b2m_bn_backward_reduce(_lib.ptr(px), None, _lib.ptr(g1), n, c_out, _lib.ptr(mean), _lib.ptr(invstd),
+                                                  1 if relu else 0, _lib.ptr(ref), _lib.ptr(mask), _lib.stream_ptr()), "reduce")
+    # an independent fp64 evaluation as well
+    gate = torch.ones(n, c_out, device=DEV, dtype=torch.float64)
+    if relu:
+        bits = (mask[:, :, None] >> torch.arange(8, device=DEV, dtype=torch.uint8)) & 1
+        gate = bits.reshape(n, c_out).double()
+    g = g1.double() * gate
+    xhat = (px.double() - mean.double()) * invstd.double()
+    exact = torch.cat([g.sum(0), (g * xhat).sum(0)])
+    scale = exact.abs().max().item() + 1.0
+    assert float((red - exact).abs().max()) <= 2e-5 * scale, float((red - exact).abs().max())
+    assert float((red - ref).abs().max()) <= 4e-5 * scale
+
+
 @pytest.mark.parametrize("kvol,c_in,c_out,n", [(27, 96, 96, 515), (27, 128, 96, 40000), (1, 96, 96, 30000), (8, 256, 256, 1500)])
 def test_conv_forward_fused_epilogue(kvol, c_in, c_out, n):
     """Fused epilogue: v = acc * scale + shift + residual, ReLU (eval-mode BatchNorm folded into the convolution, the

@@ -68,13 +68,16 @@ def _gather_mm(x, nbr, w):
     return y
 
 
+fused_reductions = []       # one entry per dgrad call that took a BatchNorm reduction (reset by the tests that count)
+
+
 @pytest.fixture()
 def fake_ops(monkeypatch):
     def cast_pad_bf16(x, c_pad):
         return torch.nn.functional.pad(x, (0, c_pad - x.shape[1]))
 
     def conv_forward(x, kmap, packed_w, kvol, n_out, c_n, colsum=None, scale=None, shift=None, residual=None, relu=False,
-                     out_fp32_cols=None):
+                     out_fp32_cols=None, bn_reduce=None):
         v = _gather_mm(x, kmap.nbr if kmap is not None else None, packed_w)
         assert v.shape == (n_out, c_n)
         if scale is not None:
@@ -88,6 +91,12 @@ def fake_ops(monkeypatch):
         if colsum is not None:
             colsum[:c_n] += v.sum(0)
             colsum[c_n:2 * c_n] += (v * v).sum(0)
+        if bn_reduce is not None:       # b2m_conv_dgrad_bn_reduce: the producer layer's BatchNorm-backward reduction
+            px, pmask, pmean, pinvstd, red = bn_reduce
+            fused_reductions.append(1)
+            g = v.float().double() * (pmask if pmask is not None else 1)
+            red[:c_n] += g.sum(0)
+            red[c_n:2 * c_n] += (g * (px.double() - pmean.double()) * pinvstd.double()).sum(0)
         return v.float()
 
     def conv_wgrad(x, dy, kmap, kvol, n_out, out=None):
@@ -154,13 +163,17 @@ def fake_ops(monkeypatch):
         return out.float(), mean.float(), invstd.float()
 
     def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, want_dresidual, n_stat=None,
-                    reduce_hook=None, n_stat_dev=None, dgamma=None, dbeta=None, relu_mask=None):
+                    reduce_hook=None, n_stat_dev=None, dgamma=None, dbeta=None, relu_mask=None, red=None):
         n = x.shape[0] if n_stat is None else n_stat
+        c = x.shape[1]
         g = dout.double()
         if relu:
             g = g * (relu_mask if relu_mask is not None else (out > 0))
         xhat = (x.double() - save_mean.double()) * save_invstd.double()
         sg, sgx = g.sum(0), (g * xhat).sum(0)
+        if red is not None:             # the reduction a dgrad epilogue took must be the one this layer would compute
+            assert torch.allclose(red[:c], sg, rtol=1e-9, atol=1e-9) and torch.allclose(red[c:2 * c], sgx, rtol=1e-9, atol=1e-9)
+            sg, sgx = red[:c].clone(), red[c:2 * c].clone()
         scale = gamma.double() * save_invstd.double()
         dx = scale * (g - sg / n - xhat * sgx / n) if training else scale * g
         for dst, val in ((dgamma, sgx), (dbeta, sg)):
@@ -237,6 +250,8 @@ def test_trunk_executor_train_matches_module_path(fake_ops):
     net.train()
     sd = {k: v.clone() for k, v in net.state_dict().items()}
     res = {}
+    net.trunk_executor().fuse_bn_reduce = "all"     # every fusable BatchNorm-backward reduction goes through a dgrad epilogue
+    del fused_reductions[:]
     for executor in (False, True):
         net.load_state_dict(sd)
         net.zero_grad(set_to_none=True)
@@ -270,6 +285,10 @@ def test_trunk_executor_train_matches_module_path(fake_ops):
     names = [u.name for u in ex.program.units]
     assert names[0] == "conv0p1s1" and names[-1] == "block8.1.conv2" and len(names) == 81
     assert ex.grads.index[id(net.block8[1].conv2.kernel)] == 0           # the last unit's gradients complete first
+    # 63 of the 81 BatchNorm-backward reductions were taken by the dgrad that completes the layer's output gradient (the
+    # stand-in bn_backward asserts each one equals the reduction the layer would have computed itself); not fusable:
+    # the 7 transposed convolutions (concatenation split), the 10 residual-branch 1x1 units, the trunk output
+    assert len(fused_reductions) == 63 == sum(u.fuse_for is not None for u in ex.program.units)
 
 
 def test_trunk_executor_accumulates_when_gradients_are_not_zeroed(fake_ops):

@@ -93,6 +93,22 @@ for mode in (["cpasync", "tma"] if args.gather == "both" else args.gather.split(
             colsum = torch.zeros(2 * args.cout, dtype=torch.float64, device=dev)
             bench(lambda: ops.conv_forward(x, km, packed, kvol, n, args.cout, colsum), "fwd[%s,%s]" % (mode, iss))
         L.set_option(L.OPT_ISSUER, 0)
+    if "dgrad" in args.which:
+        # the dgrad of a unit (square layer: cin == cout here) with the pending-gradient add, without / with the
+        # BatchNorm-backward reduction of the producer layer in its epilogue, and that reduction as a pass of its own
+        pend = torch.randn(n, args.cout, device=dev).to(torch.bfloat16)
+        px = torch.randn(n, args.cout, device=dev).to(torch.bfloat16)
+        mean, invstd = torch.randn(args.cout, device=dev), torch.rand(args.cout, device=dev) + 0.5
+        mask = torch.randint(0, 256, (n, args.cout // 8), dtype=torch.uint8, device=dev)
+        red = torch.zeros(2 * args.cout, dtype=torch.float64, device=dev)
+        bench(lambda: ops.conv_forward(x, km, packed, kvol, n, args.cout), "[%s] no statistics, no residual" % mode)
+        bench(lambda: ops.conv_forward(x, km, packed, kvol, n, args.cout, residual=pend), "dgrad[%s] plain" % mode)
+        bench(lambda: ops.conv_forward(x, km, packed, kvol, n, args.cout, residual=pend, bn_reduce=(px, mask, mean, invstd, red)),
+              "dgrad[%s] + BN reduction" % mode)
+        g = ops.conv_forward(x, km, packed, kvol, n, args.cout, residual=pend)
+        bench(lambda: L.check(L.load().b2m_bn_backward_reduce(L.ptr(px), None, L.ptr(g), n, args.cout, L.ptr(mean), L.ptr(invstd),
+                                                               1, L.ptr(red), L.ptr(mask), L.stream_ptr()), "reduce"),
+              "bn_backward_reduce alone")
     if "wgrad" in args.which:
         for r in args.wgrows.split(","):
             L.set_option(L.OPT_WGRAD_ROWS, int(r))
