@@ -402,6 +402,9 @@ def main():
                     help="flat: one all-reduce of the flat gradient buffer after backward (box2mask_b200/grad_sync.py); "
                          "ddp: torch DistributedDataParallel buckets overlapped with backward")
     ap.add_argument("--regions", type=int, default=3, help="timed regions of --steps steps each; the median is reported")
+    ap.add_argument("--hp-stream", action="store_true",
+                    help="run the step on a high-priority stream (experiment: with --prefetch the map construction of the "
+                         "next step, on a default-priority stream, then only fills SMs the step leaves idle)")
     ap.add_argument("--prefetch", action="store_true",
                     help="build the coordinate maps one step ahead on a side stream (Model.prefetch_coordinates); measured "
                          "slower than building them inside the step: the persistent conv kernels leave the side stream no SMs")
@@ -437,6 +440,8 @@ def main():
 
     scenes = balanced_scenes(args.scenes, 10 + rank, args.scale, world, dev)
     rng = np.random.default_rng(rank)
+    if args.hp_stream:
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
     model, opt, cfg = build_model(dev, multigpu=world > 1, grad_sync=args.grad_sync,
                                   trunk_executor=not args.no_trunk_executor, overlap_wgrad=not args.no_wgrad_overlap)
     if world > 1 and not args.sync_bn:
@@ -466,16 +471,23 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        staged = model.stage_batch(batches[0]) if read_loss else None      # (inside the timed region, like every copy)
         for i in range(steps):
             src = batches[i % len(batches)]
             cm = src.pop("_coordinate_manager", None)
             b = src
-            if read_loss:        # end to end: H2D of this step's inputs from pinned memory, D2H of the loss
-                b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in src.items()}
+            if read_loss:
+                # end to end: H2D of this step's inputs from pinned memory, D2H of the loss. The copy of step i + 1 is
+                # issued on a copy stream right after step i has been enqueued (Model.stage_batch - what a prefetching
+                # data loader does), so all `steps` transfers lie inside the region and all but the first run under
+                # the previous step's kernels.
+                b = staged
             if cm is not None:
                 b = dict(b)
                 b["_coordinate_manager"] = cm
             loss = train_step(model, opt, b)
+            if read_loss and i + 1 < steps:
+                staged = model.stage_batch(batches[(i + 1) % len(batches)])
             if args.prefetch:
                 model.prefetch_coordinates(batches[(i + 1) % len(batches)])
             if read_loss:

@@ -79,7 +79,32 @@ class Model:
         batch["_coordinate_manager"] = cm
         return batch
 
+    def stage_batch(self, batch):
+        """Optional: copy the tensors of a host batch (pinned memory) to the device on a copy stream NOW - typically
+        right after the previous step was enqueued, so that the transfer (59 MB for 8 ScanNet scenes) runs under that
+        step's kernels instead of in front of this one's. Returns the device batch; compute_loss_detection /
+        get_prediction wait for the copy before they touch it."""
+        dev = torch.device(self.device)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self._copy_stream):
+            out = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        out["_staged"] = done
+        return out
+
+    def _wait_staged(self, batch):
+        done = batch.pop("_staged", None) if isinstance(batch, dict) else None
+        if done is not None:
+            main = torch.cuda.current_stream(torch.device(self.device))
+            main.wait_event(done)
+            for v in batch.values():        # allocated under the copy stream, used on this one
+                if torch.is_tensor(v) and v.is_cuda:
+                    v.record_stream(main)
+
     def _input_tensor(self, batch):
+        self._wait_staged(batch)
         cm = batch.pop("_coordinate_manager", None) if isinstance(batch, dict) else None
         if cm is not None:
             return ME.SparseTensor(batch["vox_features"].to(self.device), coordinate_manager=cm)
@@ -168,6 +193,7 @@ class Model:
 
     # ---------------------------------------------------------------------------------------------
     def get_prediction(self, batch, with_grad=False, to_cpu=True, min_size=True):
+        self._wait_staged(batch)
         return self.net.get_prediction(batch, with_grad=with_grad, to_cpu=to_cpu, min_size=min_size)
 
     def pred2mask(self, batch, pred, mode="eval"):
