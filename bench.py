@@ -402,6 +402,7 @@ def main():
                     help="flat: one all-reduce of the flat gradient buffer after backward (box2mask_b200/grad_sync.py); "
                          "ddp: torch DistributedDataParallel buckets overlapped with backward")
     ap.add_argument("--regions", type=int, default=3, help="timed regions of --steps steps each; the median is reported")
+    ap.add_argument("--flush-every", type=int, default=0, help="commands per b2m_run_commands call (ops.LaunchList.FLUSH_EVERY)")
     ap.add_argument("--hp-stream", action="store_true",
                     help="run the step on a high-priority stream (experiment: with --prefetch the map construction of the "
                          "next step, on a default-priority stream, then only fills SMs the step leaves idle)")
@@ -440,6 +441,8 @@ def main():
 
     scenes = balanced_scenes(args.scenes, 10 + rank, args.scale, world, dev)
     rng = np.random.default_rng(rank)
+    if args.flush_every:
+        ops.LaunchList.FLUSH_EVERY = args.flush_every
     if args.hp_stream:
         torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
     model, opt, cfg = build_model(dev, multigpu=world > 1, grad_sync=args.grad_sync,
