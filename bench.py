@@ -40,10 +40,10 @@ def peaks():
 
 def conv_traffic():
     """(DRAM bytes (read + write) per convolution launch, source file): averaged over the conv launches of one training
-    step, from the newest committed ncu capture (profiles/*conv_dram*.json, written by tools/ncu_conv_traffic.py). It is
+    step, from the latest committed ncu capture by name (profiles/*conv_dram*.json, written by tools/ncu_conv_traffic.py). It is
     NOT measured in this run (ncu cannot run inside a timed benchmark), so the line names the file it came from."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*conv_dram*.json")), key=os.path.getmtime)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*conv_dram*.json")), key=os.path.basename)   # r1* < r2_* < r2f_*
     if not files:
         return None, None
     try:

@@ -62,6 +62,12 @@ SIGNATURES = {
     "b2m_mask_nms_workspace_bytes": (c_size_t, [c_int64]),
     "b2m_mask_nms": (c_int32, [_P, c_int64, c_int64, c_float, _P, _P, _P, c_size_t, _P]),
     "b2m_unpack_masks": (c_int32, [_P, c_int64, c_int64, c_int64, _P, _P]),
+    "b2m_peer_buffer_bytes": (c_size_t, []),
+    "b2m_peer_max_doubles": (c_int32, []),
+    "b2m_peer_buffer_create": (c_int32, [_P, _P]),
+    "b2m_peer_buffer_open": (c_int32, [_P, _P]),
+    "b2m_peer_buffer_close": (c_int32, [_P, c_int32]),
+    "b2m_peer_allreduce_f64": (c_int32, [_P, c_int32, c_double, c_int32, _P, _P, c_int32, c_int32, ctypes.c_uint64, _P, _P]),
     "b2m_copy_columns": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int32, _P]),
     "b2m_run_commands": (c_int32, [_P, c_int64, _P, _P, _P]),
     "b2m_point_box_occupancy": (c_int32, [_P, c_int64, _P, _P, _P, c_int32, _P, _P, _P, _P]),

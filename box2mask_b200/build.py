@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb2m.so")
-SOURCES = ["coords.cu", "conv.cu", "norm.cu", "pool.cu", "nms.cu", "voxel.cu", "assoc.cu", "runlist.cu"]
+SOURCES = ["coords.cu", "conv.cu", "norm.cu", "pool.cu", "nms.cu", "voxel.cu", "assoc.cu", "runlist.cu", "peer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

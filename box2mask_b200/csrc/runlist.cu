@@ -120,6 +120,10 @@ extern "C" int b2m_run_commands(const b2m_command_t* cmds, int64_t n, b2m_stream
         rc = (e && cudaStreamWaitEvent((cudaStream_t)st, e, 0) == cudaSuccess) ? B2M_OK : B2M_ERR_CUDA_LAUNCH;
         break;
       }
+      case B2M_CMD_PEER_ALLREDUCE:
+        rc = b2m_peer_allreduce_f64((const double*)P(a[0]), (int32_t)a[1], c.f[0], (int32_t)a[2], (double*)P(a[3]),
+                                    (void* const*)P(a[4]), (int32_t)a[5], (int32_t)a[6], (uint64_t)a[7], (int32_t*)P(a[8]), st);
+        break;
       default:
         rc = B2M_ERR_INVALID_ARGUMENT;
     }

@@ -97,9 +97,8 @@ class BatchNormFn(torch.autograd.Function):
             def hook(red):
                 # only dx needs the global reduction; bn.weight / bn.bias gradients stay local like torch's
                 # SyncBatchNorm (the gradient all-reduce then averages them with every other parameter)
-                tot = red.clone()
-                torch.distributed.all_reduce(tot, group=ctx.sync_group)
-                return tot
+                from .peer import allreduce_sum
+                return allreduce_sum(red, ctx.sync_group)
         dx, dres, dgamma, dbeta = ops.bn_backward(x, out, dout.contiguous(), save_mean, save_invstd, gamma.detach(),
                                                   ctx.relu, ctx.training, ctx.has_res, ctx.n_stat, hook, count)
         return dx, None, dgamma, dbeta, None, None, None, None, None, dres, None, None
@@ -111,6 +110,9 @@ def sync_bn_stats(sums, n, group):
     element and stays on the device)."""
     packed = torch.empty(sums.numel() + 1, dtype=sums.dtype, device=sums.device)
     packed[:-1] = sums
+    if sums.is_cuda and sums.dtype == torch.float64:
+        from .peer import allreduce_sum
+        return allreduce_sum(packed, group, tail=float(n))      # NVLink peer exchange when the group sits on one node
     packed[-1] = float(n)
     torch.distributed.all_reduce(packed, group=group)
     return packed
@@ -142,7 +144,11 @@ class SyncBatchNormFp32Fn(torch.autograd.Function):
         xhat, gamma, invstd = ctx.saved_tensors
         red = torch.cat([dout.sum(0), (dout * xhat).sum(0)]).double()
         dgamma, dbeta = red[xhat.shape[1]:].to(dout.dtype), red[:xhat.shape[1]].to(dout.dtype)
-        torch.distributed.all_reduce(red, group=ctx.group)
+        if red.is_cuda:
+            from .peer import allreduce_sum
+            red = allreduce_sum(red.contiguous(), ctx.group)
+        else:
+            torch.distributed.all_reduce(red, group=ctx.group)
         c = xhat.shape[1]
         sg, sgx = (red[:c] / ctx.n).to(dout.dtype), (red[c:] / ctx.n).to(dout.dtype)
         dx = gamma * invstd * (dout - sg - xhat * sgx)

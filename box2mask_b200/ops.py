@@ -70,7 +70,7 @@ class LaunchList:
     _S = struct.Struct("<ii28q2d")
     _PAD = (0,) * 28
     OP_CONV_FORWARD, OP_CONV_WGRAD, OP_BN_FORWARD, OP_BN_BACKWARD_REDUCE, OP_BN_BACKWARD_APPLY = 1, 2, 3, 4, 5
-    OP_COPY_COLUMNS, OP_RECORD, OP_WAIT = 6, 7, 8
+    OP_COPY_COLUMNS, OP_RECORD, OP_WAIT, OP_PEER_ALLREDUCE = 6, 7, 8, 9
 
     FLUSH_EVERY = 8      # commands per b2m_run_commands call: the GPU starts on a pass while the host still records it
 
@@ -629,7 +629,8 @@ def bn_backward(x, out, dout, save_mean, save_invstd, gamma, relu, training, wan
                 red.data_ptr(), _p(relu_mask)))
         red_local = None
         if reduce_hook is not None:
-            ll.flush()                      # the hook is a collective on the reduction
+            if not getattr(reduce_hook, "deferred", False):
+                ll.flush()                  # the hook is an eager collective on the reduction
             red_local = red
             red = reduce_hook(red)
         dx = torch.empty_like(x)

@@ -23,7 +23,7 @@ and is what the reference's own SelectionNet class runs on; tests compare the tw
 """
 import torch
 
-from . import ops
+from . import ops, peer
 from .me.nn import _dgrad_mode, _round16
 
 
@@ -344,11 +344,9 @@ class TrunkExecutor:
             y = ops.conv_forward(x, km_f, _packed(conv)[0], conv.kernel_volume, n_out, c_out, colsum[:2 * c_out])
             n_stat, count = n_out, None
             if group is not None:
-                if ll is not None:
-                    ll.flush()                  # the statistics are all-reduced by torch: the convolution must be enqueued
-                sums = colsum.clone()
-                sums[-1] = float(n_out)
-                torch.distributed.all_reduce(sums, group=group)
+                # global (sum, sum of squares, row count): one exchange over NVLink peer memory (a launch-list command
+                # like the kernels around it), or a torch.distributed all-reduce where the group does not qualify
+                sums = peer.allreduce_sum(colsum, group, tail=float(n_out))
                 count, n_stat = sums[-1:], 0
             else:
                 sums = colsum
@@ -459,9 +457,8 @@ class TrunkExecutor:
             hook = None
             if group is not None:
                 def hook(red, group=group):
-                    tot = red.clone()
-                    torch.distributed.all_reduce(tot, group=group)
-                    return tot
+                    return peer.allreduce_sum(red, group)
+                hook.deferred = True            # flushes the launch list itself if it has to fall back to a collective
             # the ReLU gate comes from the 1-bit mask the forward pass wrote, not from re-reading the unit's output
             dx_bn, dres, _, _ = ops.bn_backward(y, None, g_out, mean, invstd, b.weight.detach(), st.relu, True,
                                                 st.res is not None, n_stat, hook, count,

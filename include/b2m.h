@@ -370,6 +370,27 @@ int b2m_segment_association(const int32_t* num, const int32_t* first, const int3
                             b2m_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * SyncBatchNorm statistics over NVLink peer memory      reference: MinkowskiSyncBatchNorm under cfg.multigpu,
+ * models/model.py:25 (per layer one all-reduce of the batch statistics in forward and one of the gradient sums in
+ * backward). One node, one process per GPU: every rank creates an exchange buffer, hands its 64-byte CUDA-IPC handle
+ * to its peers (the host does that once, e.g. through torch.distributed) and opens theirs.
+ * b2m_peer_allreduce_f64: out[0..n) = sum over ranks of in[0..n) (added in rank order: bit-identical on all ranks), as ONE
+ * single-CTA kernel that stores this rank's vector into its slot of every peer's buffer, publishes sequence number
+ * `seq` and waits for the peers' - no library collective, no host involvement. use_tail: element n-1 of this rank's
+ * vector is `tail` instead of in[n-1] (the row count that travels with the sums). peer_buffers: DEVICE array of `world`
+ * buffer pointers (index = rank; the own buffer at index `rank`). seq: 1, 2, 3, ... identical on all ranks, consecutive
+ * calls on one stream. status (device int32): set to 1 if a peer did not arrive within ~3 s. n <= b2m_peer_max_doubles().
+ * ---------------------------------------------------------------------------------------------- */
+size_t b2m_peer_buffer_bytes(void);
+int32_t b2m_peer_max_doubles(void);
+int b2m_peer_buffer_create(void** buffer, void* ipc_handle_64_bytes);       /* synchronises the device once */
+int b2m_peer_buffer_open(const void* ipc_handle_64_bytes, void** buffer);
+int b2m_peer_buffer_close(void* buffer, int32_t own);
+int b2m_peer_allreduce_f64(const double* in, int32_t n, double tail, int32_t use_tail, double* out,
+                           void* const* peer_buffers, int32_t rank, int32_t world, uint64_t seq, int32_t* status,
+                           b2m_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Launch lists: a whole pass of the U-Net trunk (models/detection_net.py:235-337 - ~250 modules, ~540 calls per training
  * step when bound call by call) in ONE call. A command carries the arguments of one of the entry points above in their
  * declared order (pointers and integers in a[], floating-point arguments in f[]), without the stream; `stream` selects
@@ -385,6 +406,7 @@ int b2m_segment_association(const int32_t* num, const int32_t* first, const int3
 #define B2M_CMD_COPY_COLUMNS 6       /* b2m_copy_columns: a[0..5] */
 #define B2M_CMD_RECORD 7             /* record event slot a[0] on the selected stream */
 #define B2M_CMD_WAIT 8               /* the selected stream waits for event slot a[0] */
+#define B2M_CMD_PEER_ALLREDUCE 9     /* b2m_peer_allreduce_f64: a[0] = in, a[1] = n, f[0] = tail, a[2] = use_tail, a[3..8] = out..status */
 typedef struct b2m_command {
   int32_t op;
   int32_t stream;

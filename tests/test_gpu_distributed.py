@@ -72,3 +72,68 @@ def test_sync_batchnorm_two_gpus():
     out = mp.Manager().dict()
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert dict(out) == {0: 1, 1: 1}
+
+
+def _peer_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda:%d" % rank))
+    try:
+        from box2mask_b200 import ops
+        from box2mask_b200.peer import PeerExchange, allreduce_sum
+        dev = torch.device("cuda:%d" % rank)
+        px = PeerExchange.for_group(dist.group.WORLD, dev)
+        assert px is not None, "ranks of one node must get the NVLink peer exchange"
+        g = torch.Generator().manual_seed(100 + rank)
+        # 300 exchanges of different lengths back to back (the two slot sets alternate, a fast rank runs ahead), every
+        # one compared with the NCCL all-reduce of the same vector; with and without the row-count tail
+        sizes = [1, 2, 129, 513, 1025, 2048]
+        outs, refs = [], []
+        for i in range(300):
+            n = sizes[i % len(sizes)]
+            v = torch.randn(n, generator=g, dtype=torch.float64).to(dev)
+            tail = float(1000 * rank + i) if i % 3 == 0 else None
+            ref = v.clone()
+            if tail is not None:
+                ref[-1] = tail
+            dist.all_reduce(ref)
+            outs.append(px.allreduce(v, tail))
+            refs.append(ref)
+            if rank == 1 and i % 50 == 0:
+                torch.cuda._sleep(20_000_000)          # let the other rank run ahead
+        for o, r in zip(outs, refs):
+            assert torch.allclose(o, r, rtol=1e-14, atol=1e-14), float((o - r).abs().max())
+        # the sums are bit-identical on all ranks (slots added in rank order)
+        mine = torch.cat(outs)
+        other = mine.clone()
+        dist.broadcast(other, src=0)
+        assert torch.equal(mine, other)
+        # as launch-list commands, interleaved with the producing kernels of a pass
+        x = (torch.randn(4096, 64, generator=g) + rank).to(dev).to(torch.bfloat16)
+        sums = ops.colstats(x)
+        packed = torch.cat([sums, torch.zeros(1, dtype=torch.float64, device=dev)])
+        ll = ops.LaunchList.begin(dev)
+        tot = allreduce_sum(packed, dist.group.WORLD, tail=4096.0)
+        ll.end()
+        ref = packed.clone()
+        ref[-1] = 4096.0
+        dist.all_reduce(ref)
+        assert torch.allclose(tot, ref, rtol=1e-14, atol=1e-12) and float(tot[-1]) == 4096.0 * world
+        # vectors longer than a slot fall back to the library collective
+        big = torch.ones(5000, dtype=torch.float64, device=dev)
+        assert float(allreduce_sum(big, dist.group.WORLD).sum()) == 5000.0 * world
+        px.check()
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_two_gpus():
+    """b2m_peer_allreduce_f64 (SyncBatchNorm statistics over NVLink peer memory) against NCCL."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    out = mp.Manager().dict()
+    mp.spawn(_peer_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}
