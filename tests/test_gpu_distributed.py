@@ -134,6 +134,7 @@ def test_peer_exchange_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)          # every GPU of the box: 2 under `gpurun --gpus 2`, 8 on a full node
     out = mp.Manager().dict()
-    mp.spawn(_peer_worker, args=(2, _free_port(), out), nprocs=2, join=True)
-    assert dict(out) == {0: 1, 1: 1}
+    mp.spawn(_peer_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {r: 1 for r in range(world)}
