@@ -402,6 +402,7 @@ def main():
                     help="flat: one all-reduce of the flat gradient buffer after backward (box2mask_b200/grad_sync.py); "
                          "ddp: torch DistributedDataParallel buckets overlapped with backward")
     ap.add_argument("--regions", type=int, default=3, help="timed regions of --steps steps each; the median is reported")
+    ap.add_argument("--decode-threads", type=int, default=0, help="host threads of the box-vote decode (decode.DECODE_THREADS)")
     ap.add_argument("--flush-every", type=int, default=0, help="commands per b2m_run_commands call (ops.LaunchList.FLUSH_EVERY)")
     ap.add_argument("--hp-stream", action="store_true",
                     help="run the step on a high-priority stream (experiment: with --prefetch the map construction of the "
@@ -418,6 +419,9 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.decode_threads:
+        from box2mask_b200 import decode as _decode
+        _decode.DECODE_THREADS = args.decode_threads
     if args.workload == "eval":
         return run_eval(args)
     args.warmup = max(args.warmup, 3)
@@ -443,6 +447,7 @@ def main():
     rng = np.random.default_rng(rank)
     if args.flush_every:
         ops.LaunchList.FLUSH_EVERY = args.flush_every
+
     if args.hp_stream:
         torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
     model, opt, cfg = build_model(dev, multigpu=world > 1, grad_sync=args.grad_sync,

@@ -10,6 +10,16 @@ import torch
 
 from . import ops
 
+DECODE_THREADS = 4      # host threads (one CUDA stream each) that decode the scenes of a batch side by side
+_DECODE_STREAMS = {}
+
+
+def _decode_streams(dev, n):
+    pool = _DECODE_STREAMS.setdefault(dev, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
+
 
 def NMS_clustering(boxes, cluster_th=0.5, get_heatmaps=True):
     """boxes f32[M,7] = (score, min, max). Returns (representatives i64[K], clusters: list of i64 tensors in
@@ -70,8 +80,8 @@ def detection2mask(net, batch, pred, cfg, mode="eval", score_filtering=True, clu
         pred_sem = class_ids[torch.argmax(P[cfg.mlp_semantics], 1)]
         n_lab = int(class_ids.max().item()) + 1
     batch_ids = batch["batch_ids"].to(dev)
-    results = {}
-    for scene_idx, scene in enumerate(batch["scene"]):
+
+    def decode_scene(scene_idx):
         scene_mask = batch_ids == scene_idx
         seg2vox = batch["seg2vox"][scene_idx].to(dev).long().contiguous()
         n_vox = seg2vox.shape[0]
@@ -89,9 +99,8 @@ def detection2mask(net, batch, pred, cfg, mode="eval", score_filtering=True, clu
         scene_fg = torch.as_tensor(scene_fg, device=dev).bool()
         scene_bbs = pred_bbs[scene_mask][scene_fg].contiguous()
         if scene_bbs.shape[0] == 0:
-            results[scene["name"]] = {"conf": torch.zeros(0), "label_id": np.zeros(0, dtype="int32"),
-                                      "mask": torch.zeros((0, n_vox), dtype=torch.bool)}
-            continue
+            return {"conf": torch.zeros(0), "label_id": np.zeros(0, dtype="int32"),
+                    "mask": torch.zeros((0, n_vox), dtype=torch.bool)}
         reps, cluster_of, heat = ops.aabb_nms(scene_bbs, cluster_th)
         scores = scene_bbs[reps][:, 0]
         if score_filtering:
@@ -115,5 +124,37 @@ def detection2mask(net, batch, pred, cfg, mode="eval", score_filtering=True, clu
             res["cluster_representatives"] = reps.cpu()
             res["bbs"] = scene_bbs[reps].cpu()
             res["pred_fg"] = scene_fg.cpu()
-        results[scene["name"]] = res
-    return results
+        return res
+
+    # The scenes of a batch are independent and each one's chain is a dozen small kernels around half a dozen reads of
+    # a size from the device (boolean selections, the number of clusters): decoded one after the other the GPU mostly
+    # waits for the host's round trips. With several scenes each one is decoded by its own host thread on its own
+    # stream, so the round trips of one scene overlap the kernels of the others. Results are identical.
+    names = [scene["name"] for scene in batch["scene"]]
+    workers = min(len(names), DECODE_THREADS) if dev.type == "cuda" else 1
+    if workers <= 1:
+        return {name: decode_scene(i) for i, name in enumerate(names)}
+    main = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(main)              # the predictions above were produced on the caller's stream
+    streams = _decode_streams(dev, workers)
+
+    def work(w):
+        out = []
+        with torch.cuda.device(dev), torch.cuda.stream(streams[w]):
+            streams[w].wait_event(ready)
+            for i in range(w, len(names), workers):
+                out.append((i, decode_scene(i)))
+            done = torch.cuda.Event()
+            done.record(streams[w])
+        return out, done
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        parts = list(pool.map(work, range(workers)))
+    results = [None] * len(names)
+    for out, done in parts:
+        main.wait_event(done)       # the scene streams read tensors of the caller's stream: order their release after that
+        for i, res in out:
+            results[i] = res
+    return dict(zip(names, results))
