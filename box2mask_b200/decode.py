@@ -79,10 +79,22 @@ def detection2mask(net, batch, pred, cfg, mode="eval", score_filtering=True, clu
         class_ids = torch.as_tensor(net.semantic_valid_class_ids, device=dev).long()
         pred_sem = class_ids[torch.argmax(P[cfg.mlp_semantics], 1)]
         n_lab = int(class_ids.max().item()) + 1
+    # rows of each scene: the collate function concatenates the scenes in order (models/dataloader.py:946-995), so a
+    # scene is a contiguous range of superpoints and a slice replaces a boolean selection (each of which reads its size
+    # back from the device); any other batch order falls back to the selections
+    bid_src = batch["batch_ids"]
+    n_scenes = len(batch["scene"])
+    ranges = None
+    if bid_src.numel() > 0 and bool((bid_src[1:] >= bid_src[:-1]).all()):
+        counts = torch.bincount(bid_src.long().reshape(-1), minlength=n_scenes).tolist()
+        ranges, a = [], 0
+        for c in counts[:n_scenes]:
+            ranges.append(slice(a, a + c))
+            a += c
     batch_ids = batch["batch_ids"].to(dev)
 
     def decode_scene(scene_idx):
-        scene_mask = batch_ids == scene_idx
+        scene_mask = ranges[scene_idx] if ranges is not None else batch_ids == scene_idx
         seg2vox = batch["seg2vox"][scene_idx].to(dev).long().contiguous()
         n_vox = seg2vox.shape[0]
         if voxel_outputs:
@@ -106,8 +118,8 @@ def detection2mask(net, batch, pred, cfg, mode="eval", score_filtering=True, clu
         if score_filtering:
             sel = scores > score_th
             heat, scores, reps = heat[sel].contiguous(), scores[sel], reps[sel]
-        fg_rank = torch.full((scene_fg.shape[0],), -1, dtype=torch.int32, device=dev)
-        fg_rank[scene_fg] = torch.arange(int(scene_fg.sum()), dtype=torch.int32, device=dev)
+        # rank of every foreground superpoint among the foreground ones (-1 for the others), without a size read-back
+        fg_rank = torch.where(scene_fg, torch.cumsum(scene_fg, 0) - 1, -1).to(torch.int32)
         packed = ops.heatmap_project(heat, fg_rank, seg2vox, mask_bin_th)
         if not voxel_outputs:
             keep = ops.mask_nms(packed, mask_nms_th)
