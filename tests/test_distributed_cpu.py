@@ -33,6 +33,15 @@ def _worker(rank, world, port, out):
         packed = Fn.sync_bn_stats(sums, mine.shape[0], dist.group.WORLD)    # [2C sums | global row count], on the device
         assert packed.shape == (17,) and float(packed[-1]) == 50
         assert torch.allclose(packed[:-1], torch.cat([full.sum(0), (full * full).sum(0)]))
+        # 1b. the transport choice behind it (box2mask_b200/peer.py): CPU tensors / gloo groups never get the NVLink peer
+        # exchange, allreduce_sum falls back to the library collective with the same semantics (tail = the row count
+        # that replaces the vector's last element on every rank)
+        from box2mask_b200.peer import PeerExchange, allreduce_sum
+        assert PeerExchange.for_group(dist.group.WORLD, "cpu") is None
+        vec = torch.arange(5, dtype=torch.float64) * (rank + 1)
+        tot = allreduce_sum(vec, dist.group.WORLD, tail=10.0 + rank)
+        assert torch.equal(tot, torch.tensor([0.0, 3.0, 6.0, 9.0, 21.0], dtype=torch.float64)) and float(vec[-1]) == 4.0 * (rank + 1)
+        assert torch.equal(allreduce_sum(vec, dist.group.WORLD), torch.arange(5, dtype=torch.float64) * 3)
         # 2. an MLP head (reference naming) under DDP + SyncBN == the same head on the concatenated batch
         def head():
             torch.manual_seed(1)
