@@ -150,10 +150,11 @@ def detection2mask(net, batch, pred, cfg, mode="eval", score_filtering=True, clu
     ready = torch.cuda.Event()
     ready.record(main)              # the predictions above were produced on the caller's stream
     streams = _decode_streams(dev, workers)
+    grad_mode = torch.is_grad_enabled()      # thread-local in torch: the workers take over the caller's mode
 
     def work(w):
         out = []
-        with torch.cuda.device(dev), torch.cuda.stream(streams[w]):
+        with torch.set_grad_enabled(grad_mode), torch.cuda.device(dev), torch.cuda.stream(streams[w]):
             streams[w].wait_event(ready)
             for i in range(w, len(names), workers):
                 out.append((i, decode_scene(i)))
